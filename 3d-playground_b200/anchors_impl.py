@@ -1,0 +1,59 @@
+"""Anchor generation with the layout the hot path consumes (anchors.py:6-129, identical in both retinanet copies).
+
+Order: pyramid level 3..7 -> cell row-major (y outer, x inner) -> 9 shapes (ratio-major: ratios {0.5,1,2} x scales
+{2^0, 2^(1/3), 2^(2/3)}).  Values are formed in float64 and cast to float32 exactly as the reference's numpy code does,
+but once per (image shape, device) instead of on every forward (the reference rebuilds them in numpy and copies
+6.2 MB host->device per call at 1080p).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+_PYRAMID_LEVELS = (3, 4, 5, 6, 7)
+_RATIOS = np.array([0.5, 1, 2])
+_SCALES = np.array([2 ** 0, 2 ** (1.0 / 3.0), 2 ** (2.0 / 3.0)])
+
+
+def _level_shapes(size, ratios, scales):
+    """[len(ratios)*len(scales), 4] float64 boxes centred on the origin, ratio-major."""
+    side = size * np.tile(scales, len(ratios))              # square side before the ratio correction
+    ratio = np.repeat(ratios, len(scales))
+    w = np.sqrt((side * side) / ratio)
+    h = w * ratio
+    return np.stack((0.0 - w * 0.5, 0.0 - h * 0.5, w - w * 0.5, h - h * 0.5), axis=1)
+
+
+def anchors_for_image(height, width, pyramid_levels=_PYRAMID_LEVELS, ratios=_RATIOS, scales=_SCALES):
+    """float32 [A,4] anchors for an image of height x width."""
+    out = []
+    for lvl in pyramid_levels:
+        stride, size = 2 ** lvl, 2 ** (lvl + 2)
+        rows, cols = (height + stride - 1) // stride, (width + stride - 1) // stride
+        cx = (np.arange(cols) + 0.5) * stride
+        cy = (np.arange(rows) + 0.5) * stride
+        gx, gy = np.meshgrid(cx, cy)                            # [rows, cols], x fastest
+        centres = np.stack((gx.ravel(), gy.ravel(), gx.ravel(), gy.ravel()), axis=1)     # [K,4]
+        shapes = _level_shapes(size, ratios, scales)            # [9,4]
+        out.append((centres[:, None, :] + shapes[None, :, :]).reshape(-1, 4))
+    return np.concatenate(out, axis=0).astype(np.float32)
+
+
+class Anchors(nn.Module):
+    """forward(image[B,C,H,W]) -> float32 [1,A,4] on the image's device (cached per shape and device)."""
+
+    def __init__(self, pyramid_levels=None, strides=None, sizes=None, ratios=None, scales=None):
+        super().__init__()
+        self.pyramid_levels = list(_PYRAMID_LEVELS) if pyramid_levels is None else pyramid_levels
+        self.strides = [2 ** x for x in self.pyramid_levels] if strides is None else strides
+        self.sizes = [2 ** (x + 2) for x in self.pyramid_levels] if sizes is None else sizes
+        self.ratios = _RATIOS if ratios is None else ratios
+        self.scales = _SCALES if scales is None else scales
+        self._cache = {}
+
+    def forward(self, image):
+        h, w = int(image.shape[2]), int(image.shape[3])
+        key = (h, w, str(image.device))
+        if key not in self._cache:
+            a = anchors_for_image(h, w, tuple(self.pyramid_levels), np.asarray(self.ratios), np.asarray(self.scales))
+            self._cache[key] = torch.from_numpy(a).unsqueeze(0).to(image.device)
+        return self._cache[key]

@@ -1,0 +1,514 @@
+// focal_loss.cu — a2..a6 fused: FocalLoss.forward / backward of both retinanet copies in one pass over the anchors.
+//
+//   3D: pytorch_retinanet_detector_directional/retinanet/losses.py:27-362
+//   2D: retinanet/losses.py:27-177
+//
+// Forward, one launch: grid (anchor tiles, image groups).  A CTA loads its 256 anchors once, then for each image of
+// its group: culls/stages the GT boxes (assign_tile.cuh), finds IoU max/argmax per anchor, classifies the anchor
+// (negative / ignore / positive), evaluates the C focal terms from the streamed classification row, evaluates the
+// corner smooth-L1 and the three direction-cosine terms for the (rare) positives, block-reduces in FP64 and stores
+// one partial per (image, tile).  The last CTA to finish an image (atomic ticket) reduces that image's partials in a
+// fixed order, and the last image finalises the batch means - so the result is deterministic and needs no second
+// launch and no host synchronisation.
+#include "assign_tile.cuh"
+
+namespace g3d {
+
+constexpr int kImgPerCta = 4;  // images processed per CTA for one anchor tile (anchors/bbox loaded once)
+
+// clamp bounds of losses.py:56: torch.clamp(classification, 1e-4, 1.0 - 1e-4) - python doubles cast to f32
+#define G3D_PMIN ((float)1e-4)
+#define G3D_PMAX ((float)(1.0 - 1e-4))
+#define G3D_BETA ((float)(1.0 / 9.0))        // smooth-L1 switch point (losses.py:346)
+#define G3D_HALF_BETA ((float)(0.5 / 9.0))   // losses.py:348
+
+struct FocalArgs {
+    const float* cls;
+    const float* reg;
+    const float4* anchors;
+    const float* ann;
+    const float4* gt_box;
+    const int32_t* gt_row;
+    const int32_t* gt_count;
+    double* partials;    // [B][T][4] : cls_sum, num_pos, reg_sum, vp_sum
+    int32_t* counters;   // [B+1], zero on entry
+    float* losses;       // [4] : cls, reg, vp, number of non-empty images
+    float* per_image;    // [B][4]
+    int32_t* assign;     // [B][A] or null
+    int B, A, C, R, Gmax, W, T;
+};
+
+// one focal term (losses.py:138-150): alpha_t * (1 - p_t)^2 * bce, target t in {0,1}
+__device__ __forceinline__ float focal_term(float p_raw, bool t) {
+    const float p = fminf(fmaxf(p_raw, G3D_PMIN), G3D_PMAX);
+    const float u = 1.0f - p;
+    const float fw = t ? u : p;
+    const float x = t ? p : u;
+    const float w = (t ? 0.25f : 0.75f) * (fw * fw);
+    return w * (-logf(x));
+}
+
+// d(focal term)/dp, zero outside the clamp range (torch.clamp backward passes min <= x <= max)
+__device__ __forceinline__ float focal_term_grad(float p_raw, bool t) {
+    if (!(p_raw >= G3D_PMIN && p_raw <= G3D_PMAX)) return 0.0f;
+    const float p = p_raw, u = 1.0f - p;
+    if (t) return 0.5f * u * logf(p) - 0.25f * (u * u) / p;
+    return -1.5f * p * logf(u) + 0.75f * (p * p) / u;
+}
+
+__device__ __forceinline__ float smooth_l1(float d) {
+    return (d <= G3D_BETA) ? 4.5f * (d * d) : d - G3D_HALF_BETA;
+}
+
+__device__ __forceinline__ float cos_loss(float rx, float ry, float tx, float ty) {
+    const float rn = sqrtf(rx * rx + ry * ry), tn = sqrtf(tx * tx + ty * ty);
+    return 1.0f - (rx * tx + ry * ty) / (rn * tn);
+}
+// gradient of cos_loss w.r.t. (rx, ry)
+__device__ __forceinline__ void cos_loss_grad(float rx, float ry, float tx, float ty, float& gx, float& gy) {
+    const float rn = sqrtf(rx * rx + ry * ry), tn = sqrtf(tx * tx + ty * ty);
+    const float dot = rx * tx + ry * ty, den = rn * tn;
+    // d(-dot/den)/dr = -(t/den) + dot * (r/rn) * tn / den^2
+    const float k = dot / (den * den) * tn / rn;
+    gx = -tx / den + k * rx;
+    gy = -ty / den + k * ry;
+}
+
+// corner sign table of losses.py:311-327 / utils.py:114-130: corner k = c + sl*L + sw*W + sh*H
+__device__ __forceinline__ float sgn_l(int k) { return (k & 2) ? 1.0f : -1.0f; }
+__device__ __forceinline__ float sgn_w(int k) { return (k & 1) ? 1.0f : -1.0f; }
+__device__ __forceinline__ float sgn_h(int k) { return (k & 4) ? -1.0f : 1.0f; }
+
+// the three GT direction vectors (losses.py:222-223, 252-253, 281-282) from the raw 16 corner coordinates
+__device__ __forceinline__ void gt_directions(const float* t, float* tv /*6*/) {
+    tv[0] = ((t[4] + t[6] + t[12] + t[14]) - (t[0] + t[2] + t[8] + t[10])) / 4.0f;
+    tv[1] = ((t[5] + t[7] + t[13] + t[15]) - (t[1] + t[3] + t[9] + t[11])) / 4.0f;
+    tv[2] = ((t[2] + t[6] + t[10] + t[14]) - (t[0] + t[4] + t[8] + t[12])) / 4.0f;
+    tv[3] = ((t[3] + t[7] + t[11] + t[15]) - (t[1] + t[5] + t[9] + t[13])) / 4.0f;
+    tv[4] = ((t[0] + t[2] + t[4] + t[6]) - (t[8] + t[10] + t[12] + t[14])) / 4.0f;
+    tv[5] = ((t[1] + t[3] + t[5] + t[7]) - (t[9] + t[11] + t[13] + t[15])) / 4.0f;
+}
+
+__device__ __forceinline__ void pred_corners(const float* r, float* p /*20*/) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        p[2 * k] = ((r[0] + sgn_l(k) * r[2]) + sgn_w(k) * r[4]) + sgn_h(k) * r[6];
+        p[2 * k + 1] = ((r[1] + sgn_l(k) * r[3]) + sgn_w(k) * r[5]) + sgn_h(k) * r[7];
+    }
+    p[16] = r[8]; p[17] = r[9]; p[18] = r[10]; p[19] = r[11];
+}
+
+// 3D positive anchor: sum of the 20 smooth-L1 terms and the mean of the three cosine losses (losses.py:156-350)
+__device__ __forceinline__ void positive_terms_3d(const float* __restrict__ rrow, const float* __restrict__ grow,
+                                                  const float4& an, float& reg_sum, float& vp_term) {
+    float r[12], t[20], p[20], tv[6];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) r[i] = rrow[i];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) t[i] = grow[i];
+    gt_directions(t, tv);
+    vp_term = (cos_loss(r[2], r[3], tv[0], tv[1]) + cos_loss(r[4], r[5], tv[2], tv[3]) +
+               cos_loss(r[6], r[7], tv[4], tv[5])) / 3.0f;
+    pred_corners(r, p);
+    const float aw = an.z - an.x, ah = an.w - an.y;
+    const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) {
+        const float tn = (i & 1) ? (t[i] - acy) / ah : (t[i] - acx) / aw;
+        float d = fabsf(tn - p[i]);
+        if (i >= 8 && i < 16) d *= 0.5f;  // top_weighting, losses.py:343
+        s += smooth_l1(d);
+    }
+    reg_sum = s;
+}
+
+// 2D targets (retinanet/losses.py:137-157)
+__device__ __forceinline__ void targets_2d(const float* __restrict__ grow, const float4& an, float* t /*4*/) {
+    const float aw = an.z - an.x, ah = an.w - an.y;
+    const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
+    float gw = grow[2] - grow[0], gh = grow[3] - grow[1];
+    const float gcx = grow[0] + 0.5f * gw, gcy = grow[1] + 0.5f * gh;
+    gw = fmaxf(gw, 1.0f);
+    gh = fmaxf(gh, 1.0f);
+    t[0] = ((gcx - acx) / aw) / 0.1f;
+    t[1] = ((gcy - acy) / ah) / 0.1f;
+    t[2] = logf(gw / aw) / 0.2f;
+    t[3] = logf(gh / ah) / 0.2f;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* s) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) t += s[w];
+    __syncthreads();
+    return t;
+}
+
+template <int VARIANT, int CS>
+__global__ void __launch_bounds__(kTile) focal_fwd_kernel(const FocalArgs p) {
+    __shared__ TileSmem sm;
+    __shared__ double s_red[3][kWarps];
+    __shared__ int s_np[kWarps];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a = blockIdx.x * kTile + tid;
+    const bool valid = a < p.A;
+    float4 an = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) an = __ldg(p.anchors + a);
+    const float area_a = box_area_rn(an.x, an.y, an.z, an.w);
+    const float4 bb = tile_bbox(an, valid, sm);
+    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+    const int C = (CS > 0) ? CS : p.C;
+
+    const int b_end = min(p.B, (int)(blockIdx.y + 1) * kImgPerCta);
+    for (int b = blockIdx.y * kImgPerCta; b < b_end; ++b) {
+        const int64_t row = (int64_t)b * p.A + a;
+        // issue the classification loads first so they are in flight during the IoU search
+        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+        if (CS == 8 && valid) {
+            const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
+            c0 = ld_stream(cp);
+            c1 = ld_stream(cp + 1);
+        }
+        const int G = __ldg(p.gt_count + b);
+        float best = 0.0f;
+        int besti = 0;
+        tile_argmax(an, area_a, bb, p.gt_box + (int64_t)b * p.Gmax, G, sm, best, besti);
+        int code = G3D_ASSIGN_NEGATIVE;
+        if (G > 0) code = assign_code(best, besti, p.gt_row + (int64_t)b * p.Gmax);
+        if (!valid) code = G3D_ASSIGN_IGNORE;
+        if (p.assign && valid) p.assign[row] = code;
+
+        float cls_acc = 0.0f, reg_acc = 0.0f, vp_acc = 0.0f;
+        const float* grow = nullptr;
+        int pos_cls = -1;
+        if (code >= 0) {
+            grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
+            pos_cls = (int)(long long)grow[cls_col];
+        }
+        if (code != G3D_ASSIGN_IGNORE) {
+            if (CS == 8) {
+                const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) cls_acc += focal_term(pv[c], c == pos_cls);
+            } else {
+                const float* cp = p.cls + row * C;
+                for (int c = 0; c < C; ++c) cls_acc += focal_term(__ldg(cp + c), c == pos_cls);
+            }
+        }
+        if (code >= 0) {
+            const float* rrow = p.reg + row * p.R;
+            if (VARIANT == G3D_VARIANT_3D) {
+                positive_terms_3d(rrow, grow, an, reg_acc, vp_acc);
+            } else {
+                float t[4];
+                targets_2d(grow, an, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) reg_acc += smooth_l1(fabsf(t[i] - rrow[i]));
+            }
+        }
+        // ---- block reduction (FP64), one partial per (image, tile)
+        const int any_pos = __syncthreads_or(code >= 0);
+        const double cs = warp_sum((double)cls_acc);
+        if (lane == 0) s_red[0][warp] = cs;
+        if (any_pos) {
+            const int np = warp_sum(code >= 0 ? 1 : 0);
+            const double rs = warp_sum((double)reg_acc), vs = warp_sum((double)vp_acc);
+            if (lane == 0) { s_np[warp] = np; s_red[1][warp] = rs; s_red[2][warp] = vs; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double tc = 0.0, tr = 0.0, tv = 0.0;
+            int tn = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tc += s_red[0][w];
+            if (any_pos) {
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) { tn += s_np[w]; tr += s_red[1][w]; tv += s_red[2][w]; }
+            }
+            double* out = p.partials + ((int64_t)b * p.T + blockIdx.x) * 4;
+            __stcg(reinterpret_cast<double2*>(out), make_double2(tc, (double)tn));
+            __stcg(reinterpret_cast<double2*>(out) + 1, make_double2(tr, tv));
+            __threadfence();
+            s_last = (atomicAdd(p.counters + b, 1) == p.T - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            // last tile of image b: reduce its T partials in a fixed order
+            __threadfence();
+            double tc = 0.0, tn = 0.0, tr = 0.0, tv = 0.0;
+            const double2* src = reinterpret_cast<const double2*>(p.partials + (int64_t)b * p.T * 4);
+            for (int t = tid; t < p.T; t += kTile) {
+                const double2 u = __ldcg(src + 2 * t), v = __ldcg(src + 2 * t + 1);
+                tc += u.x; tn += u.y; tr += v.x; tv += v.y;
+            }
+            tc = block_sum(tc, s_red[0]);
+            tn = block_sum(tn, s_red[0]);
+            tr = block_sum(tr, s_red[0]);
+            tv = block_sum(tv, s_red[0]);
+            if (tid == 0) {
+                const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
+                float4 o;
+                o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
+                o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
+                o.z = tn > 0.0 ? (float)(tv / tn) : 0.0f;              // vp_loss.mean() (:304)
+                o.w = (float)tn;
+                __stcg(reinterpret_cast<float4*>(p.per_image) + b, o);
+                __threadfence();
+                s_last = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
+            }
+            __syncthreads();
+            if (s_last) {
+                // last image: batch means (losses.py:362).  vp: only images with >= 1 GT row contribute (:304,:353-358)
+                __threadfence();
+                double sc = 0.0, sr = 0.0, sv = 0.0, ne = 0.0;
+                for (int j = tid; j < p.B; j += kTile) {
+                    const float4 o = __ldcg(reinterpret_cast<const float4*>(p.per_image) + j);
+                    sc += o.x; sr += o.y;
+                    if (__ldg(p.gt_count + j) > 0) { sv += o.z; ne += 1.0; }
+                }
+                sc = block_sum(sc, s_red[0]);
+                sr = block_sum(sr, s_red[0]);
+                sv = block_sum(sv, s_red[0]);
+                ne = block_sum(ne, s_red[0]);
+                if (tid == 0) {
+                    p.losses[0] = (float)(sc / p.B);
+                    p.losses[1] = (float)(sr / p.B);
+                    p.losses[2] = (VARIANT == G3D_VARIANT_3D) ? (float)(sv / ne) : 0.0f;  // 0/0 -> NaN when all empty
+                    p.losses[3] = (float)ne;
+                }
+            }
+        }
+        __syncthreads();  // s_red / s_last are reused by the next image
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------- backward
+struct FocalBwdArgs {
+    const float* cls;
+    const float* reg;
+    const float4* anchors;
+    const float* ann;
+    const float* grad_out;   // [3]
+    const float* per_image;  // [B][4]
+    const float* losses;     // [4] (losses[3] = number of non-empty images)
+    const int32_t* assign;
+    float* dcls;
+    float* dreg;             // pre-zeroed; only positive rows are written
+    int B, A, C, R, Gmax, W;
+};
+
+template <int VARIANT, int CS>
+__global__ void __launch_bounds__(256) focal_bwd_kernel(const FocalBwdArgs p) {
+    const int b = blockIdx.y;
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    if (a >= p.A) return;
+    const int C = (CS > 0) ? CS : p.C;
+    const int64_t row = (int64_t)b * p.A + a;
+    const int code = __ldg(p.assign + row);
+    const float npos = __ldg(p.per_image + 4 * b + 3);
+    const float s_cls = __ldg(p.grad_out + 0) / ((float)p.B * fmaxf(npos, 1.0f));
+    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+    const float* grow = nullptr;
+    int pos_cls = -1;
+    if (code >= 0) {
+        grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
+        pos_cls = (int)(long long)grow[cls_col];
+    }
+    if (CS == 8) {
+        const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
+        float4 c0 = ld_stream(cp), c1 = ld_stream(cp + 1);
+        float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        float g[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+        float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
+        st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
+        st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
+    } else {
+        const float* cp = p.cls + row * C;
+        float* dp = p.dcls + row * C;
+        for (int c = 0; c < C; ++c)
+            dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
+    }
+    if (code < 0) return;
+    // ---- positive anchor: regression gradient
+    const float4 an = __ldg(p.anchors + a);
+    const float* rrow = p.reg + row * p.R;
+    float* drow = p.dreg + row * p.R;
+    if (VARIANT == G3D_VARIANT_3D) {
+        const float s_reg = __ldg(p.grad_out + 1) / ((float)p.B * 20.0f * npos);
+        const float s_vp = __ldg(p.grad_out + 2) / (__ldg(p.losses + 3) * npos * 3.0f);
+        float r[12], t[20], pr[20], tv[6], g[20], dr[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) r[i] = rrow[i];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) t[i] = grow[i];
+        gt_directions(t, tv);
+        pred_corners(r, pr);
+        const float aw = an.z - an.x, ah = an.w - an.y;
+        const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
+#pragma unroll
+        for (int i = 0; i < 20; ++i) {
+            const float tn = (i & 1) ? (t[i] - acy) / ah : (t[i] - acx) / aw;
+            const float diff = tn - pr[i];
+            const float w = (i >= 8 && i < 16) ? 0.5f : 1.0f;
+            const float d = fabsf(diff) * w;
+            const float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
+            // d smooth_l1 / d pred = slope(d) * w * d|diff|/dpred = slope * w * (-sign(diff))
+            g[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * w * sg;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dr[i] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            dr[0] += g[2 * k];            dr[1] += g[2 * k + 1];
+            dr[2] += sgn_l(k) * g[2 * k]; dr[3] += sgn_l(k) * g[2 * k + 1];
+            dr[4] += sgn_w(k) * g[2 * k]; dr[5] += sgn_w(k) * g[2 * k + 1];
+            dr[6] += sgn_h(k) * g[2 * k]; dr[7] += sgn_h(k) * g[2 * k + 1];
+        }
+        dr[8] = g[16]; dr[9] = g[17]; dr[10] = g[18]; dr[11] = g[19];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            float gx, gy;
+            cos_loss_grad(r[2 + 2 * v], r[3 + 2 * v], tv[2 * v], tv[2 * v + 1], gx, gy);
+            dr[2 + 2 * v] += s_vp * gx;
+            dr[3 + 2 * v] += s_vp * gy;
+        }
+#pragma unroll
+        for (int i = 0; i < 12; ++i) drow[i] = dr[i];
+    } else {
+        const float s_reg = __ldg(p.grad_out + 1) / ((float)p.B * 4.0f * npos);
+        float t[4];
+        targets_2d(grow, an, t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float diff = t[i] - rrow[i];
+            const float d = fabsf(diff);
+            const float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
+            drow[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * sg;
+        }
+    }
+}
+
+struct FocalWorkspace {
+    float4* gt_box;
+    int32_t* gt_row;
+    int32_t* gt_count;
+    double* partials;
+    int32_t* counters;
+    int64_t bytes;
+};
+
+static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
+    FocalWorkspace w;
+    const int64_t T = ceil_div(A, kTile);
+    int64_t off = 0;
+    char* p = (char*)base;
+    w.gt_box = (float4*)(p + off);   off += align_up(B * Gmax * 16, 256);
+    w.gt_row = (int32_t*)(p + off);  off += align_up(B * Gmax * 4, 256);
+    w.gt_count = (int32_t*)(p + off); off += align_up(B * 4, 256);
+    w.partials = (double*)(p + off); off += align_up(B * T * 32, 256);
+    w.counters = (int32_t*)(p + off); off += align_up((B + 1) * 4, 256);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace g3d
+
+using namespace g3d;
+
+extern "C" int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax) {
+    if (B < 0 || A < 0 || Gmax < 0) return G3D_ERR_INVALID;
+    return carve(nullptr, B, A, Gmax).bytes;
+}
+
+static int check_focal_shapes(int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant) {
+    G3D_REQUIRE(variant == G3D_VARIANT_2D || variant == G3D_VARIANT_3D, "unknown variant");
+    G3D_REQUIRE(B >= 1 && A >= 1 && C >= 1 && Gmax >= 0, "sizes must be positive");
+    G3D_REQUIRE(B <= 65535 * (int64_t)kImgPerCta && A < ((int64_t)1 << 31) - kTile && Gmax < (1 << 30) && C < (1 << 20),
+                "size out of range");
+    if (variant == G3D_VARIANT_3D) {
+        G3D_REQUIRE(R == 12, "3D variant needs 12 regression outputs per anchor");
+        G3D_REQUIRE(W >= 21, "3D variant needs >= 21 annotation columns");
+    } else {
+        G3D_REQUIRE(R == 4, "2D variant needs 4 regression outputs per anchor");
+        G3D_REQUIRE(W >= 5, "2D variant needs >= 5 annotation columns");
+    }
+    return G3D_OK;
+}
+
+extern "C" int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
+                                  int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
+                                  float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
+                                  void* workspace, int64_t workspace_bytes, int device, void* stream) {
+    int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
+    if (rc != G3D_OK) return rc;
+    G3D_REQUIRE(cls && reg && anchors && losses && per_image && workspace, "null pointer");
+    G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
+    FocalWorkspace w = carve(workspace, B, A, Gmax);
+    G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see g3d_focal_workspace_bytes)");
+    G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)anchors % 16) == 0 && ((uintptr_t)workspace % 256) == 0 &&
+                    ((uintptr_t)per_image % 16) == 0,
+                "cls/anchors/per_image must be 16-byte aligned and the workspace 256-byte aligned");
+    G3D_GUARD(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    G3D_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int32_t) * (B + 1), st));
+    rc = g3d_gt_prepare(ann, B, Gmax, W, variant, (float*)w.gt_box, w.gt_row, w.gt_count, device, stream);
+    if (rc != G3D_OK) return rc;
+    FocalArgs p;
+    p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
+    p.gt_box = w.gt_box; p.gt_row = w.gt_row; p.gt_count = w.gt_count;
+    p.partials = w.partials; p.counters = w.counters;
+    p.losses = losses; p.per_image = per_image; p.assign = assign;
+    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
+    p.T = (int)ceil_div(A, kTile);
+    dim3 grid((unsigned)p.T, (unsigned)ceil_div(B, kImgPerCta));
+    if (variant == G3D_VARIANT_3D) {
+        if (C == 8) focal_fwd_kernel<G3D_VARIANT_3D, 8><<<grid, kTile, 0, st>>>(p);
+        else        focal_fwd_kernel<G3D_VARIANT_3D, 0><<<grid, kTile, 0, st>>>(p);
+    } else {
+        if (C == 8) focal_fwd_kernel<G3D_VARIANT_2D, 8><<<grid, kTile, 0, st>>>(p);
+        else        focal_fwd_kernel<G3D_VARIANT_2D, 0><<<grid, kTile, 0, st>>>(p);
+    }
+    G3D_LAUNCH_CHECK();
+    if (gt_count_out)
+        G3D_CUDA(cudaMemcpyAsync(gt_count_out, w.gt_count, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    return G3D_OK;
+}
+
+extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
+                                  int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
+                                  const float* grad_out, const float* per_image, const float* losses,
+                                  const int32_t* assign, float* dcls, float* dreg, int device, void* stream) {
+    int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
+    if (rc != G3D_OK) return rc;
+    G3D_REQUIRE(cls && reg && anchors && grad_out && per_image && losses && assign && dcls && dreg, "null pointer");
+    G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
+    G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)dcls % 16) == 0 && ((uintptr_t)anchors % 16) == 0,
+                "cls/dcls/anchors must be 16-byte aligned");
+    G3D_REQUIRE(B <= 65535, "B out of range for the backward grid");
+    G3D_GUARD(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    G3D_CUDA(cudaMemsetAsync(dreg, 0, sizeof(float) * B * A * R, st));
+    FocalBwdArgs p;
+    p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
+    p.grad_out = grad_out; p.per_image = per_image; p.losses = losses; p.assign = assign;
+    p.dcls = dcls; p.dreg = dreg;
+    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
+    dim3 grid((unsigned)ceil_div(A, 256), (unsigned)B);
+    if (variant == G3D_VARIANT_3D) {
+        if (C == 8) focal_bwd_kernel<G3D_VARIANT_3D, 8><<<grid, 256, 0, st>>>(p);
+        else        focal_bwd_kernel<G3D_VARIANT_3D, 0><<<grid, 256, 0, st>>>(p);
+    } else {
+        if (C == 8) focal_bwd_kernel<G3D_VARIANT_2D, 8><<<grid, 256, 0, st>>>(p);
+        else        focal_bwd_kernel<G3D_VARIANT_2D, 0><<<grid, 256, 0, st>>>(p);
+    }
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}

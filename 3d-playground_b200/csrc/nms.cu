@@ -1,0 +1,350 @@
+// nms.cu — a11 greedy NMS with torchvision.ops.nms semantics, segmented (many independent box sets per launch).
+//
+// Replaces torchvision.ops.nms as called from retinanet/model.py:297, 3D model.py:383 and :336 (through batched_nms
+// :19-57), perform_3D_detection_on_video_sequences.py:78, MC3D_crop_tracker.py:507,614,634, minimal_3D_track.py:515,535.
+//
+// Pipeline per segment, all on the device (no suppression bitmask in HBM, no device->host copy):
+//   1. keys   : 64-bit key = (~orderable(score)) << 32 | index   -> ascending key order == stable descending score
+//   2. sort   : bitonic sort of the keys (shared memory up to 16384 entries; global passes above that, S == 1 only)
+//   3. greedy : one CTA walks the sorted boxes in blocks of 64: a 64x64 triangular IoU bit-matrix resolves the block
+//               (warp-shuffle scan), then every thread sweeps the still-alive later boxes against the block's kept
+//               boxes.  Work is O(kept x N) instead of O(N^2 / 2) and nothing but the boxes is ever stored.
+#include "common.cuh"
+
+namespace g3d {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kSortCap = 16384;        // longest segment the single-CTA shared-memory sort handles
+constexpr int kSmemBoxCap = 8192;      // longest segment whose sorted boxes are cached in shared memory
+constexpr int kLocalSort = 4096;       // tile of the multi-CTA (global) bitonic sort
+
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
+    if (score == 0.0f) score = 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
+    uint32_t u = __float_as_uint(score);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // monotone float -> uint
+    return ((uint64_t)(~u) << 32) | idx;             // descending score, ascending index on ties
+}
+
+__device__ __forceinline__ float4 load_box(const float* __restrict__ boxes, int64_t stride, int64_t col, int64_t row) {
+    const float* p = boxes + row * stride + col;
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+}
+
+__device__ __forceinline__ void bitonic_smem(uint64_t* sk, int P, int k_from, int k_to, int j_from) {
+    // runs stages k = k_from..k_to (doubling); within the first stage starts at j = j_from (0 -> k/2)
+    for (int k = k_from; k <= k_to; k <<= 1) {
+        for (int j = (k == k_from && j_from > 0) ? j_from : (k >> 1); j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const uint64_t a = sk[i], b = sk[l];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// one CTA per segment, n <= kSortCap
+__global__ void __launch_bounds__(kNmsThreads) seg_sort_kernel(const float* __restrict__ scores,
+                                                               const int32_t* __restrict__ seg_offsets,
+                                                               const float* __restrict__ boxes, int64_t stride, int64_t col,
+                                                               int32_t* __restrict__ sidx, float4* __restrict__ sbox) {
+    extern __shared__ uint64_t sk[];
+    const int seg = blockIdx.x;
+    const int off = seg_offsets[seg];
+    const int n = seg_offsets[seg + 1] - off;
+    if (n <= 0) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x)
+        sk[i] = (i < n) ? make_key(__ldg(scores + off + i), (uint32_t)i) : ~0ull;
+    __syncthreads();
+    bitonic_smem(sk, P, 2, P, 0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int src = (int)(sk[i] & 0xffffffffu);
+        sidx[off + i] = src;
+        sbox[off + i] = load_box(boxes, stride, col, (int64_t)off + src);
+    }
+}
+
+// ---- multi-CTA sort for one long segment (S == 1): keys in global memory, padded to a power of two
+__global__ void __launch_bounds__(256) keys_init_kernel(const float* __restrict__ scores, int n, int P,
+                                                        uint64_t* __restrict__ keys) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
+        keys[i] = (i < n) ? make_key(__ldg(scores + i), (uint32_t)i) : ~0ull;
+}
+// full sort of each kLocalSort tile (first = 1), or the tail j < kLocalSort of merge stage k (first = 0)
+__global__ void __launch_bounds__(kNmsThreads) bitonic_local_kernel(uint64_t* __restrict__ keys, int k, int first) {
+    __shared__ uint64_t sk[kLocalSort];
+    uint64_t* g = keys + (int64_t)blockIdx.x * kLocalSort;
+    for (int i = threadIdx.x; i < kLocalSort; i += blockDim.x) sk[i] = g[i];
+    __syncthreads();
+    if (first) {
+        // direction of a tile's final stage depends on its global position: emulate with the global index bit
+        for (int kk = 2; kk <= kLocalSort; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (kLocalSort >> 1); t += blockDim.x) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const int64_t gi = (int64_t)blockIdx.x * kLocalSort + i;
+                    const bool up = (gi & kk) == 0;
+                    const uint64_t a = sk[i], b = sk[l];
+                    if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        for (int j = kLocalSort >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (kLocalSort >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const int64_t gi = (int64_t)blockIdx.x * kLocalSort + i;
+                const bool up = (gi & k) == 0;
+                const uint64_t a = sk[i], b = sk[l];
+                if ((a > b) == up) { sk[i] = b; sk[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kLocalSort; i += blockDim.x) g[i] = sk[i];
+}
+__global__ void __launch_bounds__(256) bitonic_global_kernel(uint64_t* __restrict__ keys, int P, int k, int j) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < (P >> 1); t += gridDim.x * blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const uint64_t a = keys[i], b = keys[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+    }
+}
+__global__ void __launch_bounds__(256) keys_gather_kernel(const uint64_t* __restrict__ keys, int n,
+                                                          const float* __restrict__ boxes, int64_t stride, int64_t col,
+                                                          int32_t* __restrict__ sidx, float4* __restrict__ sbox) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int src = (int)(keys[i] & 0xffffffffu);
+        sidx[i] = src;
+        sbox[i] = load_box(boxes, stride, col, src);
+    }
+}
+
+// ---- greedy pass: one CTA per segment
+__device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
+    const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)(v >> 32), src);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <bool SMEM_BOXES>
+__global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* __restrict__ sbox,
+                                                                 const int32_t* __restrict__ sidx,
+                                                                 const int32_t* __restrict__ seg_offsets, float thr,
+                                                                 int relative, int removed_words, int box_cap,
+                                                                 int64_t* __restrict__ keep_out,
+                                                                 int32_t* __restrict__ keep_count) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    float4* cbox = reinterpret_cast<float4*>(dyn);  // [box_cap] when SMEM_BOXES
+    uint32_t* removed = reinterpret_cast<uint32_t*>(dyn + (SMEM_BOXES ? sizeof(float4) * box_cap : 0));
+    __shared__ float4 dbox[64];
+    __shared__ float darea[64];
+    __shared__ uint64_t diag[64];
+    __shared__ float4 kbox[64];
+    __shared__ float karea[64];
+    __shared__ uint64_t s_keep;
+
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int off = seg_offsets[seg];
+    const int n = seg_offsets[seg + 1] - off;
+    if (n <= 0) {
+        if (tid == 0) keep_count[seg] = 0;
+        return;
+    }
+    const float4* gbox = sbox + off;
+    for (int i = tid; i < removed_words; i += kNmsThreads) removed[i] = 0u;
+    if (SMEM_BOXES)
+        for (int i = tid; i < n; i += kNmsThreads) cbox[i] = gbox[i];
+    __syncthreads();
+
+    int total_kept = 0;
+    const int nblk = (n + 63) >> 6;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int base = blk << 6;
+        const int m = min(64, n - base);
+        const uint64_t mmask = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
+        const uint64_t remword = ((uint64_t)removed[2 * blk + 1] << 32) | removed[2 * blk];
+        if ((remword & mmask) == mmask) continue;  // whole block already suppressed (uniform across the CTA)
+        if (tid < m) {
+            const float4 b = SMEM_BOXES ? cbox[base + tid] : gbox[base + tid];
+            dbox[tid] = b;
+            darea[tid] = box_area_rn(b.x, b.y, b.z, b.w);
+        }
+        __syncthreads();
+        {   // 64x64 strictly-upper-triangular suppression bits: thread (row i = tid/16) covers columns l16 + 16q
+            const int i = tid >> 4, l16 = tid & 15;
+            const bool row_live = (i < m) && !((remword >> i) & 1ull);
+            uint64_t word = 0ull;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = l16 + 16 * q;
+                bool pred = false;
+                if (row_live && j > i && j < m)
+                    pred = iou_torchvision(dbox[i], darea[i], dbox[j], darea[j]) > thr;
+                const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+                const uint32_t half = (lane < 16) ? (bal & 0xffffu) : (bal >> 16);
+                word |= (uint64_t)half << (16 * q);
+            }
+            if (l16 == 0) diag[i] = word;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint64_t dA = diag[lane], dB = diag[lane + 32];
+            uint64_t rem = remword;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const uint64_t d = shfl64(i < 32 ? dA : dB, i & 31);
+                if (!((rem >> i) & 1ull)) rem |= d;
+            }
+            const uint64_t keep = ~rem & mmask;
+            if (lane == 0) s_keep = keep;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = lane + 32 * half;
+                if ((keep >> i) & 1ull) {
+                    const int pos = __popcll(keep & ((1ull << i) - 1ull));
+                    kbox[pos] = dbox[i];
+                    karea[pos] = darea[i];
+                    const int64_t src = sidx[off + base + i];
+                    keep_out[off + total_kept + pos] = relative ? src : src + off;
+                }
+            }
+        }
+        __syncthreads();
+        const int kc = __popcll(s_keep);
+        total_kept += kc;
+        if (kc > 0) {
+            for (int j = base + 64 + tid; j < n; j += kNmsThreads) {
+                if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
+                const float4 bj = SMEM_BOXES ? cbox[j] : gbox[j];
+                const float aj = box_area_rn(bj.x, bj.y, bj.z, bj.w);
+                for (int k = 0; k < kc; ++k) {
+                    if (iou_torchvision(kbox[k], karea[k], bj, aj) > thr) {
+                        atomicOr(&removed[j >> 5], 1u << (j & 31));
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) keep_count[seg] = total_kept;
+}
+
+struct NmsWorkspace {
+    int32_t* sidx;
+    float4* sbox;
+    uint64_t* keys;
+    int64_t bytes;
+};
+static NmsWorkspace carve_nms(void* base, int64_t N, int64_t S, int64_t max_seg_len) {
+    NmsWorkspace w;
+    char* p = (char*)base;
+    int64_t off = 0;
+    w.sbox = (float4*)(p + off); off += align_up(N * 16, 256);
+    w.sidx = (int32_t*)(p + off); off += align_up(N * 4, 256);
+    w.keys = (uint64_t*)(p + off);
+    if (max_seg_len > kSortCap) {
+        int64_t P = kLocalSort;
+        while (P < max_seg_len) P <<= 1;
+        off += align_up(P * 8, 256);
+    }
+    (void)S;
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace g3d
+
+using namespace g3d;
+
+extern "C" int64_t g3d_nms_workspace_bytes(int64_t N, int64_t S, int64_t max_seg_len) {
+    if (N < 0 || S < 0 || max_seg_len < 0) return G3D_ERR_INVALID;
+    return carve_nms(nullptr, N, S, max_seg_len).bytes;
+}
+
+extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t box_col, const float* scores, int64_t N,
+                                 const int32_t* seg_offsets, int64_t S, int64_t max_seg_len, double iou_threshold,
+                                 int relative, int64_t* keep_out, int32_t* keep_count, void* workspace,
+                                 int64_t workspace_bytes, int device, void* stream) {
+    G3D_REQUIRE(N >= 0 && S >= 0 && max_seg_len >= 0 && box_stride >= 4 && box_col >= 0 && box_col + 4 <= box_stride,
+                "bad size");
+    G3D_REQUIRE(N < ((int64_t)1 << 31) && S < ((int64_t)1 << 31), "size out of range");
+    if (S == 0) return G3D_OK;
+    G3D_REQUIRE(seg_offsets && keep_count, "null pointer");
+    G3D_GUARD(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N == 0 || max_seg_len == 0) {
+        G3D_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t) * S, st));
+        return G3D_OK;
+    }
+    G3D_REQUIRE(boxes && scores && keep_out && workspace, "null pointer");
+    G3D_REQUIRE(max_seg_len <= N, "max_seg_len exceeds N");
+    G3D_REQUIRE(((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
+    NmsWorkspace w = carve_nms(workspace, N, S, max_seg_len);
+    G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see g3d_nms_workspace_bytes)");
+    if (max_seg_len > kSortCap && S != 1) {
+        set_error("g3d_nms_segmented: segments longer than %d boxes are only supported for S == 1", kSortCap);
+        return G3D_ERR_UNSUPPORTED;
+    }
+    // (double)iou > iou_threshold  <=>  iou > thr_f  with thr_f the largest float <= iou_threshold (torchvision's CPU
+    // kernel compares the float IoU against the double threshold)
+    float thr_f = (float)iou_threshold;
+    if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
+
+    if (max_seg_len <= kSortCap) {
+        int P = 2;
+        while (P < max_seg_len) P <<= 1;
+        const size_t smem = (size_t)P * 8;
+        G3D_CUDA(cudaFuncSetAttribute(seg_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        seg_sort_kernel<<<(unsigned)S, kNmsThreads, smem, st>>>(scores, seg_offsets, boxes, box_stride, box_col, w.sidx,
+                                                                w.sbox);
+        G3D_LAUNCH_CHECK();
+    } else {
+        int64_t P = kLocalSort;
+        while (P < max_seg_len) P <<= 1;
+        G3D_REQUIRE(P < ((int64_t)1 << 31), "segment too long");
+        const int n = (int)N;  // S == 1: the single segment is [0, N)
+        const int g256 = (int)(ceil_div(P, 256) < 148 * 16 ? ceil_div(P, 256) : 148 * 16);
+        keys_init_kernel<<<g256, 256, 0, st>>>(scores, n, (int)P, w.keys);
+        G3D_LAUNCH_CHECK();
+        bitonic_local_kernel<<<(unsigned)(P / kLocalSort), kNmsThreads, 0, st>>>(w.keys, 0, 1);
+        G3D_LAUNCH_CHECK();
+        for (int64_t k = 2 * kLocalSort; k <= P; k <<= 1) {
+            for (int64_t j = k >> 1; j >= kLocalSort; j >>= 1) {
+                bitonic_global_kernel<<<g256, 256, 0, st>>>(w.keys, (int)P, (int)k, (int)j);
+                G3D_LAUNCH_CHECK();
+            }
+            bitonic_local_kernel<<<(unsigned)(P / kLocalSort), kNmsThreads, 0, st>>>(w.keys, (int)k, 0);
+            G3D_LAUNCH_CHECK();
+        }
+        keys_gather_kernel<<<g256, 256, 0, st>>>(w.keys, n, boxes, box_stride, box_col, w.sidx, w.sbox);
+        G3D_LAUNCH_CHECK();
+    }
+    const int removed_words = (int)(2 * ceil_div(max_seg_len, 64));
+    if (max_seg_len <= kSmemBoxCap) {
+        const int box_cap = (int)max_seg_len;
+        const size_t smem = sizeof(float4) * box_cap + (size_t)removed_words * 4;
+        G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_greedy_kernel<true><<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative,
+                                                                       removed_words, box_cap, keep_out, keep_count);
+    } else {
+        const size_t smem = (size_t)removed_words * 4;
+        G3D_REQUIRE(smem <= 200 * 1024, "segment too long for the shared-memory suppression bitset (max ~1.6M boxes)");
+        G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_greedy_kernel<false><<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative,
+                                                                        removed_words, 0, keep_out, keep_count);
+    }
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}

@@ -1,0 +1,530 @@
+"""Tensor-level wrappers over the libgeom3d C ABI (include/geom3d.h).
+
+PyTorch is used for device memory and streams only: every function validates its tensors, allocates outputs with
+torch on the inputs' device, and enqueues the CUDA kernels on torch's current stream of that device.  Nothing here
+computes on the CPU and nothing falls back: a CPU tensor raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import VARIANT_2D, VARIANT_3D, Geom3dError, check
+
+
+# ------------------------------------------------------------------------------------------------------- helpers
+def _need_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"expected a torch.Tensor, got {type(t).__name__}")
+        if not t.is_cuda:
+            raise Geom3dError("geom3d ops run on CUDA tensors only (no CPU fallback): got a tensor on "
+                              f"{t.device}; move it with .cuda()")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise Geom3dError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _prep(t, dtype):
+    """contiguous tensor of `dtype` whose data pointer is 16-byte aligned (detached: raw kernels see no autograd)"""
+    t = t.detach()
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _idx(dev):
+    return dev.index if dev.index is not None else torch.cuda.current_device()
+
+
+def _workspace(nbytes, dev):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+
+
+def sm_count(device=None):
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return check(_lib.lib().g3d_sm_count(_idx(dev)), "g3d_sm_count")
+
+
+# -------------------------------------------------------------------------------------------- a1 / a2: IoU, assignment
+def calc_iou(a, b):
+    """losses.py:5-22.  a[A,4], b[G,4] -> float32 [A,G], bit-identical to the eager reference."""
+    dev = _need_cuda(a, b)
+    a, b = _prep(a, torch.float32), _prep(b, torch.float32)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != 4 or b.shape[1] != 4:
+        raise ValueError("calc_iou expects a[A,4] and b[G,4]")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_calc_iou(_p(a), a.shape[0], _p(b), b.shape[0], _p(out), _idx(dev), _stream(dev)), "g3d_calc_iou")
+    return out
+
+
+def _variant_of(annotations, regressions=None):
+    w = annotations.shape[-1]
+    if regressions is not None:
+        r = regressions.shape[-1]
+        if r == 12:
+            return VARIANT_3D
+        if r == 4:
+            return VARIANT_2D
+        raise ValueError(f"regression width {r}: expected 12 (3D directional) or 4 (2D)")
+    return VARIANT_3D if w >= 21 else VARIANT_2D
+
+
+def gt_prepare(annotations, variant=None):
+    """Row filter (class != -1) + 2D assignment box per GT row.  Returns gt_box[B,G,4], gt_row[B,G], gt_count[B]."""
+    dev = _need_cuda(annotations)
+    ann = _prep(annotations, torch.float32)
+    if ann.dim() != 3:
+        raise ValueError("annotations must be [B,G,W]")
+    variant = _variant_of(ann) if variant is None else variant
+    B, G, W = ann.shape
+    gt_box = torch.empty((B, G, 4), dtype=torch.float32, device=dev)
+    gt_row = torch.empty((B, G), dtype=torch.int32, device=dev)
+    gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(_lib.lib().g3d_gt_prepare(_p(ann), B, G, W, variant, _p(gt_box), _p(gt_row), _p(gt_count), _idx(dev),
+                                    _stream(dev)), "g3d_gt_prepare")
+    return gt_box, gt_row, gt_count
+
+
+def assign(anchors, annotations, variant=None):
+    """IoU max / argmax / assignment code per (image, anchor).  anchors[A,4] or [1,A,4]; annotations[B,G,W].
+
+    Returns (iou_max f32[B,A], iou_argmax i64[B,A] (index into the filtered GT rows, as torch.max gives),
+             assign i32[B,A] (-2 ignore, -1 negative, >=0 original annotation row), num_pos i32[B])."""
+    dev = _need_cuda(anchors, annotations)
+    anc = _prep(anchors, torch.float32).reshape(-1, 4)
+    gt_box, gt_row, gt_count = gt_prepare(annotations, variant)
+    B, G = gt_row.shape
+    A = anc.shape[0]
+    iou_max = torch.empty((B, A), dtype=torch.float32, device=dev)
+    iou_arg = torch.empty((B, A), dtype=torch.int64, device=dev)
+    code = torch.empty((B, A), dtype=torch.int32, device=dev)
+    num_pos = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(_lib.lib().g3d_assign(_p(anc), A, _p(gt_box), _p(gt_row), _p(gt_count), B, G, _p(iou_max), _p(iou_arg),
+                                _p(code), _p(num_pos), _idx(dev), _stream(dev)), "g3d_assign")
+    return iou_max, iou_arg, code, num_pos
+
+
+# ------------------------------------------------------------------------------------------------ a2-a6: fused loss
+def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True):
+    """Fused FocalLoss forward.  Returns dict(losses f32[4], per_image f32[B,4], assign i32[B,A]|None, gt_count i32[B],
+    plus the prepared contiguous inputs for the backward)."""
+    dev = _need_cuda(classifications, regressions, anchors, annotations)
+    cls = _prep(classifications, torch.float32)
+    reg = _prep(regressions, torch.float32)
+    anc = _prep(anchors, torch.float32).reshape(-1, 4)
+    ann = _prep(annotations, torch.float32)
+    if cls.dim() != 3 or reg.dim() != 3 or ann.dim() != 3:
+        raise ValueError("expected classifications[B,A,C], regressions[B,A,R], annotations[B,G,W]")
+    B, A, C = cls.shape
+    R = reg.shape[2]
+    if reg.shape[0] != B or reg.shape[1] != A or anc.shape[0] != A or ann.shape[0] != B:
+        raise ValueError(f"shape mismatch: cls {tuple(cls.shape)}, reg {tuple(reg.shape)}, anchors {tuple(anc.shape)}, "
+                         f"annotations {tuple(ann.shape)}")
+    variant = _variant_of(ann, reg)
+    G, W = ann.shape[1], ann.shape[2]
+    L = _lib.lib()
+    wbytes = L.g3d_focal_workspace_bytes(B, A, G)
+    ws = _workspace(wbytes, dev)
+    losses = torch.empty((4,), dtype=torch.float32, device=dev)
+    per_image = torch.empty((B, 4), dtype=torch.float32, device=dev)
+    code = torch.empty((B, A), dtype=torch.int32, device=dev) if want_assign else None
+    gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
+    check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses), _p(per_image),
+                               _p(code), _p(gt_count), _p(ws), ws.numel(), _idx(dev), _stream(dev)),
+          "g3d_focal_loss_fwd")
+    return dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
+                ann=ann, variant=variant)
+
+
+def focal_loss_backward(fwd, grad_out):
+    """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R])."""
+    cls, reg, anc, ann = fwd["cls"], fwd["reg"], fwd["anchors"], fwd["ann"]
+    dev = cls.device
+    if fwd["assign"] is None:
+        raise Geom3dError("focal_loss_backward needs the assignment codes: call the forward with want_assign=True")
+    B, A, C = cls.shape
+    R = reg.shape[2]
+    G, W = ann.shape[1], ann.shape[2]
+    g = _prep(grad_out, torch.float32)
+    dcls = torch.empty_like(cls)
+    dreg = torch.empty_like(reg)
+    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g),
+                                        _p(fwd["per_image"]), _p(fwd["losses"]), _p(fwd["assign"]), _p(dcls), _p(dreg),
+                                        _idx(dev), _stream(dev)), "g3d_focal_loss_bwd")
+    return dcls, dreg
+
+
+# ------------------------------------------------------------------------------------------------ a7-a9: decode / clip
+def decode3d(anchors, regression):
+    """3D BBoxTransform: anchors[1,A,4] or [A,4], regression[B,A,12] -> [B,A,20] (utils.py:102-149)."""
+    dev = _need_cuda(anchors, regression)
+    anc = _prep(anchors, torch.float32).reshape(-1, 4)
+    reg = _prep(regression, torch.float32)
+    if reg.dim() != 3 or reg.shape[2] != 12 or reg.shape[1] != anc.shape[0]:
+        raise ValueError(f"expected regression[B,A,12] with A == {anc.shape[0]} anchors, got {tuple(reg.shape)}")
+    B, A, _ = reg.shape
+    out = torch.empty((B, A, 20), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_decode3d(_p(anc), _p(reg), B, A, _p(out), _idx(dev), _stream(dev)), "g3d_decode3d")
+    return out
+
+
+def decode2d(anchors, deltas, mean, std, clip_wh=None):
+    """2D BBoxTransform (+ optional fused ClipBoxes): anchors[Ba,A,4], deltas[B,A,4] -> [B,A,4] (retinanet/utils.py:102-126)."""
+    dev = _need_cuda(anchors, deltas)
+    anc = _prep(anchors, torch.float32)
+    dl = _prep(deltas, torch.float32)
+    if anc.dim() == 2:
+        anc = anc.unsqueeze(0)
+    if dl.dim() != 3 or dl.shape[2] != 4 or anc.shape[1] != dl.shape[1] or anc.shape[2] != 4:
+        raise ValueError(f"expected anchors[Ba,A,4] and deltas[B,A,4], got {tuple(anc.shape)} and {tuple(dl.shape)}")
+    B, A, _ = dl.shape
+    mean_h = (ctypes.c_float * 4)(*[float(x) for x in mean])
+    std_h = (ctypes.c_float * 4)(*[float(x) for x in std])
+    out = torch.empty((B, A, 4), dtype=torch.float32, device=dev)
+    clip = 0 if clip_wh is None else 1
+    cw, ch = (0.0, 0.0) if clip_wh is None else (float(clip_wh[0]), float(clip_wh[1]))
+    check(_lib.lib().g3d_decode2d(_p(anc), anc.shape[0], _p(dl), B, A, mean_h, std_h, clip, cw, ch, _p(out), _idx(dev),
+                                  _stream(dev)), "g3d_decode2d")
+    return out
+
+
+def clip_boxes_(boxes, width, height):
+    """ClipBoxes in place on a contiguous float32 tensor [..., K>=4] (retinanet/utils.py:134-144)."""
+    dev = _need_cuda(boxes)
+    if boxes.dtype != torch.float32 or not boxes.is_contiguous():
+        raise Geom3dError("clip_boxes_ works in place: needs a contiguous float32 tensor")
+    K = boxes.shape[-1]
+    N = boxes.numel() // K if K else 0
+    check(_lib.lib().g3d_clip_boxes(_p(boxes), N, K, float(width), float(height), _idx(dev), _stream(dev)),
+          "g3d_clip_boxes")
+    return boxes
+
+
+# ------------------------------------------------------------------------------------------------ a10: score filter
+def rowmax(classification):
+    """scores, classes = torch.max(classification, dim=-1) for [..., C] (3D model.py:320)."""
+    dev = _need_cuda(classification)
+    cls = _prep(classification, torch.float32)
+    C = cls.shape[-1]
+    rows = cls.numel() // C
+    smax = torch.empty(cls.shape[:-1], dtype=torch.float32, device=dev)
+    amax = torch.empty(cls.shape[:-1], dtype=torch.int64, device=dev)
+    check(_lib.lib().g3d_rowmax(_p(cls), rows, C, _p(smax), _p(amax), _idx(dev), _stream(dev)), "g3d_rowmax")
+    return smax, amax
+
+
+_RUNG_CACHE = {}
+
+
+def ladder_rungs(start, factor=10 ** .2):
+    """float32-cast rungs of the reference's `threshold *= 10**.2` loop (3D model.py:368-374), up to +inf."""
+    key = (float(start), float(factor))
+    if key not in _RUNG_CACHE:
+        t, out = float(start), []
+        while True:
+            f = np.float32(t)
+            out.append(f)
+            if np.isinf(f) or len(out) >= 512:
+                break
+            t *= factor
+        _RUNG_CACHE[key] = np.ascontiguousarray(np.array(out, dtype=np.float32))
+    return _RUNG_CACHE[key]
+
+
+def threshold_ladder(scores, outer, inner, N, outer_pitch, start, keep_max=10000):
+    """Adaptive threshold per score vector.  Returns (rung i32[S], count i32[S], thr f32[S]) on the device."""
+    dev = _need_cuda(scores)
+    if scores.dtype != torch.float32 or not scores.is_contiguous():
+        raise Geom3dError("threshold_ladder needs a contiguous float32 score tensor")
+    rungs = ladder_rungs(start)
+    S = outer * inner
+    L = _lib.lib()
+    ws = _workspace(L.g3d_ladder_workspace_bytes(S, len(rungs)), dev)
+    rung = torch.empty((S,), dtype=torch.int32, device=dev)
+    count = torch.empty((S,), dtype=torch.int32, device=dev)
+    thr = torch.empty((S,), dtype=torch.float32, device=dev)
+    check(L.g3d_threshold_ladder(_p(scores), outer, inner, N, outer_pitch, rungs.ctypes.data_as(ctypes.c_void_p),
+                                 len(rungs), keep_max, _p(rung), _p(count), _p(thr), _p(ws), ws.numel(), _idx(dev),
+                                 _stream(dev)), "g3d_threshold_ladder")
+    return rung, count, thr
+
+
+def filter_compact(scores, outer, inner, N, outer_pitch, thr, cap):
+    """Indices n with score > thr[s] per vector.  Returns (idx i32[S,cap] (arrival order), count i32[S])."""
+    dev = _need_cuda(scores, thr)
+    if scores.dtype != torch.float32 or not scores.is_contiguous():
+        raise Geom3dError("filter_compact needs a contiguous float32 score tensor")
+    S = outer * inner
+    thr = _prep(thr, torch.float32)
+    idx = torch.empty((S, cap), dtype=torch.int32, device=dev)
+    count = torch.empty((S,), dtype=torch.int32, device=dev)
+    check(_lib.lib().g3d_filter_compact(_p(scores), outer, inner, N, outer_pitch, _p(thr), cap, _p(idx), _p(count),
+                                        _idx(dev), _stream(dev)), "g3d_filter_compact")
+    return idx, count
+
+
+def gather_candidates(scores, outer, inner, N, outer_pitch, idx, count, cap, boxes=None, box_col=0):
+    """Pack filter_compact's candidates (ascending index per vector).  Returns (seg_offsets i32[S+1], cand_scores f32[T],
+    cand_boxes f32[T,4]|None, cand_src i32[T]) with T = S*cap rows allocated (only seg_offsets[S] are valid)."""
+    dev = _need_cuda(scores, idx, count, boxes)
+    S = outer * inner
+    T = S * cap
+    seg_offsets = torch.empty((S + 1,), dtype=torch.int32, device=dev)
+    cand_scores = torch.empty((T,), dtype=torch.float32, device=dev)
+    cand_src = torch.empty((T,), dtype=torch.int32, device=dev)
+    cand_boxes = None
+    stride = 4
+    if boxes is not None:
+        if boxes.dtype != torch.float32 or not boxes.is_contiguous():
+            raise Geom3dError("gather_candidates needs contiguous float32 boxes")
+        stride = boxes.shape[-1]
+        cand_boxes = torch.empty((T, 4), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_gather_candidates(_p(scores), outer, inner, N, outer_pitch, _p(boxes), stride, box_col, _p(idx),
+                                           _p(count), cap, _p(seg_offsets), _p(cand_scores), _p(cand_boxes), _p(cand_src),
+                                           _idx(dev), _stream(dev)), "g3d_gather_candidates")
+    return seg_offsets, cand_scores, cand_boxes, cand_src
+
+
+# ------------------------------------------------------------------------------------------------ a11: NMS
+def nms_segmented(boxes, scores, seg_offsets, max_seg_len, iou_threshold, box_col=0, relative=True):
+    """Greedy NMS on S independent segments.  boxes[N,K] (box columns box_col..box_col+3), scores[N],
+    seg_offsets i32[S+1] on the device.  Returns (keep i64[N] - segment s's kept indices start at seg_offsets[s] -,
+    keep_count i32[S])."""
+    dev = _need_cuda(boxes, scores, seg_offsets)
+    bx = _prep(boxes, torch.float32)
+    sc = _prep(scores, torch.float32)
+    so = _prep(seg_offsets, torch.int32)
+    if bx.dim() != 2 or bx.shape[1] < box_col + 4 or sc.dim() != 1 or sc.shape[0] != bx.shape[0]:
+        raise ValueError(f"expected boxes[N,>=4] and scores[N], got {tuple(bx.shape)} and {tuple(sc.shape)}")
+    N, K = bx.shape
+    S = so.numel() - 1
+    keep = torch.empty((N,), dtype=torch.int64, device=dev)
+    keep_count = torch.empty((max(S, 0),), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    max_seg_len = int(min(max_seg_len, N))
+    ws = _workspace(L.g3d_nms_workspace_bytes(N, S, max_seg_len), dev)
+    check(L.g3d_nms_segmented(_p(bx), K, box_col, _p(sc), N, _p(so), S, max_seg_len, float(iou_threshold),
+                              1 if relative else 0, _p(keep), _p(keep_count), _p(ws), ws.numel(), _idx(dev),
+                              _stream(dev)), "g3d_nms_segmented")
+    return keep, keep_count
+
+
+def nms(boxes, scores, iou_threshold):
+    """torchvision.ops.nms drop-in: boxes[N,4], scores[N] -> int64 kept indices in descending score order."""
+    dev = _need_cuda(boxes, scores)
+    if boxes.dim() != 2 or boxes.shape[1] != 4:
+        raise ValueError(f"boxes should be a 2d tensor of shape [N,4], got {tuple(boxes.shape)}")
+    if scores.dim() != 1 or scores.shape[0] != boxes.shape[0]:
+        raise ValueError("boxes and scores should have the same number of elements in dimension 0")
+    N = boxes.shape[0]
+    if N == 0:
+        return torch.empty((0,), dtype=torch.int64, device=dev)
+    so = torch.tensor([0, N], dtype=torch.int32, device=dev)
+    keep, cnt = nms_segmented(boxes, scores, so, N, iou_threshold, 0, True)
+    return keep[: int(cnt.item())]
+
+
+# ------------------------------------------------------------------------------------------------ a12-a19: homography
+def _cam_args(cam, dev, d):
+    """cam: None/int -> constant camera; uint8 tensor[d] -> per-object."""
+    if cam is None:
+        return None, 0
+    if isinstance(cam, int):
+        return None, cam
+    cam = cam.to(device=dev, dtype=torch.uint8).contiguous()
+    if cam.numel() != d:
+        raise ValueError(f"camera index tensor has {cam.numel()} entries for {d} objects")
+    return cam, 0
+
+
+def _pts_f(pts):
+    """float32 stays float32, everything else is promoted to float64 (the reference calls .double() on it anyway)"""
+    return _prep(pts, torch.float32 if pts.dtype == torch.float32 else torch.float64)
+
+
+def state_to_space(states):
+    """homography.py:305-320.  states[d,>=6] -> float32 [d,8,3]."""
+    dev = _need_cuda(states)
+    st = _prep(states, torch.float32)
+    if st.dim() != 2 or st.shape[1] < 6:
+        raise ValueError(f"states must be [d,>=6], got {tuple(st.shape)}")
+    d, S = st.shape
+    out = torch.empty((d, 8, 3), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_state_to_space(_p(st), d, S, _p(out), _idx(dev), _stream(dev)), "g3d_state_to_space")
+    return out
+
+
+def space_to_im(pts, P, cam=None, wrapper=False):
+    """homography.py:438-476.  pts[d,m,3], P f64[ncam,2,3,4] (device) -> float64 [d,m,2]."""
+    dev = _need_cuda(pts, P)
+    p = _pts_f(pts)
+    if p.dim() != 3 or p.shape[2] != 3:
+        raise ValueError(f"points must be [d,m,3], got {tuple(p.shape)}")
+    d, m, _ = p.shape
+    cam_t, cam_c = _cam_args(cam, dev, d)
+    out = torch.empty((d, m, 2), dtype=torch.float64, device=dev)
+    check(_lib.lib().g3d_space_to_im(_p(p), int(p.dtype == torch.float64), d, m, _p(P), P.shape[0], _p(cam_t), cam_c,
+                                     int(wrapper), _p(out), _idx(dev), _stream(dev)), "g3d_space_to_im")
+    return out
+
+
+def state_to_im(states, P, cam=None, wrapper=False, all_cams=False, out_dtype=torch.float64):
+    """homography.py:479-488 fused.  states[d,>=6] -> [d,8,2] (or [d,ncam,8,2] with all_cams) float64 (float32 opt-in)."""
+    dev = _need_cuda(states, P)
+    st = _prep(states, torch.float32)
+    if st.dim() != 2 or st.shape[1] < 6:
+        raise ValueError(f"states must be [d,>=6], got {tuple(st.shape)}")
+    if out_dtype not in (torch.float64, torch.float32):
+        raise ValueError("out_dtype must be float64 or float32")
+    d, S = st.shape
+    ncam = P.shape[0]
+    cam_t, cam_c = _cam_args(cam, dev, d)
+    shape = (d, ncam, 8, 2) if all_cams else (d, 8, 2)
+    out = torch.empty(shape, dtype=out_dtype, device=dev)
+    check(_lib.lib().g3d_state_to_im(_p(st), d, S, _p(P), ncam, _p(cam_t), cam_c, int(wrapper), int(all_cams), _p(out),
+                                     int(out_dtype == torch.float32), _idx(dev), _stream(dev)), "g3d_state_to_im")
+    return out
+
+
+def _pts_heights(pts, heights):
+    p = _pts_f(pts)
+    if p.dim() != 3 or p.shape[1] != 8 or p.shape[2] != 2:
+        raise ValueError(f"points must be [d,8,2], got {tuple(p.shape)}")
+    h = _prep(heights, p.dtype).reshape(-1)
+    if h.numel() != p.shape[0]:
+        raise ValueError(f"heights has {h.numel()} entries for {p.shape[0]} objects")
+    return p, h
+
+
+def im_to_space(pts, heights, H, cam=None, wrapper=False):
+    """homography.py:388-435.  pts[d,8,2], heights[d], H f64[ncam,2,3,3] -> float64 [d,8,3]."""
+    dev = _need_cuda(pts, heights, H)
+    p, h = _pts_heights(pts, heights)
+    d = p.shape[0]
+    cam_t, cam_c = _cam_args(cam, dev, d)
+    out = torch.empty((d, 8, 3), dtype=torch.float64, device=dev)
+    check(_lib.lib().g3d_im_to_space(_p(p), _p(h), int(p.dtype == torch.float64), d, _p(H), H.shape[0], _p(cam_t), cam_c,
+                                     int(wrapper), _p(out), _idx(dev), _stream(dev)), "g3d_im_to_space")
+    return out
+
+
+def space_to_state(pts):
+    """homography.py:274-303.  pts[d,8,3] -> float32 [d,6]."""
+    dev = _need_cuda(pts)
+    p = _pts_f(pts)
+    if p.dim() != 3 or p.shape[1] != 8 or p.shape[2] != 3:
+        raise ValueError(f"points must be [d,8,3], got {tuple(p.shape)}")
+    d = p.shape[0]
+    out = torch.empty((d, 6), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_space_to_state(_p(p), int(p.dtype == torch.float64), d, _p(out), _idx(dev), _stream(dev)),
+          "g3d_space_to_state")
+    return out
+
+
+def im_to_state(pts, heights, H, cam=None, wrapper=False):
+    """homography.py:491-500 fused.  -> float32 [d,6]."""
+    dev = _need_cuda(pts, heights, H)
+    p, h = _pts_heights(pts, heights)
+    d = p.shape[0]
+    cam_t, cam_c = _cam_args(cam, dev, d)
+    out = torch.empty((d, 6), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_im_to_state(_p(p), _p(h), int(p.dtype == torch.float64), d, _p(H), H.shape[0], _p(cam_t), cam_c,
+                                     int(wrapper), _p(out), _idx(dev), _stream(dev)), "g3d_im_to_state")
+    return out
+
+
+def im_to_state_refined(pts, heights, H, P, cam=None, wrapper=False, return_heights=False):
+    """The trackers' two-pass idiom (MC3D_crop_tracker.py:364-370) in one kernel.  -> float32 [d,6] (, f64 heights)."""
+    dev = _need_cuda(pts, heights, H, P)
+    p, h = _pts_heights(pts, heights)
+    d = p.shape[0]
+    cam_t, cam_c = _cam_args(cam, dev, d)
+    out = torch.empty((d, 6), dtype=torch.float32, device=dev)
+    hout = torch.empty((d,), dtype=torch.float64, device=dev) if return_heights else None
+    check(_lib.lib().g3d_im_to_state_refined(_p(p), _p(h), int(p.dtype == torch.float64), d, _p(H), _p(P), H.shape[0],
+                                             _p(cam_t), cam_c, int(wrapper), _p(out), _p(hout), _idx(dev), _stream(dev)),
+          "g3d_im_to_state_refined")
+    return (out, hout) if return_heights else out
+
+
+def height_from_template(template_boxes, template_space_heights, boxes):
+    """homography.py:519-551 with torch's type promotion.  -> [d] float64 if any input is, else float32."""
+    dev = _need_cuda(template_boxes, template_space_heights, boxes)
+    tb, th, bx = _pts_f(template_boxes), _pts_f(template_space_heights).reshape(-1), _pts_f(boxes)
+    d = tb.shape[0]
+    if tuple(tb.shape[1:]) != (8, 2) or tuple(bx.shape) != tuple(tb.shape) or th.numel() != d:
+        raise ValueError("expected template_boxes[d,8,2], template_space_heights[d], boxes[d,8,2]")
+    any64 = torch.float64 in (tb.dtype, th.dtype, bx.dtype)
+    out = torch.empty((d,), dtype=torch.float64 if any64 else torch.float32, device=dev)
+    check(_lib.lib().g3d_height_from_template(_p(tb), int(tb.dtype == torch.float64), _p(th), int(th.dtype == torch.float64),
+                                              _p(bx), int(bx.dtype == torch.float64), d, _p(out), _idx(dev), _stream(dev)),
+          "g3d_height_from_template")
+    return out
+
+
+def state_footprint(states):
+    """Road-plane footprint (xmin,ymin,xmax,ymax) of each state (MC3D_crop_tracker.py:625-632). -> float32 [d,4]."""
+    dev = _need_cuda(states)
+    st = _prep(states, torch.float32)
+    if st.dim() != 2 or st.shape[1] < 6:
+        raise ValueError(f"states must be [d,>=6], got {tuple(st.shape)}")
+    d, S = st.shape
+    out = torch.empty((d, 4), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_state_footprint(_p(st), d, S, _p(out), _idx(dev), _stream(dev)), "g3d_state_footprint")
+    return out
+
+
+def corners_to_box(pts):
+    """min/max box of 8 image corners (MC3D_crop_tracker.py:602-607).  pts[d,8,2] -> [d,4] same dtype."""
+    dev = _need_cuda(pts)
+    p = _pts_f(pts)
+    if p.dim() != 3 or p.shape[1] != 8 or p.shape[2] != 2:
+        raise ValueError(f"points must be [d,8,2], got {tuple(p.shape)}")
+    d = p.shape[0]
+    out = torch.empty((d, 4), dtype=p.dtype, device=dev)
+    check(_lib.lib().g3d_corners_to_box(_p(p), int(p.dtype == torch.float64), d, _p(out), _idx(dev), _stream(dev)),
+          "g3d_corners_to_box")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ a20: md_iou
+def pairwise_iou(first, second, eps=0.0, one_minus=False):
+    """out[i,j] = IoU(first[i], second[j]) in float64 (MC3D_crop_tracker.py:1030-1049 on un-broadcast inputs)."""
+    dev = _need_cuda(first, second)
+    a, b = _prep(first, torch.float32), _prep(second, torch.float32)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != 4 or b.shape[1] != 4:
+        raise ValueError("pairwise_iou expects first[n,4] and second[m,4]")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float64, device=dev)
+    check(_lib.lib().g3d_pairwise_iou_f64(_p(a), a.shape[0], _p(b), b.shape[0], float(eps), int(one_minus), _p(out),
+                                          _idx(dev), _stream(dev)), "g3d_pairwise_iou_f64")
+    return out
+
+
+def md_iou(a, b):
+    """Literal md_iou: a, b [..., 4] float64 of equal shape -> IoU [...] float64."""
+    dev = _need_cuda(a, b)
+    if a.shape != b.shape or a.shape[-1] != 4:
+        raise ValueError("md_iou expects two [...,4] tensors of equal shape")
+    a64, b64 = _prep(a, torch.float64), _prep(b, torch.float64)
+    out = torch.empty(a.shape[:-1], dtype=torch.float64, device=dev)
+    check(_lib.lib().g3d_md_iou(_p(a64), _p(b64), out.numel(), _p(out), _idx(dev), _stream(dev)), "g3d_md_iou")
+    return out

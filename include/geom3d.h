@@ -1,0 +1,258 @@
+/*
+ * geom3d.h — C ABI of libgeom3d.so: the sm_100a (B200) kernels behind the 3D-box geometry hot path of
+ * DerekGloudemans/3D-playground (anchor<->GT IoU assignment + focal / corner / direction losses, box decode,
+ * score filter, NMS, homography state<->image projection, tracker footprint IoU).
+ *
+ * The reference has no FFI layer: its boundary is the Python module surface.  Every entry point
+ * below names the reference function (file:line, relative to the reference checkout) whose arithmetic it replaces;
+ * the Python modules in 3d-playground_b200/ bind them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on CUDA device `device` unless the name ends in _host;
+ *   - all tensors are dense row-major ("contiguous"); sizes are int64_t; float = IEEE binary32, double = binary64;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is enqueued on it and the
+ *     call returns without synchronising the device;
+ *   - outputs and workspaces are caller-allocated (query the *_workspace_bytes functions);
+ *   - return value: 0 on success, negative G3D_ERR_* otherwise; g3d_last_error() returns a thread-local message;
+ *   - no global mutable state: safe to call concurrently from several host threads on different devices/streams
+ *     (nn.DataParallel calls the loss that way, train_detector_3D_angle.py:316-318);
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef GEOM3D_H
+#define GEOM3D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G3D_OK 0
+#define G3D_ERR_INVALID (-1)     /* bad argument (null pointer, negative size, unsupported width ...) */
+#define G3D_ERR_CUDA (-2)        /* a CUDA runtime call or kernel launch failed */
+#define G3D_ERR_UNSUPPORTED (-3) /* valid request outside what the kernels implement */
+
+/* annotation layout selector for the loss entry points */
+#define G3D_VARIANT_2D 0 /* retinanet/losses.py: rows (x1,y1,x2,y2,class), 4-d regression */
+#define G3D_VARIANT_3D 1 /* pytorch_retinanet_detector_directional/retinanet/losses.py: 16 corner coords + 4 box + class (+vps), 12-d regression */
+
+/* assignment codes written to the `assign` arrays */
+#define G3D_ASSIGN_IGNORE (-2)   /* 0.4 <= IoU_max < 0.5 : target row of -1 */
+#define G3D_ASSIGN_NEGATIVE (-1) /* IoU_max < 0.4        : target row of 0 */
+/* >= 0: positive; value = ORIGINAL annotation row (before the class != -1 filter) of the assigned GT box */
+
+const char* g3d_version(void);
+const char* g3d_last_error(void);
+/* number of SMs of `device` (used by hosts to size persistent grids / report rooflines); <0 on error */
+int g3d_sm_count(int device);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a1  calc_iou(a, b)            retinanet/losses.py:5-22 == pytorch_retinanet_detector_directional/retinanet/losses.py:5-22
+ * a[A,4], b[G,4] (x1,y1,x2,y2) -> out[A,G]; FP32, operation order and roundings of the reference (no FMA contraction,
+ * IEEE division, union clamped at 1e-8).
+ */
+int g3d_calc_iou(const float* a, int64_t A, const float* b, int64_t G, float* out, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a6 (prologue)  GT row filter + enclosing 2D box      3D losses.py:54,93-107 ; 2D retinanet/losses.py:46,81
+ * ann[B,Gmax,W]; rows whose class column (W-1 for 2D i.e. col 4; col 20 for 3D) equals -1 are dropped, the rest are
+ * compacted in order.  variant 3D: box = (min,min,max,max) over the 8 corners in cols 0..15; 2D: cols 0..3.
+ * gt_box[B,Gmax,4], gt_row[B,Gmax] (original row of each compacted entry), gt_count[B].
+ */
+int g3d_gt_prepare(const float* ann, int64_t B, int64_t Gmax, int64_t W, int variant,
+                   float* gt_box, int32_t* gt_row, int32_t* gt_count, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a2  assignment          3D losses.py:109-131 ; 2D retinanet/losses.py:81-104
+ * For every image b and anchor a: IoU_max, IoU_argmax = max_g calc_iou(anchor a, gt_box[b,g]) with torch.max's
+ * first-maximal-index rule (index into the compacted GT list; 0 for an image without GT).
+ * iou_max[B,A] (nullable), iou_argmax[B,A] int64 (nullable), assign[B,A] int32 codes (nullable), num_pos[B] int32
+ * (nullable; zeroed by the call itself).
+ */
+int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32_t* gt_row, const int32_t* gt_count,
+               int64_t B, int64_t Gmax, float* iou_max, int64_t* iou_argmax, int32_t* assign, int32_t* num_pos,
+               int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a2-a6  FocalLoss.forward fused: assignment + focal classification loss + regression loss (+ direction loss)
+ *        3D losses.py:27-362 ; 2D retinanet/losses.py:27-177
+ * cls[B,A,C] (post-sigmoid), reg[B,A,R] (R = 12 for 3D, 4 for 2D), anchors[A,4], ann[B,Gmax,W]
+ * (W >= 21 for 3D - only cols 0..20 are read -, W == 5 for 2D).
+ * Outputs:
+ *   losses[4]        = (classification, regression, direction "vp") batch means exactly as the reference forms them:
+ *                      mean over all B images for cls/reg, mean over the images that have >=1 GT row for vp
+ *                      (NaN if there is none: the reference raises there, the Python wrapper turns it into the raise);
+ *                      2D variant: losses[2] = 0.  losses[3] = number of images with >= 1 GT row.
+ *   per_image[B,4]   = (cls_j, reg_j, vp_j, num_pos_j) per image (vp_j = 0 and flagged by gt_count==0 for empty images)
+ *   assign[B,A]      = assignment codes (nullable; needed by the backward)
+ * workspace: g3d_focal_workspace_bytes(B, A, Gmax) bytes, 256-byte aligned, contents undefined on entry.
+ */
+int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax);
+int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
+                       int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
+                       float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
+                       void* workspace, int64_t workspace_bytes, int device, void* stream);
+
+/* backward of the above (autograd of the reference graph, same file:lines).
+ * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory).
+ * per_image / losses / assign = what the forward wrote.  dcls[B,A,C] is fully written; dreg[B,A,R] is fully
+ * written (zeros on non-positive anchors).
+ */
+int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
+                       int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
+                       const float* grad_out, const float* per_image, const float* losses, const int32_t* assign,
+                       float* dcls, float* dreg, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a7  3D BBoxTransform.forward     pytorch_retinanet_detector_directional/retinanet/utils.py:102-149
+ * anchors[A,4] (the reference's boxes[1,A,4]), reg[B,A,12] -> out[B,A,20].  Bit-identical to the eager reference
+ * (separate FP32 mul and add, left-to-right sums).
+ */
+int g3d_decode3d(const float* anchors, const float* reg, int64_t B, int64_t A, float* out, int device, void* stream);
+
+/* a8  2D BBoxTransform.forward     retinanet/utils.py:102-126
+ * anchors[Ba,A,4] with Ba == 1 or B; deltas[B,A,4]; mean[4], std[4] host arrays -> out[B,A,4].
+ * If clip != 0 the ClipBoxes clamp (a9) for an image of clip_w x clip_h is fused into the same pass.
+ */
+int g3d_decode2d(const float* anchors, int64_t Ba, const float* deltas, int64_t B, int64_t A,
+                 const float* mean_host, const float* std_host, int clip, float clip_w, float clip_h,
+                 float* out, int device, void* stream);
+
+/* a9  ClipBoxes.forward (in place)  retinanet/utils.py:134-144 ; 3D copy utils.py:157-167
+ * boxes[N,K] with K >= 4: col0,col1 = max(.,0); col2 = min(., width); col3 = min(., height).
+ */
+int g3d_clip_boxes(float* boxes, int64_t N, int64_t K, float width, float height, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a10 score filter.
+ * Score vectors are described by (outer, inner, N): vector s = o*inner + c is scores[o*outer_pitch + n*inner + c],
+ * n in [0,N).  classification[B,A,C] taken per (image, class) is (outer=B, inner=C, N=A, outer_pitch=A*C)
+ * (retinanet/model.py:287-289, 3D model.py:365-374); a flat vector is (outer=1, inner=1) (3D model.py:320-328).
+ *
+ * g3d_rowmax: scores, classes = torch.max(classification, dim=1) (3D model.py:320): cls[rows,C] -> smax[rows],
+ *   amax[rows] int64 (first maximal index).
+ * g3d_threshold_ladder: the adaptive ladder of 3D model.py:322-328 (start 1e-7, MULTI_FRAME) and :368-374 (1e-25):
+ *   thresholds_host[L] = the float32-cast rungs, ascending (the caller forms them in double by repeated
+ *   multiplication, as the Python loop does); one pass builds per-vector rung histograms, then
+ *   rung_out[s] = first rung whose count of (score > rung) is <= keep_max (-1 if none), count_out[s] that count,
+ *   thr_out[s] = the rung value (device array, feeds g3d_filter_compact without a host round trip).
+ * g3d_filter_compact: for each vector append the element index n of every score > thr[s] to idx_out[s*cap ...]
+ *   (arrival order - the NMS front end orders by (score, index)); count_out[s] = number of passing scores, which may
+ *   exceed cap (then only cap indices were stored: the caller must retry with a larger cap).
+ */
+int g3d_rowmax(const float* cls, int64_t rows, int64_t C, float* smax, int64_t* amax, int device, void* stream);
+int64_t g3d_ladder_workspace_bytes(int64_t S, int64_t L);
+int g3d_threshold_ladder(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                         const float* thresholds_host, int64_t L, int64_t keep_max, int32_t* rung_out,
+                         int32_t* count_out, float* thr_out, void* workspace, int64_t workspace_bytes, int device,
+                         void* stream);
+int g3d_filter_compact(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                       const float* thr, int64_t cap, int32_t* idx_out, int32_t* count_out, int device, void* stream);
+/* g3d_gather_candidates: packs the candidates of g3d_filter_compact for the NMS front end.  Per vector s the stored
+ *   indices (min(count[s], cap) of them, cap <= 16384) are sorted ascending - the order of the reference's boolean-mask
+ *   gather (3D model.py:380-382, retinanet/model.py:294-296) - and written contiguously from seg_offsets[s]
+ *   (seg_offsets[S+1] = exclusive scan, produced here): cand_scores[.], cand_src[.] (the element index n) and, when
+ *   boxes != NULL, cand_boxes[.,4] = boxes[(o*N + n)*box_stride + box_col ...].
+ */
+int g3d_gather_candidates(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                          const float* boxes, int64_t box_stride, int64_t box_col, const int32_t* idx,
+                          const int32_t* count, int64_t cap, int32_t* seg_offsets, float* cand_scores,
+                          float* cand_boxes, int32_t* cand_src, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a11 NMS       torchvision.ops.nms as called at retinanet/model.py:297, 3D model.py:383 (and :336 through
+ *               batched_nms :19-57), perform_3D_detection_on_video_sequences.py:78, MC3D_crop_tracker.py:507,614,634
+ * Segmented greedy NMS: S independent segments, segment s = entries seg_offsets[s] .. seg_offsets[s+1]-1 of
+ * boxes[N, box_stride floats] (the 4 box columns start at column box_col) and scores[N].
+ * Per segment: stable descending score order (ties: lower index first); box j is suppressed by a kept box i iff
+ * IoU(i,j) > iou_threshold, IoU in FP32 as torchvision computes it, the comparison against the double threshold.
+ * keep_out[N] int64: for segment s the kept indices (relative to the segment start when relative != 0, else global)
+ * in descending score order, stored from position seg_offsets[s]; keep_count[S] int32.
+ * seg_offsets is a DEVICE int32 array of S+1 entries; max_seg_len is a host upper bound of the longest segment.
+ */
+int64_t g3d_nms_workspace_bytes(int64_t N, int64_t S, int64_t max_seg_len);
+int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t box_col, const float* scores, int64_t N,
+                      const int32_t* seg_offsets, int64_t S, int64_t max_seg_len, double iou_threshold, int relative,
+                      int64_t* keep_out, int32_t* keep_count, void* workspace, int64_t workspace_bytes,
+                      int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * a12 Homography.i24_state_to_space        homography.py:305-320
+ * states[d,S] (S >= 6; x,y,l,w,h,direction in cols 0..5) -> out[d,8,3] float32.
+ */
+int g3d_state_to_space(const float* states, int64_t d, int64_t S, float* out, int device, void* stream);
+
+/* a13 Homography.space_to_im               homography.py:438-476 (wrapper select :849-856)
+ * pts[d,m,3] float32 or float64 (pts_is_f64), P[ncam,2,3,4] float64 = per camera the 3x4 projection of the first
+ * (hg1 / EB) and second (hg2 / WB) homography; cam[d] uint8 camera index per object (nullable -> camera `cam_const`);
+ * wrapper != 0 selects the second matrix for objects whose pts[i,0,1] > 60 (Homography_Wrapper), else always the first.
+ * out[d,m,2] float64.
+ */
+int g3d_space_to_im(const void* pts, int pts_is_f64, int64_t d, int64_t m, const double* P, int64_t ncam,
+                    const uint8_t* cam, int cam_const, int wrapper, double* out, int device, void* stream);
+
+/* a14 Homography.state_to_im               homography.py:479-488 (wrapper :861-862)
+ * fused a12 o a13 without the [d,8,3] intermediate.  out[d,8,2] float64 (out_f32 == 0) or float32 (opt-in).
+ * all_cams != 0: project every state into all ncam cameras -> out[d,ncam,8,2] (cam ignored).
+ */
+int g3d_state_to_im(const float* states, int64_t d, int64_t S, const double* P, int64_t ncam,
+                    const uint8_t* cam, int cam_const, int wrapper, int all_cams, void* out, int out_f32,
+                    int device, void* stream);
+
+/* a15 Homography.im_to_space               homography.py:388-435 (wrapper :840-847)
+ * pts[d,8,2] float32/float64, heights[d] float32/float64 (same flag), H[ncam,2,3,3] float64 image->road-plane
+ * homographies; out[d,8,3] float64: (x,y) = H.(u,v,1) dehomogenised, z = 0 for corners 0..3, +height for 4..7.
+ * wrapper != 0: objects whose first-matrix result has out[i,0,1] > 60 are recomputed with the second matrix.
+ */
+int g3d_im_to_space(const void* pts, const void* heights, int in_is_f64, int64_t d, const double* H, int64_t ncam,
+                    const uint8_t* cam, int cam_const, int wrapper, double* out, int device, void* stream);
+
+/* a16 Homography.i24_space_to_state        homography.py:274-303
+ * pts[d,8,3] float32/float64 -> out[d,6] float32.
+ */
+int g3d_space_to_state(const void* pts, int pts_is_f64, int64_t d, float* out, int device, void* stream);
+
+/* a17 Homography.im_to_state               homography.py:491-500 (wrapper :858-859): fused a16 o a15. */
+int g3d_im_to_state(const void* pts, const void* heights, int in_is_f64, int64_t d, const double* H, int64_t ncam,
+                    const uint8_t* cam, int cam_const, int wrapper, float* out, int device, void* stream);
+
+/* a18 Homography.height_from_template      homography.py:519-551
+ * template_boxes[d,8,2], template_heights[d], boxes[d,8,2], each float32 or float64 (its *_is_f64 flag); every
+ * operand is evaluated in the dtype torch's type promotion would use; out[d] is float64 if any input is, else float32.
+ */
+int g3d_height_from_template(const void* template_boxes, int tb_is_f64, const void* template_heights, int th_is_f64,
+                             const void* boxes, int bx_is_f64, int64_t d, void* out, int device, void* stream);
+
+/* a17+a14+a18+a17: the trackers' two-pass height refinement idiom  MC3D_crop_tracker.py:364-370, :1222-1227;
+ * mot_evaluator.py:169-176; fit_filter_3D.py:262-266:
+ *   s0 = im_to_state(pts, h0); repro = state_to_im(s0); h1 = height_from_template(repro, h0, pts);
+ *   out = im_to_state(pts, h1).  P and H as above.  heights_out[d] (nullable) receives h1 (double).
+ */
+int g3d_im_to_state_refined(const void* pts, const void* heights, int in_is_f64, int64_t d, const double* H,
+                            const double* P, int64_t ncam, const uint8_t* cam, int cam_const, int wrapper,
+                            float* out, double* heights_out, int device, void* stream);
+
+/* a19 footprint box from state             MC3D_crop_tracker.py:625-632 (also :271-275,:498-502,:668-682)
+ * states[d,S] -> out[d,4] float32 (xmin,ymin,xmax,ymax of the 4 bottom corners of state_to_space).
+ */
+int g3d_state_footprint(const float* states, int64_t d, int64_t S, float* out, int device, void* stream);
+
+/* a19' image box from 8 corners            MC3D_crop_tracker.py:602-607 ; minimal_3D_track.py:505-510
+ * pts[d,8,2] float32/float64 -> out[d,4] same dtype (min x, min y, max x, max y).
+ */
+int g3d_corners_to_box(const void* pts, int is_f64, int64_t d, void* out, int device, void* stream);
+
+/* a20 md_iou, un-broadcast form            MC3D_crop_tracker.py:1030-1049 (callers :280,:689,:1013)
+ * first[n,4], second[m,4] float32 (promoted to float64 exactly as the callers' .double()) -> out[n,m] float64
+ * = IoU(first[i], second[j]) with NO epsilon (0/0 -> NaN) when eps == 0; eps is added to the union for the
+ * evaluator variant (mot_evaluator.py:115).  one_minus != 0 writes 1 - IoU (match_hungarian's cost, :689).
+ */
+int g3d_pairwise_iou_f64(const float* first, int64_t n, const float* second, int64_t m, double eps, int one_minus,
+                         double* out, int device, void* stream);
+/* a20 literal form: a[n,4], b[n,4] float64 element-wise -> out[n] (the reference signature with pre-broadcast inputs) */
+int g3d_md_iou(const double* a, const double* b, int64_t n, double* out, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOM3D_H */

@@ -1,0 +1,64 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """dict of torch tensors from tests/golden/<name>.npz"""
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = load_golden(name)
+        return cache[name]
+    return get
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, tiny) over all elements, in float64"""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float(((a - b).abs() / b.abs().clamp(min=1e-30)).max()) if a.numel() else 0.0
+
+
+def assert_close_rel(a, b, tol, what=""):
+    """|a-b| <= tol * max(|b|, scale) with scale = mean |b| (relative to the tensor's magnitude for near-zero entries)"""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    if a.numel() == 0:
+        return
+    scale = float(b.abs().mean())
+    bound = tol * torch.maximum(b.abs(), torch.full_like(b, scale))
+    bad = (a - b).abs() > bound
+    nan_mismatch = torch.isnan(a) != torch.isnan(b)
+    bad = (bad & ~torch.isnan(b)) | nan_mismatch
+    assert not bool(bad.any()), (f"{what}: {int(bad.sum())} of {a.numel()} elements differ by more than {tol:g} relative; "
+                                 f"worst |d|={float((a - b).abs()[~torch.isnan(a - b)].max()):.3e}")

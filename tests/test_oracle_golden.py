@@ -1,0 +1,166 @@
+"""CPU: the oracle (oracle/*.py) against vectors produced by the unmodified reference (tests/golden/make_golden.py).
+Index / integer / bit-pattern results must be identical; float results are compared at 1e-6 relative (the oracle uses
+the same ATen ops in the same order, so they are in fact bit-identical almost everywhere)."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import assert_close_rel
+from oracle import decode_oracle, homography_oracle as ho, losses_oracle as lo, nms_oracle, tracker_oracle
+
+
+@pytest.mark.parametrize("name", ["loss3d", "loss2d"])
+def test_losses_forward_backward(golden, name):
+    gd = golden(name)
+    three_d = name == "loss3d"
+    cls = gd["classification"].clone().requires_grad_(True)
+    reg = gd["regression"].clone().requires_grad_(True)
+    out = lo.focal_loss(cls, reg, gd["anchors"], gd["annotations"])
+    losses, info = out[:-1], out[-1]
+    assert len(losses) == (3 if three_d else 2)
+    got = torch.cat([l.detach() for l in losses])
+    assert_close_rel(got, gd["losses"], 1e-6, "losses")
+    for j, (iou_max, iou_arg, pos, neg, _) in enumerate(info):
+        assert torch.equal(iou_max, gd["iou_max"][j]), f"IoU_max image {j} not bit-exact"
+        assert torch.equal(iou_arg, gd["iou_argmax"][j]), f"IoU_argmax image {j}"
+    w = gd["grad_weights"]
+    sum(l.sum() * float(w[i]) for i, l in enumerate(losses)).backward()
+    assert_close_rel(cls.grad, gd["dcls"], 1e-5, "dcls")
+    assert_close_rel(reg.grad, gd["dreg"], 1e-5, "dreg")
+
+
+@pytest.mark.parametrize("name", ["loss3d", "loss2d"])
+def test_calc_iou_bit_exact(golden, name):
+    gd = golden(name)
+    ann = gd["annotations"][0]
+    rows = lo.valid_rows(ann[:, :21] if name == "loss3d" else ann, name == "loss3d")
+    b = rows[:, 16:20] if name == "loss3d" else rows[:, :4]
+    assert torch.equal(lo.calc_iou(gd["anchors"][0], b), gd["iou_matrix0"])
+
+
+def test_all_empty_batch_raises_like_reference():
+    anc = synth.anchors(64, 64)
+    cls, reg = synth.head_outputs(2, anc.shape[1], 8, 12, synth.gen(1))
+    ann = -torch.ones(2, 3, 27)
+    with pytest.raises(RuntimeError):
+        lo.focal_loss(cls, reg, anc, ann)
+
+
+def test_decode(golden):
+    gd = golden("decode")
+    assert torch.equal(decode_oracle.decode3d(gd["anchors"], gd["regression"]), gd["decoded3d"])
+    d2 = decode_oracle.decode2d(gd["anchors"], gd["deltas"])
+    assert torch.equal(d2, gd["decoded2d"])
+    h, w = gd["image_hw"].tolist()
+    assert torch.equal(decode_oracle.clip(d2, h, w), gd["clipped2d"])
+
+
+def test_nms(golden):
+    gd = golden("nms")
+    for thr in (0.5, 0.3, 0.1, 0.8, 0.2):
+        assert torch.equal(nms_oracle.nms(gd["boxes"], gd["scores"], thr), gd[f"keep_{thr}"]), f"thr {thr}"
+    assert torch.equal(nms_oracle.batched_nms(gd["boxes"], gd["scores"], gd["idxs"], 0.5), gd["keep_batched_0.5"])
+    assert torch.equal(nms_oracle.nms(gd["eq_boxes"], gd["eq_scores"], 0.5), gd["eq_keep_0.5"])
+    assert gd["eq_keep_0.5"].tolist() == [0, 1, 2]        # IoU == threshold is kept
+
+
+def test_nms_matches_installed_torchvision_random():
+    from torchvision.ops import nms as tv_nms
+    for seed in range(5):
+        b, s = synth.clustered_boxes(400, synth.gen(100 + seed))
+        s = (s * 20).round() / 20           # many ties
+        for thr in (0.5, 0.3):
+            assert torch.equal(nms_oracle.nms(b, s, thr), tv_nms(b, s, thr))
+
+
+def test_postprocess_3d(golden):
+    gd = golden("post3d")
+    h, w = gd["image_hw"].tolist()
+    anc = synth.anchors(h, w)
+    tr = decode_oracle.decode3d(anc, gd["regression"])
+    assert np.array_equal(synth.digest(tr), gd["loc_boxes_digest"].numpy())
+    s, c, b = nms_oracle.detect_3d(gd["classification"][:1], tr[:1])
+    assert torch.equal(s, gd["scores"]) and torch.equal(c, gd["classes"]) and torch.equal(b, gd["boxes"])
+    s, c, b, im = nms_oracle.detect_multi_frame(gd["classification"], tr)
+    assert torch.equal(s, gd["mf_scores"]) and torch.equal(c, gd["mf_classes"])
+    assert torch.equal(b, gd["mf_boxes"]) and torch.equal(im, gd["mf_im"])
+
+
+def test_postprocess_3d_dense_ladder(golden):
+    gd = golden("post3d")
+    h, w = gd["dense_hw"].tolist()
+    cls, reg = synth.dense_detection_inputs(int(gd["dense_seed"][0]), h, w)
+    tr = decode_oracle.decode3d(synth.anchors(h, w), reg)
+    s, c, b = nms_oracle.detect_3d(cls, tr)
+    assert np.array_equal(np.bincount(c.numpy(), minlength=8), gd["dense_count"].numpy())
+    assert np.array_equal(synth.digest(s), gd["dense_scores_digest"].numpy())
+    assert np.array_equal(synth.digest(b), gd["dense_boxes_digest"].numpy())
+
+
+def test_postprocess_2d(golden):
+    gd = golden("post2d")
+    h, w = gd["image_hw"].tolist()
+    tr = decode_oracle.clip(decode_oracle.decode2d(synth.anchors(h, w), gd["regression"]), h, w)
+    s, c, b = nms_oracle.detect_2d(gd["classification"], tr)
+    assert torch.equal(s, gd["scores"]) and torch.equal(c, gd["classes"]) and torch.equal(b, gd["boxes"])
+
+
+def test_ladder_rungs_are_float32_casts_of_repeated_products():
+    mask, last = nms_oracle.ladder_threshold(torch.tensor([0.5, 0.2, 0.9]), 1e-25, keep=1)
+    assert mask.tolist() == [False, False, True]
+    t = 1e-25
+    while np.float32(t) != last:
+        t *= 10 ** .2
+    assert 0.5 <= t < 0.9
+
+
+def test_homography_csv_rows(golden):
+    """the reference's own stored outputs: 3D_tracking_results.csv"""
+    gd = golden("homography")
+    st = gd["csv_states"]
+    space = ho.state_to_space(st)
+    assert torch.equal(space[:, :4, :2].reshape(-1, 8), gd["csv_space"]), "state_to_space vs CSV cols 27-34 (bit-exact)"
+    im = ho.wrapper_state_to_im(st, gd["csv_P_lo"], gd["csv_P_hi"])
+    # the CSV stores states printed as float32 and P is a DLT fit: agreement to ~1e-6 relative
+    assert_close_rel(im, gd["csv_im"], 5e-6, "state_to_im vs CSV cols 11-26")
+
+
+def test_homography_transforms(golden):
+    gd = golden("homography")
+    P, H = gd["P"].numpy(), gd["H"].numpy()
+    st, cam = gd["states"], gd["cam"].long()
+    assert torch.equal(ho.state_to_space(st), gd["space"])
+    tol = 1e-12
+    assert_close_rel(ho.state_to_im(st, P[1, 0]), gd["im_single"], tol, "state_to_im single")
+    Pl = torch.from_numpy(P)[cam]
+    assert_close_rel(ho.state_to_im(st, Pl[:, 0]), gd["im_list"], tol, "state_to_im list")
+    assert_close_rel(ho.wrapper_state_to_im(st, Pl[:, 0], Pl[:, 1]), gd["im_wrapper_list"], tol, "wrapper list")
+    assert_close_rel(ho.wrapper_state_to_im(st, P[2, 0], P[2, 1]), gd["im_wrapper_single"], tol, "wrapper single")
+    assert_close_rel(ho.wrapper_space_to_im(gd["space"], Pl[:, 0], Pl[:, 1]), gd["space_to_im_f32pts"], tol, "space_to_im")
+    det, hts = gd["det"], gd["heights"]
+    Hl = torch.from_numpy(H)[cam]
+    assert_close_rel(ho.im_to_space(det, Hl[:, 0], hts), gd["space_from_im_list"], tol, "im_to_space list")
+    assert_close_rel(ho.wrapper_im_to_space(det, Hl[:, 0], Hl[:, 1], hts), gd["space_from_im_wrapper"], tol, "im_to_space wrapper")
+    assert_close_rel(ho.im_to_state(det, H[1, 0], hts), gd["state_single"], 1e-6, "im_to_state single")
+    assert_close_rel(ho.im_to_state(det, Hl[:, 0], hts), gd["state_list"], 1e-6, "im_to_state list")
+    assert_close_rel(ho.wrapper_im_to_state(det, Hl[:, 0], Hl[:, 1], hts), gd["state_wrapper_list"], 1e-6, "im_to_state wrapper")
+    assert torch.equal(ho.space_to_state(gd["space_from_im_list"]), gd["state_from_space"])
+    assert torch.equal(ho.space_to_state(gd["space"]), gd["state_from_space_f32"])
+    s1, h1 = ho.refined_im_to_state(det, Hl[:, 0], Hl[:, 1], Pl[:, 0], Pl[:, 1], hts)
+    assert_close_rel(h1, gd["hft_f64_f32_f32"], 1e-9, "refined heights")
+    assert_close_rel(s1, gd["state_refined"], 1e-6, "refined state")
+
+
+def test_tracker(golden):
+    gd = golden("tracker")
+    st, sec, sc = gd["states"], gd["second"], gd["scores"]
+    assert torch.equal(tracker_oracle.footprint(st), gd["footprint"])
+    cost = tracker_oracle.association_cost(st, sec)
+    assert torch.equal(cost, gd["cost"])
+    assert torch.isnan(tracker_oracle.md_iou(torch.ones(1, 1, 4, dtype=torch.float64), torch.ones(1, 1, 4, dtype=torch.float64))).all()
+    assert torch.isnan(gd["md_iou_degenerate"]).all()
+    assert torch.equal(tracker_oracle.space_nms(st, sc, 0.1), gd["space_nms_0_1"])
+    assert torch.equal(tracker_oracle.space_nms(st, sc, 0.4), gd["space_nms_0_4"])
+    assert torch.equal(tracker_oracle.im_nms(gd["corners"], sc, 0.3), gd["im_nms_0_3"])
+    assert torch.equal(tracker_oracle.im_nms(gd["corners"], sc, 0.3, groups=torch.zeros(120)), gd["im_nms_groups"])
