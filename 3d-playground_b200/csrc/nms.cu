@@ -15,7 +15,7 @@ namespace g3d {
 
 constexpr int kNmsThreads = 1024;
 constexpr int kSortCap = 16384;        // longest segment the single-CTA shared-memory sort handles
-constexpr int kSmemBoxCap = 8192;      // longest segment whose sorted boxes are cached in shared memory
+constexpr int kSmemBoxCap = 4096;      // longest segment whose sorted boxes are cached in shared memory
 constexpr int kLocalSort = 4096;       // tile of the multi-CTA (global) bitonic sort
 
 __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
@@ -137,7 +137,6 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-template <bool SMEM_BOXES>
 __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* __restrict__ sbox,
                                                                  const int32_t* __restrict__ sidx,
                                                                  const int32_t* __restrict__ seg_offsets, float thr,
@@ -145,8 +144,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
                                                                  int64_t* __restrict__ keep_out,
                                                                  int32_t* __restrict__ keep_count) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    float4* cbox = reinterpret_cast<float4*>(dyn);  // [box_cap] when SMEM_BOXES
-    uint32_t* removed = reinterpret_cast<uint32_t*>(dyn + (SMEM_BOXES ? sizeof(float4) * box_cap : 0));
+    float4* cbox = reinterpret_cast<float4*>(dyn);  // [box_cap]: sorted boxes of segments with n <= box_cap
+    uint32_t* removed = reinterpret_cast<uint32_t*>(dyn + sizeof(float4) * box_cap);
     __shared__ float4 dbox[64];
     __shared__ float darea[64];
     __shared__ uint64_t diag[64];
@@ -162,9 +161,14 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
         return;
     }
     const float4* gbox = sbox + off;
-    for (int i = tid; i < removed_words; i += kNmsThreads) removed[i] = 0u;
-    if (SMEM_BOXES)
+    const int my_words = 2 * ((n + 63) >> 6);
+    for (int i = tid; i < my_words; i += kNmsThreads) removed[i] = 0u;
+    // short segments keep their boxes in shared memory; long ones stream them from L2 (generic pointer)
+    const float4* bsrc = gbox;
+    if (n <= box_cap) {
         for (int i = tid; i < n; i += kNmsThreads) cbox[i] = gbox[i];
+        bsrc = cbox;
+    }
     __syncthreads();
 
     int total_kept = 0;
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
         const uint64_t remword = ((uint64_t)removed[2 * blk + 1] << 32) | removed[2 * blk];
         if ((remword & mmask) == mmask) continue;  // whole block already suppressed (uniform across the CTA)
         if (tid < m) {
-            const float4 b = SMEM_BOXES ? cbox[base + tid] : gbox[base + tid];
+            const float4 b = bsrc[base + tid];
             dbox[tid] = b;
             darea[tid] = box_area_rn(b.x, b.y, b.z, b.w);
         }
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
         if (kc > 0) {
             for (int j = base + 64 + tid; j < n; j += kNmsThreads) {
                 if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
-                const float4 bj = SMEM_BOXES ? cbox[j] : gbox[j];
+                const float4 bj = bsrc[j];
                 const float aj = box_area_rn(bj.x, bj.y, bj.z, bj.w);
                 for (int k = 0; k < kc; ++k) {
                     if (iou_torchvision(kbox[k], karea[k], bj, aj) > thr) {
@@ -332,19 +336,12 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
         G3D_LAUNCH_CHECK();
     }
     const int removed_words = (int)(2 * ceil_div(max_seg_len, 64));
-    if (max_seg_len <= kSmemBoxCap) {
-        const int box_cap = (int)max_seg_len;
-        const size_t smem = sizeof(float4) * box_cap + (size_t)removed_words * 4;
-        G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_greedy_kernel<true><<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative,
-                                                                       removed_words, box_cap, keep_out, keep_count);
-    } else {
-        const size_t smem = (size_t)removed_words * 4;
-        G3D_REQUIRE(smem <= 200 * 1024, "segment too long for the shared-memory suppression bitset (max ~1.6M boxes)");
-        G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        nms_greedy_kernel<false><<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative,
-                                                                        removed_words, 0, keep_out, keep_count);
-    }
+    const int box_cap = (int)(max_seg_len < kSmemBoxCap ? max_seg_len : kSmemBoxCap);
+    const size_t smem = sizeof(float4) * box_cap + (size_t)removed_words * 4;
+    G3D_REQUIRE(smem <= 220 * 1024, "segment too long for the shared-memory suppression bitset (max ~1.2M boxes)");
+    G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nms_greedy_kernel<<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative, removed_words,
+                                                              box_cap, keep_out, keep_count);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }
