@@ -50,12 +50,14 @@ def rel_err(a, b):
 
 
 def assert_close_rel(a, b, tol, what=""):
-    """|a-b| <= tol * max(|b|, scale) with scale = mean |b| (relative to the tensor's magnitude for near-zero entries)"""
+    """|a-b| <= tol * max(|b|, scale), scale = mean |b| over the non-zero entries: element-wise relative error, except
+    that entries far below the tensor's typical magnitude (sums with cancellation) are judged against that magnitude"""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
     if a.numel() == 0:
         return
-    scale = float(b.abs().mean())
+    nz = b[(b != 0) & ~torch.isnan(b)]
+    scale = float(nz.abs().mean()) if nz.numel() else 0.0
     bound = tol * torch.maximum(b.abs(), torch.full_like(b, scale))
     bad = (a - b).abs() > bound
     nan_mismatch = torch.isnan(a) != torch.isnan(b)
