@@ -74,8 +74,18 @@ __device__ __forceinline__ void tile_argmax(const float4& an, float area_a, cons
         __syncthreads();
 #pragma unroll 2
         for (int k = 0; k < total; ++k) {
-            const float v = iou_retinanet(an, area_a, sm.box[k], sm.area[k]);
-            if (v > best) { best = v; besti = sm.idx[k]; }
+            const float4 gk = sm.box[k];
+            const float iw = __fsub_rn(fminf(an.z, gk.z), fmaxf(an.x, gk.x));
+            const float ih = __fsub_rn(fminf(an.w, gk.w), fmaxf(an.y, gk.y));
+            // iw <= 0 or ih <= 0 -> the clamped intersection is 0 -> IoU == +0.0 exactly, which can never beat `best`
+            // under the strict '>' rule: skip the union / IEEE division (most survivors of the tile-level cull are
+            // still disjoint from most anchors of the tile)
+            if (iw > 0.0f && ih > 0.0f) {
+                const float inter = __fmul_rn(iw, ih);
+                const float ua = fmaxf(__fsub_rn(__fadd_rn(area_a, sm.area[k]), inter), 1e-8f);
+                const float v = __fdiv_rn(inter, ua);
+                if (v > best) { best = v; besti = sm.idx[k]; }
+            }
         }
     }
 }

@@ -48,12 +48,24 @@ __device__ __forceinline__ float focal_term(float p_raw, bool t) {
     return w * (-logf(x));
 }
 
-// d(focal term)/dp, zero outside the clamp range (torch.clamp backward passes min <= x <= max)
-__device__ __forceinline__ float focal_term_grad(float p_raw, bool t) {
-    if (!(p_raw >= G3D_PMIN && p_raw <= G3D_PMAX)) return 0.0f;
-    const float p = p_raw, u = 1.0f - p;
-    if (t) return 0.5f * u * logf(p) - 0.25f * (u * u) / p;
-    return -1.5f * p * logf(u) + 0.75f * (p * p) / u;
+// focal term of a negative anchor (target 0 for every class): 0.75 p^2 * -log(1-p)
+__device__ __forceinline__ float focal_term_neg(float p_raw) {
+    const float p = fminf(fmaxf(p_raw, G3D_PMIN), G3D_PMAX);
+    return (0.75f * (p * p)) * (-logf(1.0f - p));
+}
+
+// d(focal term)/dp, zero outside the clamp range (torch.clamp backward passes min <= x <= max).
+// The two quotients use the 2-ulp fast division: gradients are compared at 1e-5 relative, nothing is index-critical.
+__device__ __forceinline__ float focal_term_grad_neg(float p) {
+    if (!(p >= G3D_PMIN && p <= G3D_PMAX)) return 0.0f;
+    const float u = 1.0f - p;
+    return -1.5f * p * logf(u) + __fdividef(0.75f * (p * p), u);
+}
+__device__ __forceinline__ float focal_term_grad(float p, bool t) {
+    if (!t) return focal_term_grad_neg(p);
+    if (!(p >= G3D_PMIN && p <= G3D_PMAX)) return 0.0f;
+    const float u = 1.0f - p;
+    return 0.5f * u * logf(p) - __fdividef(0.25f * (u * u), p);
 }
 
 __device__ __forceinline__ float smooth_l1(float d) {
@@ -99,7 +111,7 @@ __device__ __forceinline__ void pred_corners(const float* r, float* p /*20*/) {
 }
 
 // 3D positive anchor: sum of the 20 smooth-L1 terms and the mean of the three cosine losses (losses.py:156-350)
-__device__ __forceinline__ void positive_terms_3d(const float* __restrict__ rrow, const float* __restrict__ grow,
+__device__ __noinline__ void positive_terms_3d(const float* __restrict__ rrow, const float* __restrict__ grow,
                                                   const float4& an, float& reg_sum, float& vp_term) {
     float r[12], t[20], p[20], tv[6];
 #pragma unroll
@@ -148,38 +160,197 @@ __device__ __forceinline__ double block_sum(double v, double* s) {
     return t;
 }
 
+// Shared state of one CTA of the forward kernel: the culled GT lists of its kImgPerCta images (staged once, behind two
+// barriers); everything after that is warp-private - no barrier per image and none at the end: the last warp of the
+// CTA to finish (shared-memory ticket) combines the 8 warp partials.
+struct FwdSmem {
+    float4 box[kImgPerCta][kTile];
+    float area[kImgPerCta][kTile];
+    int idx[kImgPerCta][kTile];
+    float bbred[4][kWarps];
+    int wcount[kImgPerCta][kWarps];
+    double dred[kImgPerCta][3][kWarps];
+    int nred[kImgPerCta][kWarps];
+    int total[kImgPerCta];
+    int arrive;
+};
+
+// Executed by ONE warp - the last tile of image b: reduce the image's T partials in a fixed order (lane-strided
+// accumulation + shuffle tree), then (last image of the batch) the batch means.
+template <int VARIANT>
+__device__ __forceinline__ void finalize_image(const FocalArgs& p, int b) {
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    double tc = 0.0, tn = 0.0, tr = 0.0, tv = 0.0;
+    const double2* src = reinterpret_cast<const double2*>(p.partials + (int64_t)b * p.T * 4);
+#pragma unroll 4
+    for (int t = lane; t < p.T; t += 32) {
+        const double2 u = __ldcg(src + 2 * t), v = __ldcg(src + 2 * t + 1);
+        tc += u.x; tn += u.y; tr += v.x; tv += v.y;
+    }
+    tc = warp_sum(tc); tn = warp_sum(tn); tr = warp_sum(tr); tv = warp_sum(tv);
+    int last = 0;
+    if (lane == 0) {
+        const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
+        float4 o;
+        o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
+        o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
+        o.z = tn > 0.0 ? (float)(tv / tn) : 0.0f;              // vp_loss.mean() (:304)
+        o.w = (float)tn;
+        __stcg(reinterpret_cast<float4*>(p.per_image) + b, o);
+        __threadfence();
+        last = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        // last image: batch means (losses.py:362).  vp: only images with >= 1 GT row contribute (:304,:353-358)
+        __threadfence();
+        double sc = 0.0, sr = 0.0, sv = 0.0, ne = 0.0;
+        for (int j = lane; j < p.B; j += 32) {
+            const float4 o = __ldcg(reinterpret_cast<const float4*>(p.per_image) + j);
+            sc += o.x; sr += o.y;
+            if (__ldg(p.gt_count + j) > 0) { sv += o.z; ne += 1.0; }
+        }
+        sc = warp_sum(sc); sr = warp_sum(sr); sv = warp_sum(sv); ne = warp_sum(ne);
+        if (lane == 0) {
+            p.losses[0] = (float)(sc / p.B);
+            p.losses[1] = (float)(sr / p.B);
+            p.losses[2] = (VARIANT == G3D_VARIANT_3D) ? (float)(sv / ne) : 0.0f;  // 0/0 -> NaN when all empty
+            p.losses[3] = (float)ne;
+        }
+    }
+}
+
 template <int VARIANT, int CS>
-__global__ void __launch_bounds__(kTile) focal_fwd_kernel(const FocalArgs p) {
-    __shared__ TileSmem sm;
-    __shared__ double s_red[3][kWarps];
-    __shared__ int s_np[kWarps];
-    __shared__ int s_last;
+__global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) {
+    __shared__ FwdSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a = blockIdx.x * kTile + tid;
     const bool valid = a < p.A;
     float4 an = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) an = __ldg(p.anchors + a);
     const float area_a = box_area_rn(an.x, an.y, an.z, an.w);
-    const float4 bb = tile_bbox(an, valid, sm);
     const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
     const int C = (CS > 0) ? CS : p.C;
+    const int b0 = blockIdx.y * kImgPerCta;
+    const int nimg = min(kImgPerCta, p.B - b0);
+    if (tid == 0) sm.arrive = 0;
 
-    const int b_end = min(p.B, (int)(blockIdx.y + 1) * kImgPerCta);
-    for (int b = blockIdx.y * kImgPerCta; b < b_end; ++b) {
+    // ---- bounding boxes of the warp's and of the tile's anchors (one barrier)
+    float4 wb, bb;
+    {
+        float mnx = valid ? an.x : INFINITY, mny = valid ? an.y : INFINITY;
+        float mxx = valid ? an.z : -INFINITY, mxy = valid ? an.w : -INFINITY;
+        mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
+        wb = make_float4(mnx, mny, mxx, mxy);
+        if (lane == 0) { sm.bbred[0][warp] = mnx; sm.bbred[1][warp] = mny; sm.bbred[2][warp] = mxx; sm.bbred[3][warp] = mxy; }
+        __syncthreads();
+        bb = make_float4(sm.bbred[0][0], sm.bbred[1][0], sm.bbred[2][0], sm.bbred[3][0]);
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) {
+            bb.x = fminf(bb.x, sm.bbred[0][w]); bb.y = fminf(bb.y, sm.bbred[1][w]);
+            bb.z = fmaxf(bb.z, sm.bbred[2][w]); bb.w = fmaxf(bb.w, sm.bbred[3][w]);
+        }
+    }
+
+    // ---- stage the GT boxes of the group's images: cull against the tile bounding box with an ordered compaction
+    // (ascending GT index), all images behind the same two barriers.  An image with more than kTile GT rows keeps its
+    // first kTile candidates here and is finished by the (rare) overflow loop further down.
+    {
+        const int g = tid;
+        float4 gb[kImgPerCta];
+        unsigned bal[kImgPerCta];
+#pragma unroll
+        for (int i = 0; i < kImgPerCta; ++i) {
+            bool hit = false;
+            gb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int Gi = (i < nimg) ? __ldg(p.gt_count + b0 + i) : 0;
+            if (g < Gi) {
+                gb[i] = __ldg(p.gt_box + (int64_t)(b0 + i) * p.Gmax + g);
+                // keep unless provably disjoint from every anchor of the tile (NaN coordinates are never culled)
+                hit = !(gb[i].z <= bb.x || gb[i].x >= bb.z || gb[i].w <= bb.y || gb[i].y >= bb.w);
+            }
+            bal[i] = __ballot_sync(0xffffffffu, hit);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < kImgPerCta; ++i) sm.wcount[i][warp] = __popc(bal[i]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kImgPerCta; ++i) {
+            int off = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int c = sm.wcount[i][w];
+                off += (w < warp) ? c : 0;
+                tot += c;
+            }
+            if (tid == 0) sm.total[i] = tot;
+            if ((bal[i] >> lane) & 1u) {
+                const int pos = off + __popc(bal[i] & ((1u << lane) - 1u));
+                sm.box[i][pos] = gb[i];
+                sm.area[i][pos] = box_area_rn(gb[i].x, gb[i].y, gb[i].z, gb[i].w);
+                sm.idx[i][pos] = g;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per image (a real loop: the body is large, unrolling it thrashes the instruction cache): IoU max/argmax over
+    // the staged survivors, classify the anchor, focal terms, positive terms, warp-level partial sums.  No barriers.
+#pragma unroll 1
+    for (int i = 0; i < nimg; ++i) {
+        const int b = b0 + i;
         const int64_t row = (int64_t)b * p.A + a;
-        // issue the classification loads first so they are in flight during the IoU search
+        // request the classification row first: it is in flight during the IoU search
         float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
         if (CS == 8 && valid) {
             const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
             c0 = ld_stream(cp);
             c1 = ld_stream(cp + 1);
         }
-        const int G = __ldg(p.gt_count + b);
+        const int Gi = __ldg(p.gt_count + b);
         float best = 0.0f;
         int besti = 0;
-        tile_argmax(an, area_a, bb, p.gt_box + (int64_t)b * p.Gmax, G, sm, best, besti);
+        const int total = sm.total[i];
+        for (int k0 = 0; k0 < total; k0 += 32) {
+            // warp-level refinement: which of these (up to 32) tile survivors can touch this warp's anchors at all?
+            bool near = false;
+            if (k0 + lane < total) {
+                const float4 t = sm.box[i][k0 + lane];
+                near = !(t.z <= wb.x || t.x >= wb.z || t.w <= wb.y || t.y >= wb.w);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, near);
+            while (m) {
+                const int k = k0 + __ffs(m) - 1;
+                m &= m - 1;
+                const float4 gk = sm.box[i][k];
+                const float iw = __fsub_rn(fminf(an.z, gk.z), fmaxf(an.x, gk.x));
+                const float ih = __fsub_rn(fminf(an.w, gk.w), fmaxf(an.y, gk.y));
+                // a disjoint pair has IoU == +0.0 exactly and can never beat `best` under the strict '>' rule
+                if (iw > 0.0f && ih > 0.0f) {
+                    const float inter = __fmul_rn(iw, ih);
+                    const float ua = fmaxf(__fsub_rn(__fadd_rn(area_a, sm.area[i][k]), inter), 1e-8f);
+                    const float v = __fdiv_rn(inter, ua);
+                    if (v > best) { best = v; besti = sm.idx[i][k]; }
+                }
+            }
+        }
+        // overflow: GT rows beyond the first kTile of this image, straight from global memory (warp-uniform loop)
+        for (int g = kTile; g < Gi; ++g) {
+            const float4 gk = __ldg(p.gt_box + (int64_t)b * p.Gmax + g);
+            const float iw = __fsub_rn(fminf(an.z, gk.z), fmaxf(an.x, gk.x));
+            const float ih = __fsub_rn(fminf(an.w, gk.w), fmaxf(an.y, gk.y));
+            if (iw > 0.0f && ih > 0.0f) {
+                const float inter = __fmul_rn(iw, ih);
+                const float ua = fmaxf(__fsub_rn(__fadd_rn(area_a, box_area_rn(gk.x, gk.y, gk.z, gk.w)), inter), 1e-8f);
+                const float v = __fdiv_rn(inter, ua);
+                if (v > best) { best = v; besti = g; }
+            }
+        }
         int code = G3D_ASSIGN_NEGATIVE;
-        if (G > 0) code = assign_code(best, besti, p.gt_row + (int64_t)b * p.Gmax);
+        if (Gi > 0) code = assign_code(best, besti, p.gt_row + (int64_t)b * p.Gmax);
         if (!valid) code = G3D_ASSIGN_IGNORE;
         if (p.assign && valid) p.assign[row] = code;
 
@@ -193,8 +364,13 @@ __global__ void __launch_bounds__(kTile) focal_fwd_kernel(const FocalArgs p) {
         if (code != G3D_ASSIGN_IGNORE) {
             if (CS == 8) {
                 const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                if (code == G3D_ASSIGN_NEGATIVE) {  // the overwhelmingly common case: no per-class selects
 #pragma unroll
-                for (int c = 0; c < 8; ++c) cls_acc += focal_term(pv[c], c == pos_cls);
+                    for (int c = 0; c < 8; ++c) cls_acc += focal_term_neg(pv[c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) cls_acc += focal_term(pv[c], c == pos_cls);
+                }
             } else {
                 const float* cp = p.cls + row * C;
                 for (int c = 0; c < C; ++c) cls_acc += focal_term(__ldg(cp + c), c == pos_cls);
@@ -208,82 +384,51 @@ __global__ void __launch_bounds__(kTile) focal_fwd_kernel(const FocalArgs p) {
                 float t[4];
                 targets_2d(grow, an, t);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) reg_acc += smooth_l1(fabsf(t[i] - rrow[i]));
+                for (int j = 0; j < 4; ++j) reg_acc += smooth_l1(fabsf(t[j] - rrow[j]));
             }
         }
-        // ---- block reduction (FP64), one partial per (image, tile)
-        const int any_pos = __syncthreads_or(code >= 0);
         const double cs = warp_sum((double)cls_acc);
-        if (lane == 0) s_red[0][warp] = cs;
-        if (any_pos) {
-            const int np = warp_sum(code >= 0 ? 1 : 0);
-            const double rs = warp_sum((double)reg_acc), vs = warp_sum((double)vp_acc);
-            if (lane == 0) { s_np[warp] = np; s_red[1][warp] = rs; s_red[2][warp] = vs; }
+        const unsigned posmask = __ballot_sync(0xffffffffu, code >= 0);
+        double rs = 0.0, vs = 0.0;
+        if (posmask) {
+            rs = warp_sum((double)reg_acc);
+            vs = warp_sum((double)vp_acc);
         }
-        __syncthreads();
-        if (tid == 0) {
-            double tc = 0.0, tr = 0.0, tv = 0.0;
-            int tn = 0;
+        if (lane == 0) {
+            sm.dred[i][0][warp] = cs; sm.dred[i][1][warp] = rs; sm.dred[i][2][warp] = vs;
+            sm.nred[i][warp] = __popc(posmask);
+        }
+    }
+    // ---- the last warp of the CTA to get here combines the warp partials: one partial per (image, tile); the last
+    // tile of an image (global ticket) reduces that image.  No block barrier: finished warps retire immediately.
+    int arrived = 0;
+    if (lane == 0) {
+        __threadfence_block();
+        arrived = atomicAdd(&sm.arrive, 1);
+    }
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != kWarps - 1) return;
+    __threadfence_block();
+    int is_last = 0;
+    if (lane < nimg) {
+        const int i = lane, b = b0 + i;
+        const volatile double* dr = &sm.dred[i][0][0];
+        const volatile int* nr = &sm.nred[i][0];
+        double tc = 0.0, tr = 0.0, tv = 0.0;
+        int tn = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) tc += s_red[0][w];
-            if (any_pos) {
-#pragma unroll
-                for (int w = 0; w < kWarps; ++w) { tn += s_np[w]; tr += s_red[1][w]; tv += s_red[2][w]; }
-            }
-            double* out = p.partials + ((int64_t)b * p.T + blockIdx.x) * 4;
-            __stcg(reinterpret_cast<double2*>(out), make_double2(tc, (double)tn));
-            __stcg(reinterpret_cast<double2*>(out) + 1, make_double2(tr, tv));
-            __threadfence();
-            s_last = (atomicAdd(p.counters + b, 1) == p.T - 1);
-        }
-        __syncthreads();
-        if (s_last) {
-            // last tile of image b: reduce its T partials in a fixed order
-            __threadfence();
-            double tc = 0.0, tn = 0.0, tr = 0.0, tv = 0.0;
-            const double2* src = reinterpret_cast<const double2*>(p.partials + (int64_t)b * p.T * 4);
-            for (int t = tid; t < p.T; t += kTile) {
-                const double2 u = __ldcg(src + 2 * t), v = __ldcg(src + 2 * t + 1);
-                tc += u.x; tn += u.y; tr += v.x; tv += v.y;
-            }
-            tc = block_sum(tc, s_red[0]);
-            tn = block_sum(tn, s_red[0]);
-            tr = block_sum(tr, s_red[0]);
-            tv = block_sum(tv, s_red[0]);
-            if (tid == 0) {
-                const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
-                float4 o;
-                o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
-                o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
-                o.z = tn > 0.0 ? (float)(tv / tn) : 0.0f;              // vp_loss.mean() (:304)
-                o.w = (float)tn;
-                __stcg(reinterpret_cast<float4*>(p.per_image) + b, o);
-                __threadfence();
-                s_last = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
-            }
-            __syncthreads();
-            if (s_last) {
-                // last image: batch means (losses.py:362).  vp: only images with >= 1 GT row contribute (:304,:353-358)
-                __threadfence();
-                double sc = 0.0, sr = 0.0, sv = 0.0, ne = 0.0;
-                for (int j = tid; j < p.B; j += kTile) {
-                    const float4 o = __ldcg(reinterpret_cast<const float4*>(p.per_image) + j);
-                    sc += o.x; sr += o.y;
-                    if (__ldg(p.gt_count + j) > 0) { sv += o.z; ne += 1.0; }
-                }
-                sc = block_sum(sc, s_red[0]);
-                sr = block_sum(sr, s_red[0]);
-                sv = block_sum(sv, s_red[0]);
-                ne = block_sum(ne, s_red[0]);
-                if (tid == 0) {
-                    p.losses[0] = (float)(sc / p.B);
-                    p.losses[1] = (float)(sr / p.B);
-                    p.losses[2] = (VARIANT == G3D_VARIANT_3D) ? (float)(sv / ne) : 0.0f;  // 0/0 -> NaN when all empty
-                    p.losses[3] = (float)ne;
-                }
-            }
-        }
-        __syncthreads();  // s_red / s_last are reused by the next image
+        for (int w = 0; w < kWarps; ++w) { tc += dr[w]; tr += dr[kWarps + w]; tv += dr[2 * kWarps + w]; tn += nr[w]; }
+        double* out = p.partials + ((int64_t)b * p.T + blockIdx.x) * 4;
+        __stcg(reinterpret_cast<double2*>(out), make_double2(tc, (double)tn));
+        __stcg(reinterpret_cast<double2*>(out) + 1, make_double2(tr, tv));
+        __threadfence();
+        is_last = (atomicAdd(p.counters + b, 1) == p.T - 1);
+    }
+    unsigned lastmask = __ballot_sync(0xffffffffu, is_last);
+    while (lastmask) {
+        const int i = __ffs(lastmask) - 1;
+        lastmask &= lastmask - 1;
+        finalize_image<VARIANT>(p, b0 + i);
     }
 }
 
@@ -303,7 +448,7 @@ struct FocalBwdArgs {
 };
 
 template <int VARIANT, int CS>
-__global__ void __launch_bounds__(256) focal_bwd_kernel(const FocalBwdArgs p) {
+__global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const FocalBwdArgs p) {
     const int b = blockIdx.y;
     const int a = blockIdx.x * 256 + threadIdx.x;
     if (a >= p.A) return;
@@ -324,9 +469,14 @@ __global__ void __launch_bounds__(256) focal_bwd_kernel(const FocalBwdArgs p) {
         float4 c0 = ld_stream(cp), c1 = ld_stream(cp + 1);
         float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         float g[8];
+        if (code == G3D_ASSIGN_NEGATIVE) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+            for (int c = 0; c < 8; ++c) g[c] = s_cls * focal_term_grad_neg(pv[c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+        }
         float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
         st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
         st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));

@@ -91,30 +91,72 @@ __global__ void __launch_bounds__(256) space_to_im_kernel(const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------- a14 state_to_im
-// thread per (state, [camera,] corner): stores of a warp are contiguous (16 B per lane, FP64 parity output).
-template <typename OUT2>
-__global__ void __launch_bounds__(256) state_to_im_kernel(const float* __restrict__ states, int64_t d, int64_t S,
-                                                          const double* __restrict__ P, int ncam,
-                                                          const uint8_t* __restrict__ cam, int cam_const, int wrapper,
-                                                          int all_cams, OUT2* __restrict__ out) {
-    extern __shared__ double s_m[];
+// One thread per (state[, camera]).  P.[X,Y,Z,1] is affine in the corner signs, so the three rows are assembled from
+// shared partial products (2 x-terms, 2 y-terms, 1 z-term) instead of 8 full 3x4 products; each corner then costs one
+// FP64 reciprocal and two multiplies.  The 8 (u,v) pairs of a thread are staged through shared memory with an XOR
+// swizzle (conflict-free 16-byte stores at a 128-byte lane stride) so that every warp store covers whole 128-byte
+// output rows: the kernel is bound by the 128 B/state it has to write.
+constexpr int kS2IThreads = 256;
+
+template <typename OUT2, bool ALL_CAMS>
+__global__ void __launch_bounds__(kS2IThreads, 4) state_to_im_kernel(const float* __restrict__ states, int64_t d, int64_t S,
+                                                                  const double* __restrict__ P, int ncam,
+                                                                  const uint8_t* __restrict__ cam, int cam_const,
+                                                                  int wrapper, OUT2* __restrict__ out) {
+    extern __shared__ __align__(16) double s_m[];
+    const int mat_doubles = (ncam * 24 + 1) & ~1;                 // keep the staging area 16-byte aligned
+    OUT2* stage = reinterpret_cast<OUT2*>(s_m + mat_doubles) + (threadIdx.x & ~31) * 8;   // this warp's 256 slots
     stage_mats(s_m, P, ncam * 24);
-    const int64_t per_state = all_cams ? (int64_t)ncam * 8 : 8;
-    const int64_t total = d * per_state;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t obj = i / per_state;
-        const int rem = (int)(i - obj * per_state);
-        const int k = rem & 7;
-        const int c = all_cams ? (rem >> 3) : (cam ? (int)__ldg(cam + obj) : cam_const);
-        const StateF s = load_state(states, S, obj);
-        int sel = 0;
-        if (wrapper) sel = (space_y(s, 0) > 60.0f) ? 1 : 0;
-        double u, v;
-        project(s_m + (c * 2 + sel) * 12, (double)space_x(s, k), (double)space_y(s, k), (double)space_z(s, k), u, v);
-        OUT2 o;
-        o.x = u;
-        o.y = v;
-        out[i] = o;
+    const int lane = threadIdx.x & 31;
+    const int64_t items = ALL_CAMS ? d * ncam : d;
+    const int64_t stride = (int64_t)gridDim.x * kS2IThreads;
+    for (int64_t base = (int64_t)blockIdx.x * kS2IThreads + (threadIdx.x & ~31); base < items; base += stride) {
+        const int64_t item = base + lane;
+        if (item < items) {
+            int64_t obj = item;
+            int c;
+            if (ALL_CAMS) {
+                if (items < (int64_t)0x7fffffff) { obj = (uint32_t)item / (uint32_t)ncam; c = (int)((uint32_t)item - (uint32_t)obj * ncam); }
+                else { obj = item / ncam; c = (int)(item - obj * ncam); }
+            } else {
+                c = cam ? (int)__ldg(cam + obj) : cam_const;
+            }
+            const StateF s = load_state(states, S, obj);
+            const float ylo = space_y(s, 0), yhi = space_y(s, 1);
+            const double xf = (double)space_x(s, 0), xb = (double)s.x, y0 = (double)ylo, y1 = (double)yhi, z = (double)(-s.h);
+            const int sel = (wrapper && ylo > 60.0f) ? 1 : 0;      // points[:,0,1] > 60 (homography.py:854)
+            const double* M = s_m + (c * 2 + sel) * 12;
+            double ax[2][3], by[2][3], cz[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                ax[0][r] = M[4 * r] * xf;
+                ax[1][r] = M[4 * r] * xb;
+                by[0][r] = fma(M[4 * r + 1], y0, M[4 * r + 3]);
+                by[1][r] = fma(M[4 * r + 1], y1, M[4 * r + 3]);
+                cz[r] = M[4 * r + 2] * z;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int ix = (k >> 1) & 1, iy = k & 1;
+                double v0 = ax[ix][0] + by[iy][0], v1 = ax[ix][1] + by[iy][1], v2 = ax[ix][2] + by[iy][2];
+                if (k & 4) { v0 += cz[0]; v1 += cz[1]; v2 += cz[2]; }
+                const double inv = 1.0 / v2;
+                OUT2 o;
+                o.x = v0 * inv;
+                o.y = v1 * inv;
+                stage[lane * 8 + (k ^ (lane & 7))] = o;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int slot = lane + 32 * r;
+            const int o_local = slot >> 3;
+            const int k = (slot & 7) ^ (o_local & 7);
+            const int64_t it = base + o_local;
+            if (it < items) out[it * 8 + k] = stage[slot];
+        }
+        __syncwarp();
     }
 }
 
@@ -198,6 +240,11 @@ __device__ __forceinline__ void im_to_state_one(const T* __restrict__ p /*object
     state_from_bottom(bx, by, fabs(height), o);
 }
 
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Four lanes per object, lane q owning bottom corner q: the quad's loads cover one contiguous 32/64-byte run per
+// object (coalesced), the four plane maps run in parallel and the state is assembled with quad shuffles.
 template <typename T>
 __global__ void __launch_bounds__(256) im_to_state_kernel(const T* __restrict__ pts, const T* __restrict__ heights,
                                                           int64_t d, const double* __restrict__ H, int ncam,
@@ -205,14 +252,50 @@ __global__ void __launch_bounds__(256) im_to_state_kernel(const T* __restrict__ 
                                                           float* __restrict__ out) {
     extern __shared__ double s_m[];
     stage_mats(s_m, H, ncam * 18);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < d; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = cam ? (int)__ldg(cam + i) : cam_const;
-        float o[6];
-        im_to_state_one<T>(pts + i * 16, (double)heights[i], s_m + c * 18, wrapper, o);
-        float2* dst = reinterpret_cast<float2*>(out + i * 6);
-        dst[0] = make_float2(o[0], o[1]);
-        dst[1] = make_float2(o[2], o[3]);
-        dst[2] = make_float2(o[4], o[5]);
+    const int lane = threadIdx.x & 31, q = lane & 3, qbase = lane & ~3;
+    const int64_t nquads = (int64_t)gridDim.x * (blockDim.x >> 2);
+    const int64_t d_round = ((d + 7) >> 3) << 3;      // whole warps stay in the loop (full-mask shuffles)
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2); i < d_round; i += nquads) {
+        const bool in = i < d;
+        double u = 0.0, v = 0.0, hgt = 0.0;
+        int c = 0;
+        if (in) {
+            c = cam ? (int)__ldg(cam + i) : cam_const;
+            if (sizeof(T) == 8) {
+                const double2 uv = __ldg(reinterpret_cast<const double2*>(pts + i * 16) + q);
+                u = uv.x; v = uv.y;
+            } else {
+                const float2 uv = __ldg(reinterpret_cast<const float2*>(pts + i * 16) + q);
+                u = (double)uv.x; v = (double)uv.y;
+            }
+            hgt = (double)heights[i];
+        }
+        double x, y;
+        plane_map(s_m + c * 18, u, v, x, y);
+        if (wrapper) {  // boxes[:,0,1] > 60 of the first correspondence decides for the whole object (:845)
+            const double y_first = shfl_d(y, qbase);
+            if (y_first > 60.0) plane_map(s_m + c * 18 + 9, u, v, x, y);
+        }
+        // quad reductions (space_to_state, homography.py:274-303)
+        const double xpair = x + shfl_xor_d(x, 1);                 // lanes 0,1: x0+x1 (front); lanes 2,3: x2+x3 (rear)
+        const double other = shfl_xor_d(xpair, 2);
+        const double front = (q < 2) ? xpair : other, rear = (q < 2) ? other : xpair;
+        const double ypair = y + shfl_xor_d(y, 1);
+        const double ysum = ypair + shfl_xor_d(ypair, 2);
+        const double ycol = y + shfl_xor_d(y, 2);                  // lanes 0,2: y0+y2 ; lanes 1,3: y1+y3
+        const double ycol_o = shfl_xor_d(ycol, 1);
+        const double even = (q & 1) ? ycol_o : ycol, odd = (q & 1) ? ycol : ycol_o;
+        const double signed_l = (front - rear) / 2.0;
+        float2 o;
+        if (q == 0) {
+            o = make_float2((float)(rear / 2.0), (float)(ysum / 4.0));
+        } else if (q == 1) {
+            o = make_float2((float)fabs(signed_l), (float)fabs((even - odd) / 2.0));
+        } else {
+            const float dir = (signed_l > 0.0) ? 1.0f : ((signed_l < 0.0) ? -1.0f : (float)signed_l);
+            o = make_float2((float)fabs(hgt), dir);
+        }
+        if (in && q < 3) reinterpret_cast<float2*>(out + i * 6)[q] = o;
     }
 }
 
@@ -380,17 +463,23 @@ extern "C" int g3d_state_to_im(const float* states, int64_t d, int64_t S, const 
     G3D_REQUIRE(states && P && out, "null pointer");
     G3D_REQUIRE(((uintptr_t)out % 16) == 0, "out must be 16-byte aligned");
     G3D_GUARD(device);
-    const size_t smem = (size_t)ncam * 24 * 8;
-    const int64_t total = d * (all_cams ? ncam * 8 : 8);
+    const int64_t items = d * (all_cams ? ncam : 1);
+    const size_t mat_bytes = (size_t)((ncam * 24 + 1) & ~1) * 8;
+    cudaStream_t st = (cudaStream_t)stream;
+#define S2I_LAUNCH(OUT2, ALLC)                                                                                         \
+    do {                                                                                                               \
+        const size_t smem = mat_bytes + sizeof(OUT2) * 8 * kS2IThreads;                                                \
+        G3D_CUDA(cudaFuncSetAttribute(state_to_im_kernel<OUT2, ALLC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                      (int)smem));                                                                     \
+        state_to_im_kernel<OUT2, ALLC><<<grid_for(items), kS2IThreads, smem, st>>>(states, d, S, P, (int)ncam, cam,    \
+                                                                                   cam_const, wrapper, (OUT2*)out);    \
+    } while (0)
     if (out_f32) {
-        G3D_CUDA(cudaFuncSetAttribute(state_to_im_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        state_to_im_kernel<float2><<<grid_for(total), 256, smem, (cudaStream_t)stream>>>(
-            states, d, S, P, (int)ncam, cam, cam_const, wrapper, all_cams, (float2*)out);
+        if (all_cams) S2I_LAUNCH(float2, true); else S2I_LAUNCH(float2, false);
     } else {
-        G3D_CUDA(cudaFuncSetAttribute(state_to_im_kernel<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        state_to_im_kernel<double2><<<grid_for(total), 256, smem, (cudaStream_t)stream>>>(
-            states, d, S, P, (int)ncam, cam, cam_const, wrapper, all_cams, (double2*)out);
+        if (all_cams) S2I_LAUNCH(double2, true); else S2I_LAUNCH(double2, false);
     }
+#undef S2I_LAUNCH
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }
@@ -439,11 +528,12 @@ extern "C" int g3d_im_to_state(const void* pts, const void* heights, int in_is_f
     G3D_REQUIRE(((uintptr_t)out % 8) == 0, "out must be 8-byte aligned");
     G3D_GUARD(device);
     const size_t smem = (size_t)ncam * 18 * 8;
+    G3D_REQUIRE(((uintptr_t)pts % 16) == 0, "pts must be 16-byte aligned");
     if (in_is_f64)
-        im_to_state_kernel<double><<<grid_for(d), 256, smem, (cudaStream_t)stream>>>(
+        im_to_state_kernel<double><<<grid_for(d * 4), 256, smem, (cudaStream_t)stream>>>(
             (const double*)pts, (const double*)heights, d, H, (int)ncam, cam, cam_const, wrapper, out);
     else
-        im_to_state_kernel<float><<<grid_for(d), 256, smem, (cudaStream_t)stream>>>(
+        im_to_state_kernel<float><<<grid_for(d * 4), 256, smem, (cudaStream_t)stream>>>(
             (const float*)pts, (const float*)heights, d, H, (int)ncam, cam, cam_const, wrapper, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;

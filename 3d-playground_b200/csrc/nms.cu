@@ -130,6 +130,17 @@ __global__ void __launch_bounds__(256) keys_gather_kernel(const uint64_t* __rest
     }
 }
 
+// suppression test "IoU(a,b) > thr" with torchvision's arithmetic.  For thr >= 0 a pair whose clamped intersection is
+// zero can never pass (IoU is 0, -0 or NaN), so the union and the IEEE division are skipped for disjoint pairs.
+__device__ __forceinline__ bool suppresses(const float4& a, float area_a, const float4& b, float area_b, float thr,
+                                           bool thr_nonneg) {
+    const float w = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float h = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (thr_nonneg && !(w > 0.0f && h > 0.0f)) return false;
+    const float inter = __fmul_rn(fmaxf(w, 0.0f), fmaxf(h, 0.0f));
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter)) > thr;
+}
+
 // ---- greedy pass: one CTA per segment
 __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)v, src);
@@ -154,6 +165,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
     __shared__ uint64_t s_keep;
 
     const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool thr_nonneg = thr >= 0.0f;
     const int off = seg_offsets[seg];
     const int n = seg_offsets[seg + 1] - off;
     if (n <= 0) {
@@ -194,7 +206,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
                 const int j = l16 + 16 * q;
                 bool pred = false;
                 if (row_live && j > i && j < m)
-                    pred = iou_torchvision(dbox[i], darea[i], dbox[j], darea[j]) > thr;
+                    pred = suppresses(dbox[i], darea[i], dbox[j], darea[j], thr, thr_nonneg);
                 const uint32_t bal = __ballot_sync(0xffffffffu, pred);
                 const uint32_t half = (lane < 16) ? (bal & 0xffffu) : (bal >> 16);
                 word |= (uint64_t)half << (16 * q);
@@ -233,7 +245,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
                 const float4 bj = bsrc[j];
                 const float aj = box_area_rn(bj.x, bj.y, bj.z, bj.w);
                 for (int k = 0; k < kc; ++k) {
-                    if (iou_torchvision(kbox[k], karea[k], bj, aj) > thr) {
+                    if (suppresses(kbox[k], karea[k], bj, aj, thr, thr_nonneg)) {
                         atomicOr(&removed[j >> 5], 1u << (j & 31));
                         break;
                     }
