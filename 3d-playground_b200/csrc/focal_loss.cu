@@ -48,10 +48,74 @@ __device__ __forceinline__ float focal_term(float p_raw, bool t) {
     return w * (-logf(x));
 }
 
+// -log(u) for u = fl(1 - p) in (0, 1).  Negative anchors dominate and their probabilities are small, so the common
+// case avoids the ~22-instruction logf: with pe = 1 - u (exact, Sterbenz) and z = pe / (2 - pe) = pe / (1 + u),
+//     -log(1 - pe) = 2 atanh(z) = 2 z (1 + z^2/3 + z^4/5 + z^6/7 + z^8/9 + ...),
+// truncated after z^8 (|z| < 1/7 for pe < 0.25: relative truncation error < 4e-10).  The series is evaluated on the
+// SAME rounded u the reference takes the log of, so it tracks torch.log(1.0 - classification) to ~2e-7 relative.
+__device__ __forceinline__ float neg_log_u_series(float u) {   // valid for 1 - u < 0.25
+    const float pe = 1.0f - u;
+    const float z = __fdividef(pe, 1.0f + u);
+    const float z2 = z * z;
+    float s = fmaf(z2, 1.0f / 9.0f, 1.0f / 7.0f);
+    s = fmaf(z2, s, 0.2f);
+    s = fmaf(z2, s, 1.0f / 3.0f);
+    s = fmaf(z2, s, 1.0f);
+    return (z + z) * s;
+}
+__device__ __forceinline__ float neg_log_u(float u) {
+    return (1.0f - u < 0.25f) ? neg_log_u_series(u) : -logf(u);
+}
+
+// The 8 class terms of a NEGATIVE anchor, forward (sum) and backward (per-class derivative times `scale`).
+// Straight-line code - the series for all 8 classes first, so the 8 dependency chains interleave - and a rare,
+// separate fix-up for probabilities >= 0.25 (which need the full logf).
+__device__ __forceinline__ float focal_neg_sum8(const float* pv) {
+    float p[8], nl[8];
+    bool big = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        p[c] = fminf(fmaxf(pv[c], G3D_PMIN), G3D_PMAX);
+        const float u = 1.0f - p[c];
+        nl[c] = neg_log_u_series(u);
+        big |= (1.0f - u >= 0.25f);
+    }
+    if (big) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (1.0f - (1.0f - p[c]) >= 0.25f) nl[c] = -logf(1.0f - p[c]);
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc += (0.75f * (p[c] * p[c])) * nl[c];
+    return acc;
+}
+__device__ __forceinline__ void focal_neg_grad8(const float* pv, float scale, float* g) {
+    float nl[8];
+    bool big = false;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float u = 1.0f - pv[c];
+        nl[c] = neg_log_u_series(u);
+        big |= !(1.0f - u < 0.25f);
+    }
+    if (big) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (!(1.0f - (1.0f - pv[c]) < 0.25f)) nl[c] = -logf(1.0f - pv[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float p = pv[c], u = 1.0f - p;
+        const float d = 1.5f * p * nl[c] + __fdividef(0.75f * (p * p), u);
+        g[c] = (p >= G3D_PMIN && p <= G3D_PMAX) ? scale * d : 0.0f;   // clamp backward: zero outside [min, max]
+    }
+}
+
 // focal term of a negative anchor (target 0 for every class): 0.75 p^2 * -log(1-p)
 __device__ __forceinline__ float focal_term_neg(float p_raw) {
     const float p = fminf(fmaxf(p_raw, G3D_PMIN), G3D_PMAX);
-    return (0.75f * (p * p)) * (-logf(1.0f - p));
+    return (0.75f * (p * p)) * neg_log_u(1.0f - p);
 }
 
 // d(focal term)/dp, zero outside the clamp range (torch.clamp backward passes min <= x <= max).
@@ -59,7 +123,7 @@ __device__ __forceinline__ float focal_term_neg(float p_raw) {
 __device__ __forceinline__ float focal_term_grad_neg(float p) {
     if (!(p >= G3D_PMIN && p <= G3D_PMAX)) return 0.0f;
     const float u = 1.0f - p;
-    return -1.5f * p * logf(u) + __fdividef(0.75f * (p * p), u);
+    return 1.5f * p * neg_log_u(u) + __fdividef(0.75f * (p * p), u);
 }
 __device__ __forceinline__ float focal_term_grad(float p, bool t) {
     if (!t) return focal_term_grad_neg(p);
@@ -124,10 +188,11 @@ __device__ __noinline__ void positive_terms_3d(const float* __restrict__ rrow, c
     pred_corners(r, p);
     const float aw = an.z - an.x, ah = an.w - an.y;
     const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
+    const float iaw = 1.0f / aw, iah = 1.0f / ah;   // 2 divisions instead of 20 (the loss is compared at 1e-5)
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < 20; ++i) {
-        const float tn = (i & 1) ? (t[i] - acy) / ah : (t[i] - acx) / aw;
+        const float tn = (i & 1) ? (t[i] - acy) * iah : (t[i] - acx) * iaw;
         float d = fabsf(tn - p[i]);
         if (i >= 8 && i < 16) d *= 0.5f;  // top_weighting, losses.py:343
         s += smooth_l1(d);
@@ -365,8 +430,7 @@ __global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) 
             if (CS == 8) {
                 const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                 if (code == G3D_ASSIGN_NEGATIVE) {  // the overwhelmingly common case: no per-class selects
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) cls_acc += focal_term_neg(pv[c]);
+                    cls_acc = focal_neg_sum8(pv);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) cls_acc += focal_term(pv[c], c == pos_cls);
@@ -447,47 +511,12 @@ struct FocalBwdArgs {
     int B, A, C, R, Gmax, W;
 };
 
-template <int VARIANT, int CS>
-__global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const FocalBwdArgs p) {
-    const int b = blockIdx.y;
-    const int a = blockIdx.x * 256 + threadIdx.x;
-    if (a >= p.A) return;
-    const int C = (CS > 0) ? CS : p.C;
+// regression gradient of one positive anchor (rare path, kept out of line so that the streaming main path of the
+// backward kernel stays small in registers and code)
+template <int VARIANT>
+__device__ __noinline__ void positive_grad(const FocalBwdArgs& p, int b, int a, int code, float npos) {
     const int64_t row = (int64_t)b * p.A + a;
-    const int code = __ldg(p.assign + row);
-    const float npos = __ldg(p.per_image + 4 * b + 3);
-    const float s_cls = __ldg(p.grad_out + 0) / ((float)p.B * fmaxf(npos, 1.0f));
-    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
-    const float* grow = nullptr;
-    int pos_cls = -1;
-    if (code >= 0) {
-        grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
-        pos_cls = (int)(long long)grow[cls_col];
-    }
-    if (CS == 8) {
-        const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
-        float4 c0 = ld_stream(cp), c1 = ld_stream(cp + 1);
-        float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        float g[8];
-        if (code == G3D_ASSIGN_NEGATIVE) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) g[c] = s_cls * focal_term_grad_neg(pv[c]);
-        } else {
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
-        }
-        float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
-        st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
-        st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
-    } else {
-        const float* cp = p.cls + row * C;
-        float* dp = p.dcls + row * C;
-        for (int c = 0; c < C; ++c)
-            dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
-    }
-    if (code < 0) return;
-    // ---- positive anchor: regression gradient
+    const float* grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
     const float4 an = __ldg(p.anchors + a);
     const float* rrow = p.reg + row * p.R;
     float* drow = p.dreg + row * p.R;
@@ -544,6 +573,73 @@ __global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const FocalBwdArgs p)
             drow[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * sg;
         }
     }
+}
+
+// Backward: one thread per (image, anchor).  Streaming part: assignment code + classification row in, gradient row
+// out; the regression-gradient tile of the warp (32 rows) is zero-filled with coalesced 16-byte stores and the rare
+// positive rows are then overwritten (ordered by __syncwarp), so dreg needs no separate memset pass.
+template <int VARIANT, int CS>
+__global__ void __launch_bounds__(256, 5) focal_bwd_kernel(const FocalBwdArgs p) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    const bool valid = a < p.A;
+    const int C = (CS > 0) ? CS : p.C;
+    const int64_t row = (int64_t)b * p.A + a;
+    int code = G3D_ASSIGN_IGNORE;
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
+    if (valid) {
+        code = __ldg(p.assign + row);
+        if (CS == 8) {
+            const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
+            c0 = ld_stream(cp);
+            c1 = ld_stream(cp + 1);
+        }
+    }
+    const float npos = __ldg(p.per_image + 4 * b + 3);
+    const float s_cls = __ldg(p.grad_out + 0) / ((float)p.B * fmaxf(npos, 1.0f));
+    // ---- zero-fill this warp's rows of dreg (R floats each, contiguous across the warp)
+    {
+        const int64_t wrow0 = (int64_t)b * p.A + (a - lane);             // first row of the warp
+        const int nrows = min(32, p.A - (a - lane));
+        if (nrows > 0) {
+            float* base = p.dreg + wrow0 * p.R;
+            const int nfloat = nrows * p.R;
+            if (((uintptr_t)base & 15) == 0) {
+                const int nvec = nfloat >> 2;
+                for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4*>(base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = (nvec << 2) + lane; i < nfloat; i += 32) base[i] = 0.0f;
+            } else {
+                for (int i = lane; i < nfloat; i += 32) base[i] = 0.0f;
+            }
+        }
+    }
+    if (valid) {
+        const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+        int pos_cls = -1;
+        if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
+        if (CS == 8) {
+            const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float g[8];
+            if (code == G3D_ASSIGN_NEGATIVE) {
+                focal_neg_grad8(pv, s_cls, g);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+            }
+            float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
+            st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
+            st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
+        } else {
+            const float* cp = p.cls + row * C;
+            float* dp = p.dcls + row * C;
+            for (int c = 0; c < C; ++c)
+                dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
+        }
+    }
+    __syncwarp();   // the zero-fill above is ordered before the positive rows written below
+    if (code >= 0) positive_grad<VARIANT>(p, b, a, code, npos);
 }
 
 struct FocalWorkspace {
@@ -645,7 +741,6 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     G3D_REQUIRE(B <= 65535, "B out of range for the backward grid");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
-    G3D_CUDA(cudaMemsetAsync(dreg, 0, sizeof(float) * B * A * R, st));
     FocalBwdArgs p;
     p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
     p.grad_out = grad_out; p.per_image = per_image; p.losses = losses; p.assign = assign;
