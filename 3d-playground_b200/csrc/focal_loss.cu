@@ -1,42 +1,50 @@
-// focal_loss.cu — a2..a6 fused: FocalLoss.forward / backward of both retinanet copies in one pass over the anchors.
+// focal_loss.cu — a2..a6: FocalLoss.forward / backward of both retinanet copies.
 //
 //   3D: pytorch_retinanet_detector_directional/retinanet/losses.py:27-362
 //   2D: retinanet/losses.py:27-177
 //
-// Forward, one launch: grid (anchor tiles, image groups).  A CTA loads its 256 anchors once, then for each image of
-// its group: culls/stages the GT boxes (assign_tile.cuh), finds IoU max/argmax per anchor, classifies the anchor
-// (negative / ignore / positive), evaluates the C focal terms from the streamed classification row, evaluates the
-// corner smooth-L1 and the three direction-cosine terms for the (rare) positives, block-reduces in FP64 and stores
-// one partial per (image, tile).  The last CTA to finish an image (atomic ticket) reduces that image's partials in a
-// fixed order, and the last image finalises the batch means - so the result is deterministic and needs no second
-// launch and no host synchronisation.
+// Two launches per call (plus the tiny GT prologue of iou_assign.cu):
+//
+//   1. assign_codes_kernel  (compute only, anchors and GT boxes are L2 resident)
+//        grid (anchor tiles, image groups).  A CTA owns 256 consecutive anchors and kImgPerCta images.  GT boxes are
+//        culled against the tile (bounding box + "can this box reach IoU 0.4 with any anchor of the tile at all"),
+//        compacted into shared memory in ascending GT order, refined per warp, and only pairs whose IoU can still
+//        reach 0.4 pay the IEEE division.  Output: one int32 assignment code per (image, anchor) and the number of
+//        positives per image (integer atomics - deterministic).
+//   2. focal_stream_kernel  (HBM bound - the dominant kernel)
+//        grid (anchor tiles, images), one warp per 32 consecutive (image, anchor) rows.  Streams the classification
+//        rows (fully coalesced 16-byte loads: lane l takes float4 l and l+32 of the warp's 1 KB - the focal term of a
+//        negative anchor does not depend on which row an element belongs to), evaluates the focal terms AND their
+//        gradients from the same -log(1-p), streams the gradient rows out, zero-fills the regression-gradient rows
+//        and lets the (rare) positive anchors add their corner / direction loss terms.
+//        The per-image normaliser 1/num_pos is already known from launch 1, so forward and backward of the whole
+//        loss are ONE pass over the data: cls is read once, -log once, dcls / dreg are written once.
+//        Partial sums: FP32 inside a warp (<= 256 terms), FP64 across warps / tiles, fixed order; the last CTA of an
+//        image (atomic ticket) reduces that image's partials, the last image forms the batch means - deterministic,
+//        no second launch, no host synchronisation.
+//
+// The classification gradient written by launch 2 assumes the upstream gradient of the classification loss that the
+// host announces (1 for `(cls + reg + vp).backward()`, 1/world under dist.py).  g3d_focal_loss_bwd checks that
+// assumption ON THE DEVICE: if the real upstream gradient is the announced one, dcls is already right and the kernel
+// only scans the assignment codes and writes the regression-gradient rows of the positive anchors (for whatever the
+// real upstream gradients of the regression / direction losses are); otherwise it also recomputes dcls.  No host
+// synchronisation either way.
 #include "assign_tile.cuh"
 
 namespace g3d {
+int gt_prepare_launch(const float* ann, int64_t B, int64_t Gmax, int64_t W, int variant, float* gt_box, int32_t* gt_row,
+                      int32_t* gt_count, int32_t* zero_ptr, int64_t zero_n, int device, void* stream);
+}
 
-constexpr int kImgPerCta = 4;  // images processed per CTA for one anchor tile (anchors/bbox loaded once)
+namespace g3d {
+
+constexpr int kImgPerCta = 4;  // images processed per CTA of assign_codes_kernel (anchors / statistics loaded once)
 
 // clamp bounds of losses.py:56: torch.clamp(classification, 1e-4, 1.0 - 1e-4) - python doubles cast to f32
 #define G3D_PMIN ((float)1e-4)
 #define G3D_PMAX ((float)(1.0 - 1e-4))
 #define G3D_BETA ((float)(1.0 / 9.0))        // smooth-L1 switch point (losses.py:346)
 #define G3D_HALF_BETA ((float)(0.5 / 9.0))   // losses.py:348
-
-struct FocalArgs {
-    const float* cls;
-    const float* reg;
-    const float4* anchors;
-    const float* ann;
-    const float4* gt_box;
-    const int32_t* gt_row;
-    const int32_t* gt_count;
-    double* partials;    // [B][T][4] : cls_sum, num_pos, reg_sum, vp_sum
-    int32_t* counters;   // [B+1], zero on entry
-    float* losses;       // [4] : cls, reg, vp, number of non-empty images
-    float* per_image;    // [B][4]
-    int32_t* assign;     // [B][A] or null
-    int B, A, C, R, Gmax, W, T;
-};
 
 // one focal term (losses.py:138-150): alpha_t * (1 - p_t)^2 * bce, target t in {0,1}
 __device__ __forceinline__ float focal_term(float p_raw, bool t) {
@@ -67,59 +75,41 @@ __device__ __forceinline__ float neg_log_u(float u) {
     return (1.0f - u < 0.25f) ? neg_log_u_series(u) : -logf(u);
 }
 
-// The 8 class terms of a NEGATIVE anchor, forward (sum) and backward (per-class derivative times `scale`).
-// Straight-line code - the series for all 8 classes first, so the 8 dependency chains interleave - and a rare,
-// separate fix-up for probabilities >= 0.25 (which need the full logf).
-__device__ __forceinline__ float focal_neg_sum8(const float* pv) {
-    float p[8], nl[8];
+// N elements of NEGATIVE anchors (target 0): sum of 0.75 p^2 * -log(1-p) and, if GRAD, d/dp of each term times
+// `scale` (zero outside the clamp range: torch.clamp's backward passes min <= x <= max).  Straight-line code - the
+// series of all N elements first, so the dependency chains interleave - with a rare, separate fix-up for
+// probabilities >= 0.25 (which need the full logf).  The quotient p^2/u uses the 2-ulp fast division: gradients are
+// compared at 1e-5 relative, nothing here is index-critical.
+template <int N, bool GRAD>
+__device__ __forceinline__ float focal_neg(const float* pv, float scale, float* g) {
+    float p[N], nl[N];
     bool big = false;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < N; ++c) {
         p[c] = fminf(fmaxf(pv[c], G3D_PMIN), G3D_PMAX);
         const float u = 1.0f - p[c];
-        nl[c] = neg_log_u_series(u);
-        big |= (1.0f - u >= 0.25f);
-    }
-    if (big) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (1.0f - (1.0f - p[c]) >= 0.25f) nl[c] = -logf(1.0f - p[c]);
-    }
-    float acc = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc += (0.75f * (p[c] * p[c])) * nl[c];
-    return acc;
-}
-__device__ __forceinline__ void focal_neg_grad8(const float* pv, float scale, float* g) {
-    float nl[8];
-    bool big = false;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float u = 1.0f - pv[c];
         nl[c] = neg_log_u_series(u);
         big |= !(1.0f - u < 0.25f);
     }
     if (big) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            if (!(1.0f - (1.0f - pv[c]) < 0.25f)) nl[c] = -logf(1.0f - pv[c]);
+        for (int c = 0; c < N; ++c)
+            if (!(1.0f - (1.0f - p[c]) < 0.25f)) nl[c] = -logf(1.0f - p[c]);
     }
+    float acc = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const float p = pv[c], u = 1.0f - p;
-        const float d = 1.5f * p * nl[c] + __fdividef(0.75f * (p * p), u);
-        g[c] = (p >= G3D_PMIN && p <= G3D_PMAX) ? scale * d : 0.0f;   // clamp backward: zero outside [min, max]
+    for (int c = 0; c < N; ++c) {
+        const float q = 0.75f * (p[c] * p[c]);
+        acc = fmaf(q, nl[c], acc);
+        if (GRAD) {
+            const float d = fmaf(1.5f * p[c], nl[c], __fdividef(q, 1.0f - p[c]));
+            g[c] = (p[c] == pv[c]) ? scale * d : 0.0f;   // p == p_raw  <=>  p_raw inside [min, max]
+        }
     }
+    return acc;
 }
 
-// focal term of a negative anchor (target 0 for every class): 0.75 p^2 * -log(1-p)
-__device__ __forceinline__ float focal_term_neg(float p_raw) {
-    const float p = fminf(fmaxf(p_raw, G3D_PMIN), G3D_PMAX);
-    return (0.75f * (p * p)) * neg_log_u(1.0f - p);
-}
-
-// d(focal term)/dp, zero outside the clamp range (torch.clamp backward passes min <= x <= max).
-// The two quotients use the 2-ulp fast division: gradients are compared at 1e-5 relative, nothing is index-critical.
+// d(focal term)/dp, zero outside the clamp range.
 __device__ __forceinline__ float focal_term_grad_neg(float p) {
     if (!(p >= G3D_PMIN && p <= G3D_PMAX)) return 0.0f;
     const float u = 1.0f - p;
@@ -174,32 +164,6 @@ __device__ __forceinline__ void pred_corners(const float* r, float* p /*20*/) {
     p[16] = r[8]; p[17] = r[9]; p[18] = r[10]; p[19] = r[11];
 }
 
-// 3D positive anchor: sum of the 20 smooth-L1 terms and the mean of the three cosine losses (losses.py:156-350)
-__device__ __noinline__ void positive_terms_3d(const float* __restrict__ rrow, const float* __restrict__ grow,
-                                                  const float4& an, float& reg_sum, float& vp_term) {
-    float r[12], t[20], p[20], tv[6];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) r[i] = rrow[i];
-#pragma unroll
-    for (int i = 0; i < 20; ++i) t[i] = grow[i];
-    gt_directions(t, tv);
-    vp_term = (cos_loss(r[2], r[3], tv[0], tv[1]) + cos_loss(r[4], r[5], tv[2], tv[3]) +
-               cos_loss(r[6], r[7], tv[4], tv[5])) / 3.0f;
-    pred_corners(r, p);
-    const float aw = an.z - an.x, ah = an.w - an.y;
-    const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
-    const float iaw = 1.0f / aw, iah = 1.0f / ah;   // 2 divisions instead of 20 (the loss is compared at 1e-5)
-    float s = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 20; ++i) {
-        const float tn = (i & 1) ? (t[i] - acy) * iah : (t[i] - acx) * iaw;
-        float d = fabsf(tn - p[i]);
-        if (i >= 8 && i < 16) d *= 0.5f;  // top_weighting, losses.py:343
-        s += smooth_l1(d);
-    }
-    reg_sum = s;
-}
-
 // 2D targets (retinanet/losses.py:137-157)
 __device__ __forceinline__ void targets_2d(const float* __restrict__ grow, const float4& an, float* t /*4*/) {
     const float aw = an.z - an.x, ah = an.w - an.y;
@@ -214,113 +178,184 @@ __device__ __forceinline__ void targets_2d(const float* __restrict__ grow, const
     t[3] = logf(gh / ah) / 0.2f;
 }
 
-__device__ __forceinline__ double block_sum(double v, double* s) {
-    v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
+// One POSITIVE anchor (rare path, out of line so that the streaming main path stays small in registers and code):
+// the regression loss terms of the row (3D: 20 smooth-L1 terms + mean of the three cosine losses, losses.py:156-350;
+// 2D: 4 smooth-L1 terms, retinanet/losses.py:129-173) and, if drow != null, the row's regression gradient for the
+// upstream gradients (g_reg, g_vp).
+template <int VARIANT>
+__device__ __noinline__ void positive_row(const float* __restrict__ rrow, const float* __restrict__ grow, const float4 an,
+                                           float s_reg, float s_vp, float* __restrict__ drow, float& reg_sum,
+                                           float& vp_term) {
+    if (VARIANT == G3D_VARIANT_3D) {
+        float r[12], t[20], pr[20], tv[6];
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += s[w];
-    __syncthreads();
-    return t;
+        for (int i = 0; i < 12; ++i) r[i] = rrow[i];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) t[i] = grow[i];
+        gt_directions(t, tv);
+        vp_term = (cos_loss(r[2], r[3], tv[0], tv[1]) + cos_loss(r[4], r[5], tv[2], tv[3]) +
+                   cos_loss(r[6], r[7], tv[4], tv[5])) / 3.0f;
+        pred_corners(r, pr);
+        const float aw = an.z - an.x, ah = an.w - an.y;
+        const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
+        float s = 0.0f, g[20];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) {
+            const float tn = (i & 1) ? (t[i] - acy) / ah : (t[i] - acx) / aw;   // losses.py:330-331
+            const float diff = tn - pr[i];
+            const float w = (i >= 8 && i < 16) ? 0.5f : 1.0f;                   // top_weighting, losses.py:343
+            const float d = fabsf(diff) * w;
+            s += smooth_l1(d);
+            const float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
+            // d smooth_l1 / d pred = slope(d) * w * d|diff|/dpred = slope * w * (-sign(diff))
+            g[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * w * sg;
+        }
+        reg_sum = s;
+        if (drow) {
+            float dr[12];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dr[i] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                dr[0] += g[2 * k];            dr[1] += g[2 * k + 1];
+                dr[2] += sgn_l(k) * g[2 * k]; dr[3] += sgn_l(k) * g[2 * k + 1];
+                dr[4] += sgn_w(k) * g[2 * k]; dr[5] += sgn_w(k) * g[2 * k + 1];
+                dr[6] += sgn_h(k) * g[2 * k]; dr[7] += sgn_h(k) * g[2 * k + 1];
+            }
+            dr[8] = g[16]; dr[9] = g[17]; dr[10] = g[18]; dr[11] = g[19];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                float gx, gy;
+                cos_loss_grad(r[2 + 2 * v], r[3 + 2 * v], tv[2 * v], tv[2 * v + 1], gx, gy);
+                dr[2 + 2 * v] += s_vp * gx;
+                dr[3 + 2 * v] += s_vp * gy;
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) drow[i] = dr[i];
+        }
+    } else {
+        float t[4];
+        targets_2d(grow, an, t);
+        float s = 0.0f;
+        vp_term = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float diff = t[i] - rrow[i];
+            const float d = fabsf(diff);
+            s += smooth_l1(d);
+            if (drow) {
+                const float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
+                drow[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * sg;
+            }
+        }
+        reg_sum = s;
+    }
 }
 
-// Shared state of one CTA of the forward kernel: the culled GT lists of its kImgPerCta images (staged once, behind two
-// barriers); everything after that is warp-private - no barrier per image and none at the end: the last warp of the
-// CTA to finish (shared-memory ticket) combines the 8 warp partials.
-struct FwdSmem {
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =====================================================================================================================
+// launch 1: assignment codes
+// =====================================================================================================================
+struct AssignCodesArgs {
+    const float4* anchors;
+    const float4* gt_box;
+    const int32_t* gt_row;
+    const int32_t* gt_count;
+    int32_t* assign;     // [B][A]
+    int32_t* npos;       // [B], zero on entry
+    int B, A, Gmax;
+};
+
+struct StageSmem {
     float4 box[kImgPerCta][kTile];
     float area[kImgPerCta][kTile];
     int idx[kImgPerCta][kTile];
-    float bbred[4][kWarps];
+    float red[8][kWarps];
     int wcount[kImgPerCta][kWarps];
-    double dred[kImgPerCta][3][kWarps];
-    int nred[kImgPerCta][kWarps];
     int total[kImgPerCta];
-    int arrive;
 };
 
-// Executed by ONE warp - the last tile of image b: reduce the image's T partials in a fixed order (lane-strided
-// accumulation + shuffle tree), then (last image of the batch) the batch means.
-template <int VARIANT>
-__device__ __forceinline__ void finalize_image(const FocalArgs& p, int b) {
-    const int lane = threadIdx.x & 31;
-    __threadfence();
-    double tc = 0.0, tn = 0.0, tr = 0.0, tv = 0.0;
-    const double2* src = reinterpret_cast<const double2*>(p.partials + (int64_t)b * p.T * 4);
-#pragma unroll 4
-    for (int t = lane; t < p.T; t += 32) {
-        const double2 u = __ldcg(src + 2 * t), v = __ldcg(src + 2 * t + 1);
-        tc += u.x; tn += u.y; tr += v.x; tv += v.y;
+// Size statistics of a group of anchors (a warp or a tile), for the "can the IoU reach 0.4 at all" cull:
+// for well-formed boxes  IoU = inter / union,  inter <= min(wa, wg) * min(ha, hg)  and  inter <= min(area_a, area_g),
+// union >= max(area_a, area_g).  So a GT box whose best case over the group stays below 0.38 (margin for the FP32
+// roundings of the real thing, which are ~1e-7 relative) has IoU < 0.4 with every anchor of the group: whatever
+// its exact IoU, it cannot move an anchor out of the `negative` class, and it can be skipped.
+struct GroupStats {
+    float4 bb;          // min x1, min y1, max x2, max y2
+    float wmax, hmax;   // largest width / height
+    float amin, amax;   // smallest / largest area
+    bool wellformed;    // every anchor has positive width and height
+};
+
+__device__ __forceinline__ bool can_touch(const float4& g, const GroupStats& s) {
+    // keep unless provably disjoint from every anchor of the group (NaN coordinates are never culled here)
+    if (g.z <= s.bb.x || g.x >= s.bb.z || g.w <= s.bb.y || g.y >= s.bb.w) return false;
+    const float gw = g.z - g.x, gh = g.w - g.y;
+    if (s.wellformed && gw > 0.0f && gh > 0.0f) {
+        const float ga = gw * gh;
+        const float best_inter = fminf(fminf(s.wmax, gw) * fminf(s.hmax, gh), fminf(s.amax, ga));
+        if (best_inter < 0.38f * fmaxf(s.amin, ga)) return false;
     }
-    tc = warp_sum(tc); tn = warp_sum(tn); tr = warp_sum(tr); tv = warp_sum(tv);
-    int last = 0;
-    if (lane == 0) {
-        const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
-        float4 o;
-        o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
-        o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
-        o.z = tn > 0.0 ? (float)(tv / tn) : 0.0f;              // vp_loss.mean() (:304)
-        o.w = (float)tn;
-        __stcg(reinterpret_cast<float4*>(p.per_image) + b, o);
-        __threadfence();
-        last = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {
-        // last image: batch means (losses.py:362).  vp: only images with >= 1 GT row contribute (:304,:353-358)
-        __threadfence();
-        double sc = 0.0, sr = 0.0, sv = 0.0, ne = 0.0;
-        for (int j = lane; j < p.B; j += 32) {
-            const float4 o = __ldcg(reinterpret_cast<const float4*>(p.per_image) + j);
-            sc += o.x; sr += o.y;
-            if (__ldg(p.gt_count + j) > 0) { sv += o.z; ne += 1.0; }
-        }
-        sc = warp_sum(sc); sr = warp_sum(sr); sv = warp_sum(sv); ne = warp_sum(ne);
-        if (lane == 0) {
-            p.losses[0] = (float)(sc / p.B);
-            p.losses[1] = (float)(sr / p.B);
-            p.losses[2] = (VARIANT == G3D_VARIANT_3D) ? (float)(sv / ne) : 0.0f;  // 0/0 -> NaN when all empty
-            p.losses[3] = (float)ne;
-        }
-    }
+    return true;
 }
 
-template <int VARIANT, int CS>
-__global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) {
-    __shared__ FwdSmem sm;
+__global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCodesArgs p) {
+    __shared__ StageSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a = blockIdx.x * kTile + tid;
     const bool valid = a < p.A;
     float4 an = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) an = __ldg(p.anchors + a);
     const float area_a = box_area_rn(an.x, an.y, an.z, an.w);
-    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
-    const int C = (CS > 0) ? CS : p.C;
     const int b0 = blockIdx.y * kImgPerCta;
     const int nimg = min(kImgPerCta, p.B - b0);
-    if (tid == 0) sm.arrive = 0;
 
-    // ---- bounding boxes of the warp's and of the tile's anchors (one barrier)
-    float4 wb, bb;
+    // ---- statistics of the warp's and of the tile's anchors (one barrier)
+    GroupStats ws, ts;
     {
-        float mnx = valid ? an.x : INFINITY, mny = valid ? an.y : INFINITY;
-        float mxx = valid ? an.z : -INFINITY, mxy = valid ? an.w : -INFINITY;
-        mnx = warp_min(mnx); mny = warp_min(mny); mxx = warp_max(mxx); mxy = warp_max(mxy);
-        wb = make_float4(mnx, mny, mxx, mxy);
-        if (lane == 0) { sm.bbred[0][warp] = mnx; sm.bbred[1][warp] = mny; sm.bbred[2][warp] = mxx; sm.bbred[3][warp] = mxy; }
-        __syncthreads();
-        bb = make_float4(sm.bbred[0][0], sm.bbred[1][0], sm.bbred[2][0], sm.bbred[3][0]);
+        const float w = an.z - an.x, h = an.w - an.y;
+        float v[8];
+        v[0] = valid ? -an.x : -INFINITY; v[1] = valid ? -an.y : -INFINITY;    // maxima of negated values = minima
+        v[2] = valid ? an.z : -INFINITY;  v[3] = valid ? an.w : -INFINITY;
+        v[4] = valid ? w : -INFINITY;     v[5] = valid ? h : -INFINITY;
+        v[6] = valid ? -area_a : -INFINITY; v[7] = valid ? area_a : -INFINITY;
 #pragma unroll
-        for (int w = 1; w < kWarps; ++w) {
-            bb.x = fminf(bb.x, sm.bbred[0][w]); bb.y = fminf(bb.y, sm.bbred[1][w]);
-            bb.z = fmaxf(bb.z, sm.bbred[2][w]); bb.w = fmaxf(bb.w, sm.bbred[3][w]);
+        for (int k = 0; k < 8; ++k) v[k] = warp_max(v[k]);
+        const bool wf = __all_sync(0xffffffffu, !valid || (w > 0.0f && h > 0.0f));
+        ws.bb = make_float4(-v[0], -v[1], v[2], v[3]);
+        ws.wmax = v[4]; ws.hmax = v[5]; ws.amin = -v[6]; ws.amax = v[7];
+        ws.wellformed = wf;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm.red[k][warp] = v[k];
+            sm.wcount[0][warp] = wf ? 1 : 0;
         }
+        __syncthreads();
+        float t[8];
+        bool twf = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = sm.red[k][0];
+#pragma unroll
+        for (int w2 = 1; w2 < kWarps; ++w2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = fmaxf(t[k], sm.red[k][w2]);
+        }
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps; ++w2) twf &= (sm.wcount[0][w2] != 0);
+        ts.bb = make_float4(-t[0], -t[1], t[2], t[3]);
+        ts.wmax = t[4]; ts.hmax = t[5]; ts.amin = -t[6]; ts.amax = t[7];
+        ts.wellformed = twf;
+        __syncthreads();   // sm.wcount[0] is reused below
     }
 
-    // ---- stage the GT boxes of the group's images: cull against the tile bounding box with an ordered compaction
-    // (ascending GT index), all images behind the same two barriers.  An image with more than kTile GT rows keeps its
-    // first kTile candidates here and is finished by the (rare) overflow loop further down.
+    // ---- stage the GT boxes of the group's images: cull against the tile with an ordered compaction (ascending GT
+    // index), all images behind the same two barriers.  An image with more than kTile GT rows keeps its first kTile
+    // candidates here and is finished by the (rare) overflow loop further down.
     {
         const int g = tid;
         float4 gb[kImgPerCta];
@@ -332,8 +367,7 @@ __global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) 
             const int Gi = (i < nimg) ? __ldg(p.gt_count + b0 + i) : 0;
             if (g < Gi) {
                 gb[i] = __ldg(p.gt_box + (int64_t)(b0 + i) * p.Gmax + g);
-                // keep unless provably disjoint from every anchor of the tile (NaN coordinates are never culled)
-                hit = !(gb[i].z <= bb.x || gb[i].x >= bb.z || gb[i].w <= bb.y || gb[i].y >= bb.w);
+                hit = can_touch(gb[i], ts);
             }
             bal[i] = __ballot_sync(0xffffffffu, hit);
         }
@@ -362,30 +396,18 @@ __global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) 
         __syncthreads();
     }
 
-    // ---- per image (a real loop: the body is large, unrolling it thrashes the instruction cache): IoU max/argmax over
-    // the staged survivors, classify the anchor, focal terms, positive terms, warp-level partial sums.  No barriers.
+    // ---- per image: IoU max / first argmax over the staged survivors that can still matter.  No barriers.
 #pragma unroll 1
     for (int i = 0; i < nimg; ++i) {
         const int b = b0 + i;
-        const int64_t row = (int64_t)b * p.A + a;
-        // request the classification row first: it is in flight during the IoU search
-        float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-        if (CS == 8 && valid) {
-            const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
-            c0 = ld_stream(cp);
-            c1 = ld_stream(cp + 1);
-        }
         const int Gi = __ldg(p.gt_count + b);
         float best = 0.0f;
         int besti = 0;
         const int total = sm.total[i];
         for (int k0 = 0; k0 < total; k0 += 32) {
-            // warp-level refinement: which of these (up to 32) tile survivors can touch this warp's anchors at all?
+            // warp-level refinement: which of these (up to 32) tile survivors matter for this warp's anchors?
             bool near = false;
-            if (k0 + lane < total) {
-                const float4 t = sm.box[i][k0 + lane];
-                near = !(t.z <= wb.x || t.x >= wb.z || t.w <= wb.y || t.y >= wb.w);
-            }
+            if (k0 + lane < total) near = can_touch(sm.box[i][k0 + lane], ws);
             unsigned m = __ballot_sync(0xffffffffu, near);
             while (m) {
                 const int k = k0 + __ffs(m) - 1;
@@ -396,9 +418,13 @@ __global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) 
                 // a disjoint pair has IoU == +0.0 exactly and can never beat `best` under the strict '>' rule
                 if (iw > 0.0f && ih > 0.0f) {
                     const float inter = __fmul_rn(iw, ih);
-                    const float ua = fmaxf(__fsub_rn(__fadd_rn(area_a, sm.area[i][k]), inter), 1e-8f);
-                    const float v = __fdiv_rn(inter, ua);
-                    if (v > best) { best = v; besti = sm.idx[i][k]; }
+                    const float ua0 = __fsub_rn(__fadd_rn(area_a, sm.area[i][k]), inter);
+                    // inter <= ua0 / 2.6  =>  IoU <= 0.3847 < 0.4: cannot change the code of this anchor, skip the
+                    // division (the clamp of the union only matters below 1e-8, where this test passes)
+                    if (__fmul_rn(inter, 2.6f) > ua0) {
+                        const float v = __fdiv_rn(inter, fmaxf(ua0, 1e-8f));
+                        if (v > best) { best = v; besti = sm.idx[i][k]; }
+                    }
                 }
             }
         }
@@ -414,59 +440,197 @@ __global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) 
                 if (v > best) { best = v; besti = g; }
             }
         }
+        // `best` is exact whenever it is >= 0.4 (every pair that can reach 0.3847 was evaluated exactly, in ascending
+        // GT order with the strict '>' rule = torch.max's first-maximal-index); below that only "< 0.4" is used.
         int code = G3D_ASSIGN_NEGATIVE;
         if (Gi > 0) code = assign_code(best, besti, p.gt_row + (int64_t)b * p.Gmax);
-        if (!valid) code = G3D_ASSIGN_IGNORE;
-        if (p.assign && valid) p.assign[row] = code;
+        if (valid) p.assign[(int64_t)b * p.A + a] = code;
+        const unsigned posmask = __ballot_sync(0xffffffffu, valid && code >= 0);
+        if (posmask && lane == 0) atomicAdd(p.npos + b, __popc(posmask));
+    }
+}
 
-        float cls_acc = 0.0f, reg_acc = 0.0f, vp_acc = 0.0f;
-        const float* grow = nullptr;
-        int pos_cls = -1;
-        if (code >= 0) {
-            grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
-            pos_cls = (int)(long long)grow[cls_col];
+// =====================================================================================================================
+// launch 2: the streaming loss (+ gradient) pass
+// =====================================================================================================================
+struct StreamArgs {
+    const float* cls;
+    const float* reg;
+    const float4* anchors;
+    const float* ann;
+    const int32_t* assign;     // [B][A]
+    const int32_t* npos;       // [B]
+    const int32_t* gt_count;   // [B]
+    int32_t* gt_count_out;     // [B] or null: copy of gt_count for the caller
+    double* partials;          // [B][T][4] : cls_sum, -, reg_sum, vp_sum
+    int32_t* counters;         // [B+1], zero on entry
+    float* losses;             // [4] : cls, reg, vp, number of non-empty images
+    float* per_image;          // [B][4]
+    float* dcls;               // [B][A][C]  (GRAD only)
+    float* dreg;               // [B][A][R]  (GRAD only)
+    float g0;                  // upstream gradient of the classification loss that dcls is formed for
+    int B, A, C, R, Gmax, W, T;
+};
+
+// Executed by ONE warp - the last tile of image b: reduce the image's T partials in a fixed order (lane-strided
+// accumulation + shuffle tree), then (last image of the batch) the batch means.
+template <int VARIANT>
+__device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
+    const int lane = threadIdx.x & 31;
+    __threadfence();
+    double tc = 0.0, tr = 0.0, tv = 0.0;
+    const double2* src = reinterpret_cast<const double2*>(p.partials + (int64_t)b * p.T * 4);
+#pragma unroll 4
+    for (int t = lane; t < p.T; t += 32) {
+        const double2 u = __ldcg(src + 2 * t), v = __ldcg(src + 2 * t + 1);
+        tc += u.x; tr += v.x; tv += v.y;
+    }
+    tc = warp_sum(tc); tr = warp_sum(tr); tv = warp_sum(tv);
+    int last = 0;
+    if (lane == 0) {
+        const double tn = (double)__ldg(p.npos + b);
+        const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
+        float4 o;
+        o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
+        o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
+        o.z = tn > 0.0 ? (float)(tv / tn) : 0.0f;              // vp_loss.mean() (:304)
+        o.w = (float)tn;
+        __stcg(reinterpret_cast<float4*>(p.per_image) + b, o);
+        if (p.gt_count_out) p.gt_count_out[b] = __ldg(p.gt_count + b);
+        __threadfence();
+        last = (atomicAdd(p.counters + p.B, 1) == p.B - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        // last image: batch means (losses.py:362).  vp: only images with >= 1 GT row contribute (:304,:353-358)
+        __threadfence();
+        double sc = 0.0, sr = 0.0, sv = 0.0, ne = 0.0;
+        for (int j = lane; j < p.B; j += 32) {
+            const float4 o = __ldcg(reinterpret_cast<const float4*>(p.per_image) + j);
+            sc += o.x; sr += o.y;
+            if (__ldg(p.gt_count + j) > 0) { sv += o.z; ne += 1.0; }
         }
-        if (code != G3D_ASSIGN_IGNORE) {
-            if (CS == 8) {
-                const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                if (code == G3D_ASSIGN_NEGATIVE) {  // the overwhelmingly common case: no per-class selects
-                    cls_acc = focal_neg_sum8(pv);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) cls_acc += focal_term(pv[c], c == pos_cls);
-                }
-            } else {
-                const float* cp = p.cls + row * C;
-                for (int c = 0; c < C; ++c) cls_acc += focal_term(__ldg(cp + c), c == pos_cls);
-            }
-        }
-        if (code >= 0) {
-            const float* rrow = p.reg + row * p.R;
-            if (VARIANT == G3D_VARIANT_3D) {
-                positive_terms_3d(rrow, grow, an, reg_acc, vp_acc);
-            } else {
-                float t[4];
-                targets_2d(grow, an, t);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) reg_acc += smooth_l1(fabsf(t[j] - rrow[j]));
-            }
-        }
-        const double cs = warp_sum((double)cls_acc);
-        const unsigned posmask = __ballot_sync(0xffffffffu, code >= 0);
-        double rs = 0.0, vs = 0.0;
-        if (posmask) {
-            rs = warp_sum((double)reg_acc);
-            vs = warp_sum((double)vp_acc);
-        }
+        sc = warp_sum(sc); sr = warp_sum(sr); sv = warp_sum(sv); ne = warp_sum(ne);
         if (lane == 0) {
-            sm.dred[i][0][warp] = cs; sm.dred[i][1][warp] = rs; sm.dred[i][2][warp] = vs;
-            sm.nred[i][warp] = __popc(posmask);
+            p.losses[0] = (float)(sc / p.B);
+            p.losses[1] = (float)(sr / p.B);
+            p.losses[2] = (VARIANT == G3D_VARIANT_3D) ? (float)(sv / ne) : 0.0f;  // 0/0 -> NaN when all empty
+            p.losses[3] = (float)ne;
         }
     }
-    // ---- the last warp of the CTA to get here combines the warp partials: one partial per (image, tile); the last
-    // tile of an image (global ticket) reduces that image.  No block barrier: finished warps retire immediately.
+}
+
+// zero-fill the warp's rows of dreg (R floats each, contiguous across the warp) with coalesced 16-byte stores
+__device__ __forceinline__ void zero_rows(float* base, int nfloat, int lane) {
+    if (((uintptr_t)base & 15) == 0) {
+        const int nvec = nfloat >> 2;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = lane; i < nvec; i += 32) st_stream(reinterpret_cast<float4*>(base) + i, z);
+        for (int i = (nvec << 2) + lane; i < nfloat; i += 32) base[i] = 0.0f;
+    } else {
+        for (int i = lane; i < nfloat; i += 32) base[i] = 0.0f;
+    }
+}
+
+struct StreamSmem {
+    double dred[3][kWarps];
+    int arrive;
+};
+
+template <int VARIANT, int CS, bool GRAD>
+__global__ void __launch_bounds__(kTile, 6) focal_stream_kernel(const StreamArgs p) {
+    __shared__ StreamSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int a0 = blockIdx.x * kTile + warp * 32;   // first anchor of this warp
+    const int a = a0 + lane;
+    const bool valid = a < p.A;
+    const int64_t row0 = (int64_t)b * p.A + a0;
+    int code = G3D_ASSIGN_IGNORE;
+    if (valid) code = __ldg(p.assign + row0 + lane);
+    if (tid == 0) sm.arrive = 0;
+    __syncthreads();   // the ticket must be zero before the first warp finishes (all warps are still at the start: cheap)
+    const float npos = (float)__ldg(p.npos + b);
+    const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
+    const unsigned special = __ballot_sync(0xffffffffu, code != G3D_ASSIGN_NEGATIVE);   // invalid rows count as special
+    const int nrows = min(32, p.A - a0);
+
+    if (GRAD && nrows > 0) zero_rows(p.dreg + row0 * p.R, nrows * p.R, lane);
+
+    float cls_acc = 0.0f;
+    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+    int pos_cls = -1;
+    const float* grow = nullptr;
+    if (code >= 0) {
+        grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
+        pos_cls = (int)(long long)grow[cls_col];
+    }
+    if (CS == 8) {
+        // lane l owns float4 l and l + 32 of the warp's 64 (32 rows x 2): fully coalesced in both directions
+        const float4* cp = reinterpret_cast<const float4*>(p.cls + row0 * 8);
+        float4* dp = reinterpret_cast<float4*>(p.dcls + row0 * 8);
+        if (special == 0) {
+            const float4 v0 = ld_stream(cp + lane), v1 = ld_stream(cp + 32 + lane);
+            const float pv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float g[8];
+            cls_acc = focal_neg<8, GRAD>(pv, s_cls, g);
+            if (GRAD) {
+                st_stream(dp + lane, make_float4(g[0], g[1], g[2], g[3]));
+                st_stream(dp + 32 + lane, make_float4(g[4], g[5], g[6], g[7]));
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = lane + 32 * h, r = j >> 1, c0 = (j & 1) * 4;
+                const int code_r = __shfl_sync(0xffffffffu, code, r);
+                const int pc_r = __shfl_sync(0xffffffffu, pos_cls, r);
+                if (r < nrows) {
+                    const float4 v = ld_stream(cp + j);
+                    const float pv[4] = {v.x, v.y, v.z, v.w};
+                    float g[4];
+                    if (code_r == G3D_ASSIGN_NEGATIVE) {
+                        cls_acc += focal_neg<4, GRAD>(pv, s_cls, g);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            g[e] = 0.0f;
+                            if (code_r != G3D_ASSIGN_IGNORE) {
+                                cls_acc += focal_term(pv[e], c0 + e == pc_r);
+                                if (GRAD) g[e] = s_cls * focal_term_grad(pv[e], c0 + e == pc_r);
+                            }
+                        }
+                    }
+                    if (GRAD) st_stream(dp + j, make_float4(g[0], g[1], g[2], g[3]));
+                }
+            }
+        }
+    } else if (valid) {
+        const int C = p.C;
+        const float* cp = p.cls + (row0 + lane) * C;
+        float* dp = p.dcls + (row0 + lane) * C;
+        for (int c = 0; c < C; ++c) {
+            const float pr = __ldg(cp + c);
+            const bool ign = (code == G3D_ASSIGN_IGNORE);
+            if (!ign) cls_acc += focal_term(pr, c == pos_cls);
+            if (GRAD) dp[c] = ign ? 0.0f : s_cls * focal_term_grad(pr, c == pos_cls);
+        }
+    }
+
+    // ---- positive anchors: regression / direction loss terms (their gradient rows are written by the backward)
+    float reg_acc = 0.0f, vp_acc = 0.0f;
+    const unsigned posmask = __ballot_sync(0xffffffffu, code >= 0);
+    if (code >= 0)
+        positive_row<VARIANT>(p.reg + (row0 + lane) * p.R, grow, __ldg(p.anchors + a), 0.0f, 0.0f, nullptr, reg_acc, vp_acc);
+
+    // ---- partial sums: FP32 inside the warp, FP64 from here on.  The last warp of the CTA to get here (shared-memory
+    // ticket, no block barrier: finished warps retire immediately) combines the 8 warp partials in warp order; the
+    // last tile of the image (global ticket) reduces that image.
+    const float cs = warp_sum_f(cls_acc);
+    float rs = 0.0f, vs = 0.0f;
+    if (posmask) { rs = warp_sum_f(reg_acc); vs = warp_sum_f(vp_acc); }
     int arrived = 0;
     if (lane == 0) {
+        sm.dred[0][warp] = (double)cs; sm.dred[1][warp] = (double)rs; sm.dred[2][warp] = (double)vs;
         __threadfence_block();
         arrived = atomicAdd(&sm.arrive, 1);
     }
@@ -474,172 +638,103 @@ __global__ void __launch_bounds__(kTile, 4) focal_fwd_kernel(const FocalArgs p) 
     if (arrived != kWarps - 1) return;
     __threadfence_block();
     int is_last = 0;
-    if (lane < nimg) {
-        const int i = lane, b = b0 + i;
-        const volatile double* dr = &sm.dred[i][0][0];
-        const volatile int* nr = &sm.nred[i][0];
+    if (lane == 0) {
+        const volatile double* dr = &sm.dred[0][0];
         double tc = 0.0, tr = 0.0, tv = 0.0;
-        int tn = 0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { tc += dr[w]; tr += dr[kWarps + w]; tv += dr[2 * kWarps + w]; tn += nr[w]; }
+        for (int w = 0; w < kWarps; ++w) { tc += dr[w]; tr += dr[kWarps + w]; tv += dr[2 * kWarps + w]; }
         double* out = p.partials + ((int64_t)b * p.T + blockIdx.x) * 4;
-        __stcg(reinterpret_cast<double2*>(out), make_double2(tc, (double)tn));
+        __stcg(reinterpret_cast<double2*>(out), make_double2(tc, 0.0));
         __stcg(reinterpret_cast<double2*>(out) + 1, make_double2(tr, tv));
         __threadfence();
         is_last = (atomicAdd(p.counters + b, 1) == p.T - 1);
     }
-    unsigned lastmask = __ballot_sync(0xffffffffu, is_last);
-    while (lastmask) {
-        const int i = __ffs(lastmask) - 1;
-        lastmask &= lastmask - 1;
-        finalize_image<VARIANT>(p, b0 + i);
-    }
+    is_last = __shfl_sync(0xffffffffu, is_last, 0);
+    if (is_last) finalize_image<VARIANT>(p, b);
 }
 
-// ----------------------------------------------------------------------------------------------------- backward
+// =====================================================================================================================
+// backward for upstream gradients other than the ones launch 2 was told to expect
+// =====================================================================================================================
 struct FocalBwdArgs {
     const float* cls;
     const float* reg;
     const float4* anchors;
     const float* ann;
-    const float* grad_out;   // [3]
+    const float* grad_out;   // [3] device
     const float* per_image;  // [B][4]
     const float* losses;     // [4] (losses[3] = number of non-empty images)
     const int32_t* assign;
     float* dcls;
-    float* dreg;             // pre-zeroed; only positive rows are written
-    int B, A, C, R, Gmax, W;
+    float* dreg;
+    float e0;                // upstream classification gradient dcls was formed for (valid if have_dcls)
+    int have_dcls;           // dcls already holds the gradient for e0 and dreg is already zero-filled
+    int B, A, C, R, Gmax, W, T;
 };
 
-// regression gradient of one positive anchor (rare path, kept out of line so that the streaming main path of the
-// backward kernel stays small in registers and code)
-template <int VARIANT>
-__device__ __noinline__ void positive_grad(const FocalBwdArgs& p, int b, int a, int code, float npos) {
-    const int64_t row = (int64_t)b * p.A + a;
-    const float* grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
-    const float4 an = __ldg(p.anchors + a);
-    const float* rrow = p.reg + row * p.R;
-    float* drow = p.dreg + row * p.R;
-    if (VARIANT == G3D_VARIANT_3D) {
-        const float s_reg = __ldg(p.grad_out + 1) / ((float)p.B * 20.0f * npos);
-        const float s_vp = __ldg(p.grad_out + 2) / (__ldg(p.losses + 3) * npos * 3.0f);
-        float r[12], t[20], pr[20], tv[6], g[20], dr[12];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) r[i] = rrow[i];
-#pragma unroll
-        for (int i = 0; i < 20; ++i) t[i] = grow[i];
-        gt_directions(t, tv);
-        pred_corners(r, pr);
-        const float aw = an.z - an.x, ah = an.w - an.y;
-        const float acx = an.x + 0.5f * aw, acy = an.y + 0.5f * ah;
-#pragma unroll
-        for (int i = 0; i < 20; ++i) {
-            const float tn = (i & 1) ? (t[i] - acy) / ah : (t[i] - acx) / aw;
-            const float diff = tn - pr[i];
-            const float w = (i >= 8 && i < 16) ? 0.5f : 1.0f;
-            const float d = fabsf(diff) * w;
-            const float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
-            // d smooth_l1 / d pred = slope(d) * w * d|diff|/dpred = slope * w * (-sign(diff))
-            g[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * w * sg;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dr[i] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            dr[0] += g[2 * k];            dr[1] += g[2 * k + 1];
-            dr[2] += sgn_l(k) * g[2 * k]; dr[3] += sgn_l(k) * g[2 * k + 1];
-            dr[4] += sgn_w(k) * g[2 * k]; dr[5] += sgn_w(k) * g[2 * k + 1];
-            dr[6] += sgn_h(k) * g[2 * k]; dr[7] += sgn_h(k) * g[2 * k + 1];
-        }
-        dr[8] = g[16]; dr[9] = g[17]; dr[10] = g[18]; dr[11] = g[19];
-#pragma unroll
-        for (int v = 0; v < 3; ++v) {
-            float gx, gy;
-            cos_loss_grad(r[2 + 2 * v], r[3 + 2 * v], tv[2 * v], tv[2 * v + 1], gx, gy);
-            dr[2 + 2 * v] += s_vp * gx;
-            dr[3 + 2 * v] += s_vp * gy;
-        }
-#pragma unroll
-        for (int i = 0; i < 12; ++i) drow[i] = dr[i];
-    } else {
-        const float s_reg = __ldg(p.grad_out + 1) / ((float)p.B * 4.0f * npos);
-        float t[4];
-        targets_2d(grow, an, t);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float diff = t[i] - rrow[i];
-            const float d = fabsf(diff);
-            const float sg = (diff > 0.0f) ? 1.0f : ((diff < 0.0f) ? -1.0f : 0.0f);
-            drow[i] = -s_reg * ((d <= G3D_BETA) ? 9.0f * d : 1.0f) * sg;
-        }
-    }
-}
-
-// Backward: one thread per (image, anchor).  Streaming part: assignment code + classification row in, gradient row
-// out; the regression-gradient tile of the warp (32 rows) is zero-filled with coalesced 16-byte stores and the rare
-// positive rows are then overwritten (ordered by __syncwarp), so dreg needs no separate memset pass.
+// Persistent grid-stride kernel over (image, tile) items, one thread per (image, anchor) row inside an item.
+// Usual training step (dcls already right): read the codes, write the few positive rows of dreg - ~50 MB of traffic.
 template <int VARIANT, int CS>
-__global__ void __launch_bounds__(256, 5) focal_bwd_kernel(const FocalBwdArgs p) {
-    const int b = blockIdx.y;
+__global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const FocalBwdArgs p) {
+    const float go0 = __ldg(p.grad_out + 0), go1 = __ldg(p.grad_out + 1);
+    const float go2 = (VARIANT == G3D_VARIANT_3D) ? __ldg(p.grad_out + 2) : 0.0f;
+    const bool cls_ok = p.have_dcls && go0 == p.e0;
     const int lane = threadIdx.x & 31;
-    const int a = blockIdx.x * 256 + threadIdx.x;
-    const bool valid = a < p.A;
     const int C = (CS > 0) ? CS : p.C;
-    const int64_t row = (int64_t)b * p.A + a;
-    int code = G3D_ASSIGN_IGNORE;
-    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0;
-    if (valid) {
-        code = __ldg(p.assign + row);
-        if (CS == 8) {
-            const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
-            c0 = ld_stream(cp);
-            c1 = ld_stream(cp + 1);
-        }
-    }
-    const float npos = __ldg(p.per_image + 4 * b + 3);
-    const float s_cls = __ldg(p.grad_out + 0) / ((float)p.B * fmaxf(npos, 1.0f));
-    // ---- zero-fill this warp's rows of dreg (R floats each, contiguous across the warp)
-    {
-        const int64_t wrow0 = (int64_t)b * p.A + (a - lane);             // first row of the warp
-        const int nrows = min(32, p.A - (a - lane));
-        if (nrows > 0) {
-            float* base = p.dreg + wrow0 * p.R;
-            const int nfloat = nrows * p.R;
-            if (((uintptr_t)base & 15) == 0) {
-                const int nvec = nfloat >> 2;
-                for (int i = lane; i < nvec; i += 32) reinterpret_cast<float4*>(base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int i = (nvec << 2) + lane; i < nfloat; i += 32) base[i] = 0.0f;
-            } else {
-                for (int i = lane; i < nfloat; i += 32) base[i] = 0.0f;
-            }
-        }
-    }
-    if (valid) {
-        const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+    const int64_t items = (int64_t)p.T * p.B;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = (int)(item / p.T);
+        const int a = (int)(item - (int64_t)b * p.T) * 256 + threadIdx.x;
+        const bool valid = a < p.A;
+        const int64_t row = (int64_t)b * p.A + a;
+        int code = G3D_ASSIGN_IGNORE;
+        if (valid) code = __ldg(p.assign + row);
+        const float npos = __ldg(p.per_image + 4 * b + 3);
         int pos_cls = -1;
-        if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
-        if (CS == 8) {
-            const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            float g[8];
-            if (code == G3D_ASSIGN_NEGATIVE) {
-                focal_neg_grad8(pv, s_cls, g);
-            } else {
+        const float* grow = nullptr;
+        if (code >= 0) {
+            grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
+            pos_cls = (int)(long long)grow[cls_col];
+        }
+        if (!p.have_dcls) {
+            const int nrows = min(32, p.A - (a - lane));
+            if (nrows > 0) zero_rows(p.dreg + ((int64_t)b * p.A + (a - lane)) * p.R, nrows * p.R, lane);
+        }
+        if (!cls_ok && valid) {
+            const float s_cls = go0 / ((float)p.B * fmaxf(npos, 1.0f));
+            if (CS == 8) {
+                const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
+                const float4 c0 = ld_stream(cp), c1 = ld_stream(cp + 1);
+                const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                float g[8];
+                if (code == G3D_ASSIGN_NEGATIVE) {
+                    focal_neg<8, true>(pv, s_cls, g);
+                } else {
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+                    for (int c = 0; c < 8; ++c)
+                        g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+                }
+                float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
+                st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
+                st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
+            } else {
+                const float* cp = p.cls + row * C;
+                float* dp = p.dcls + row * C;
+                for (int c = 0; c < C; ++c)
+                    dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
             }
-            float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
-            st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
-            st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
-        } else {
-            const float* cp = p.cls + row * C;
-            float* dp = p.dcls + row * C;
-            for (int c = 0; c < C; ++c)
-                dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
+        }
+        __syncwarp();   // a zero-fill above is ordered before the positive rows written below
+        if (code >= 0) {
+            const float per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0f : 4.0f;
+            const float s_reg = go1 / ((float)p.B * per_pos * npos);
+            const float s_vp = (VARIANT == G3D_VARIANT_3D) ? go2 / (__ldg(p.losses + 3) * npos * 3.0f) : 0.0f;
+            float unused0, unused1;
+            positive_row<VARIANT>(p.reg + row * p.R, grow, __ldg(p.anchors + a), s_reg, s_vp, p.dreg + row * p.R, unused0,
+                                  unused1);
         }
     }
-    __syncwarp();   // the zero-fill above is ordered before the positive rows written below
-    if (code >= 0) positive_grad<VARIANT>(p, b, a, code, npos);
 }
 
 struct FocalWorkspace {
@@ -647,7 +742,7 @@ struct FocalWorkspace {
     int32_t* gt_row;
     int32_t* gt_count;
     double* partials;
-    int32_t* counters;
+    int32_t* counters;   // [B] image tickets, [1] batch ticket, [B] positives per image
     int64_t bytes;
 };
 
@@ -660,7 +755,7 @@ static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
     w.gt_row = (int32_t*)(p + off);  off += align_up(B * Gmax * 4, 256);
     w.gt_count = (int32_t*)(p + off); off += align_up(B * 4, 256);
     w.partials = (double*)(p + off); off += align_up(B * T * 32, 256);
-    w.counters = (int32_t*)(p + off); off += align_up((B + 1) * 4, 256);
+    w.counters = (int32_t*)(p + off); off += align_up((2 * B + 1) * 4, 256);
     w.bytes = off;
     return w;
 }
@@ -677,8 +772,7 @@ extern "C" int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax)
 static int check_focal_shapes(int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant) {
     G3D_REQUIRE(variant == G3D_VARIANT_2D || variant == G3D_VARIANT_3D, "unknown variant");
     G3D_REQUIRE(B >= 1 && A >= 1 && C >= 1 && Gmax >= 0, "sizes must be positive");
-    G3D_REQUIRE(B <= 65535 * (int64_t)kImgPerCta && A < ((int64_t)1 << 31) - kTile && Gmax < (1 << 30) && C < (1 << 20),
-                "size out of range");
+    G3D_REQUIRE(B <= 65535 && A < ((int64_t)1 << 31) - kTile && Gmax < (1 << 30) && C < (1 << 20), "size out of range");
     if (variant == G3D_VARIANT_3D) {
         G3D_REQUIRE(R == 12, "3D variant needs 12 regression outputs per anchor");
         G3D_REQUIRE(W >= 21, "3D variant needs >= 21 annotation columns");
@@ -689,64 +783,98 @@ static int check_focal_shapes(int64_t B, int64_t A, int64_t C, int64_t R, int64_
     return G3D_OK;
 }
 
+template <int VARIANT, int CS>
+static void launch_stream(const StreamArgs& p, bool grad, dim3 grid, cudaStream_t st) {
+    if (grad) focal_stream_kernel<VARIANT, CS, true><<<grid, kTile, 0, st>>>(p);
+    else      focal_stream_kernel<VARIANT, CS, false><<<grid, kTile, 0, st>>>(p);
+}
+
+extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
+                                      int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
+                                      float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
+                                      int32_t* gt_count_out, float* dcls, float* dreg, void* workspace,
+                                      int64_t workspace_bytes, void* const* trace_events, int device, void* stream) {
+    int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
+    if (rc != G3D_OK) return rc;
+    G3D_REQUIRE(cls && reg && anchors && losses && per_image && assign && workspace, "null pointer");
+    G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
+    G3D_REQUIRE((dcls == nullptr) == (dreg == nullptr), "dcls and dreg must both be given or both be null");
+    FocalWorkspace w = carve(workspace, B, A, Gmax);
+    G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see g3d_focal_workspace_bytes)");
+    G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)anchors % 16) == 0 && ((uintptr_t)workspace % 256) == 0 &&
+                    ((uintptr_t)per_image % 16) == 0 && ((uintptr_t)dcls % 16) == 0,
+                "cls/dcls/anchors/per_image must be 16-byte aligned and the workspace 256-byte aligned");
+    G3D_GUARD(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // launch 0: GT prologue; the same kernel zeroes the tickets and the positive counters
+    rc = gt_prepare_launch(ann, B, Gmax, W, variant, (float*)w.gt_box, w.gt_row, w.gt_count, w.counters, 2 * B + 1, device,
+                           stream);
+    if (rc != G3D_OK) return rc;
+    int32_t* npos = w.counters + B + 1;
+
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[0], st));
+    AssignCodesArgs q;
+    q.anchors = (const float4*)anchors; q.gt_box = w.gt_box; q.gt_row = w.gt_row; q.gt_count = w.gt_count;
+    q.assign = assign; q.npos = npos; q.B = (int)B; q.A = (int)A; q.Gmax = (int)Gmax;
+    const int T = (int)ceil_div(A, kTile);
+    assign_codes_kernel<<<dim3((unsigned)T, (unsigned)ceil_div(B, kImgPerCta)), kTile, 0, st>>>(q);
+    G3D_LAUNCH_CHECK();
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));
+
+    StreamArgs p;
+    p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
+    p.assign = assign; p.npos = npos; p.gt_count = w.gt_count; p.gt_count_out = gt_count_out;
+    p.partials = w.partials; p.counters = w.counters; p.losses = losses; p.per_image = per_image;
+    p.dcls = dcls; p.dreg = dreg;
+    p.g0 = grad_cls_expected;
+    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W; p.T = T;
+    const dim3 grid((unsigned)T, (unsigned)B);
+    const bool grad = dcls != nullptr;
+    if (variant == G3D_VARIANT_3D) {
+        if (C == 8) launch_stream<G3D_VARIANT_3D, 8>(p, grad, grid, st);
+        else        launch_stream<G3D_VARIANT_3D, 0>(p, grad, grid, st);
+    } else {
+        if (C == 8) launch_stream<G3D_VARIANT_2D, 8>(p, grad, grid, st);
+        else        launch_stream<G3D_VARIANT_2D, 0>(p, grad, grid, st);
+    }
+    G3D_LAUNCH_CHECK();
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
+    return G3D_OK;
+}
+
 extern "C" int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                   int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                                   float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
                                   void* workspace, int64_t workspace_bytes, int device, void* stream) {
-    int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
-    if (rc != G3D_OK) return rc;
-    G3D_REQUIRE(cls && reg && anchors && losses && per_image && workspace, "null pointer");
-    G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
-    FocalWorkspace w = carve(workspace, B, A, Gmax);
-    G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see g3d_focal_workspace_bytes)");
-    G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)anchors % 16) == 0 && ((uintptr_t)workspace % 256) == 0 &&
-                    ((uintptr_t)per_image % 16) == 0,
-                "cls/anchors/per_image must be 16-byte aligned and the workspace 256-byte aligned");
-    G3D_GUARD(device);
-    cudaStream_t st = (cudaStream_t)stream;
-    G3D_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(int32_t) * (B + 1), st));
-    rc = g3d_gt_prepare(ann, B, Gmax, W, variant, (float*)w.gt_box, w.gt_row, w.gt_count, device, stream);
-    if (rc != G3D_OK) return rc;
-    FocalArgs p;
-    p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
-    p.gt_box = w.gt_box; p.gt_row = w.gt_row; p.gt_count = w.gt_count;
-    p.partials = w.partials; p.counters = w.counters;
-    p.losses = losses; p.per_image = per_image; p.assign = assign;
-    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
-    p.T = (int)ceil_div(A, kTile);
-    dim3 grid((unsigned)p.T, (unsigned)ceil_div(B, kImgPerCta));
-    if (variant == G3D_VARIANT_3D) {
-        if (C == 8) focal_fwd_kernel<G3D_VARIANT_3D, 8><<<grid, kTile, 0, st>>>(p);
-        else        focal_fwd_kernel<G3D_VARIANT_3D, 0><<<grid, kTile, 0, st>>>(p);
-    } else {
-        if (C == 8) focal_fwd_kernel<G3D_VARIANT_2D, 8><<<grid, kTile, 0, st>>>(p);
-        else        focal_fwd_kernel<G3D_VARIANT_2D, 0><<<grid, kTile, 0, st>>>(p);
-    }
-    G3D_LAUNCH_CHECK();
-    if (gt_count_out)
-        G3D_CUDA(cudaMemcpyAsync(gt_count_out, w.gt_count, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
-    return G3D_OK;
+    return g3d_focal_loss_fwd_bwd(cls, reg, anchors, ann, B, A, C, R, Gmax, W, variant, 0.0f, losses, per_image,
+                                  assign, gt_count_out, nullptr, nullptr, workspace, workspace_bytes, nullptr, device, stream);
 }
 
 extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                   int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                                  const float* grad_out, const float* per_image, const float* losses,
-                                  const int32_t* assign, float* dcls, float* dreg, int device, void* stream) {
+                                  const float* grad_out, int have_dcls, float grad_cls_expected, const float* per_image,
+                                  const float* losses, const int32_t* assign, float* dcls, float* dreg, int device,
+                                  void* stream) {
     int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
     if (rc != G3D_OK) return rc;
     G3D_REQUIRE(cls && reg && anchors && grad_out && per_image && losses && assign && dcls && dreg, "null pointer");
     G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
     G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)dcls % 16) == 0 && ((uintptr_t)anchors % 16) == 0,
                 "cls/dcls/anchors must be 16-byte aligned");
-    G3D_REQUIRE(B <= 65535, "B out of range for the backward grid");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
     FocalBwdArgs p;
     p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
     p.grad_out = grad_out; p.per_image = per_image; p.losses = losses; p.assign = assign;
     p.dcls = dcls; p.dreg = dreg;
+    p.have_dcls = have_dcls ? 1 : 0;
+    p.e0 = grad_cls_expected;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
-    dim3 grid((unsigned)ceil_div(A, 256), (unsigned)B);
+    p.T = (int)ceil_div(A, 256);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t items = (int64_t)p.T * B;
+    const int grid = (int)(items < (int64_t)sms * 8 ? items : (int64_t)sms * 8);
     if (variant == G3D_VARIANT_3D) {
         if (C == 8) focal_bwd_kernel<G3D_VARIANT_3D, 8><<<grid, 256, 0, st>>>(p);
         else        focal_bwd_kernel<G3D_VARIANT_3D, 0><<<grid, 256, 0, st>>>(p);

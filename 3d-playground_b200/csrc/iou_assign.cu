@@ -19,11 +19,14 @@ __global__ void __launch_bounds__(256) calc_iou_kernel(const float4* __restrict_
 // ------------------------------------------------------------------------------------------------- GT prologue (a6)
 // One CTA per image: drop rows whose class column is -1 (3D losses.py:54, 2D retinanet/losses.py:46), keep order,
 // and form the 2D box used for assignment (3D: min/max over the 8 projected corners, losses.py:93-107).
+// Optionally zero-fills `zero_n` int32 counters (the loss kernels' tickets) in the same launch.
 __global__ void __launch_bounds__(kTile) gt_prepare_kernel(const float* __restrict__ ann, int Gmax, int W, int variant,
                                                            float4* __restrict__ gt_box, int32_t* __restrict__ gt_row,
-                                                           int32_t* __restrict__ gt_count) {
+                                                           int32_t* __restrict__ gt_count, int32_t* __restrict__ zero_ptr,
+                                                           int zero_n) {
     __shared__ int wcount[kWarps];
     const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = b * kTile + threadIdx.x; i < zero_n; i += gridDim.x * kTile) zero_ptr[i] = 0;
     const float* img = ann + (int64_t)b * Gmax * W;
     const int cls_col = (variant == G3D_VARIANT_3D) ? 20 : 4;
     int count = 0;
@@ -127,8 +130,19 @@ extern "C" int g3d_calc_iou(const float* a, int64_t A, const float* b, int64_t G
     return G3D_OK;
 }
 
+namespace g3d {
+int gt_prepare_launch(const float* ann, int64_t B, int64_t Gmax, int64_t W, int variant, float* gt_box, int32_t* gt_row,
+                      int32_t* gt_count, int32_t* zero_ptr, int64_t zero_n, int device, void* stream);
+}
+
 extern "C" int g3d_gt_prepare(const float* ann, int64_t B, int64_t Gmax, int64_t W, int variant, float* gt_box,
                               int32_t* gt_row, int32_t* gt_count, int device, void* stream) {
+    return g3d::gt_prepare_launch(ann, B, Gmax, W, variant, gt_box, gt_row, gt_count, nullptr, 0, device, stream);
+}
+
+int g3d::gt_prepare_launch(const float* ann, int64_t B, int64_t Gmax, int64_t W, int variant, float* gt_box,
+                           int32_t* gt_row, int32_t* gt_count, int32_t* zero_ptr, int64_t zero_n, int device,
+                           void* stream) {
     G3D_REQUIRE(B >= 0 && Gmax >= 0, "negative size");
     G3D_REQUIRE(variant == G3D_VARIANT_2D || variant == G3D_VARIANT_3D, "unknown variant");
     G3D_REQUIRE(variant == G3D_VARIANT_3D ? W >= 21 : W >= 5, "annotation rows too narrow for this variant");
@@ -137,8 +151,9 @@ extern "C" int g3d_gt_prepare(const float* ann, int64_t B, int64_t Gmax, int64_t
     G3D_REQUIRE(gt_count, "null pointer");
     G3D_REQUIRE(Gmax == 0 || (ann && gt_box && gt_row), "null pointer");
     G3D_GUARD(device);
+    G3D_REQUIRE(zero_n >= 0 && zero_n < (1 << 30) && (zero_n == 0 || zero_ptr), "bad counter range");
     gt_prepare_kernel<<<(int)B, kTile, 0, (cudaStream_t)stream>>>(ann, (int)Gmax, (int)W, variant, (float4*)gt_box,
-                                                                  gt_row, gt_count);
+                                                                  gt_row, gt_count, zero_ptr, (int)zero_n);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

@@ -47,9 +47,15 @@ def combine_stats(stats, group=None):
 
 class _ShardedFocalLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, classifications, regressions, anchors, annotations, group):
+    def forward(ctx, classifications, regressions, anchors, annotations, group, trace_events=None):
         from . import ops
-        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True)
+        # expected upstream gradient of the LOCAL classification mean: B_local / B_global = 1 / world for equal shards
+        # (a hint: the backward kernel checks it against the real value on the device and recomputes if it is off)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        needs_grad = classifications.requires_grad or regressions.requires_grad
+        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations,
+                                     grad_cls_expected=(1.0 / world) if needs_grad else None,
+                                     trace_events=trace_events if needs_grad else None)
         stats = local_stats(fwd["per_image"], fwd["gt_count"])
         losses, total = combine_stats(stats, group)
         ctx.fwd = fwd
@@ -63,11 +69,11 @@ class _ShardedFocalLossFn(torch.autograd.Function):
     def backward(ctx, g):
         from . import ops
         dcls, dreg = ops.focal_loss_backward(ctx.fwd, (g.to(torch.float32) * ctx.scale).contiguous())
-        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None
+        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None
 
 
-def sharded_focal_loss(classifications, regressions, anchors, annotations, group=None):
+def sharded_focal_loss(classifications, regressions, anchors, annotations, group=None, trace_events=None):
     """Loss of the global batch from this rank's image shard.  Returns float32[3] (cls, reg, vp), identical on every
     rank and differentiable w.r.t. the local classifications / regressions (gradients need no collective: they are
     per-image local, scaled by 1/B_global)."""
-    return _ShardedFocalLossFn.apply(classifications, regressions, anchors, annotations, group)
+    return _ShardedFocalLossFn.apply(classifications, regressions, anchors, annotations, group, trace_events)

@@ -16,32 +16,35 @@ def calc_iou(a, b):
 
 
 class _FocalLossFn(torch.autograd.Function):
-    """losses[3] = (cls, reg, vp) of the fused forward; backward = fused gradient kernel."""
+    """losses[3] = (cls, reg, vp).  When an input requires grad, the forward pass already writes the classification
+    gradient for the expected upstream gradient (1 for `(cls + reg + vp).backward()`,
+    train_detector_3D_angle.py:374-382) in the same sweep over the classification tensor; the backward kernel verifies
+    that expectation on the device and recomputes only if it does not hold."""
 
     @staticmethod
-    def forward(ctx, classifications, regressions, anchors, annotations, scale):
+    def forward(ctx, classifications, regressions, anchors, annotations, expected_grad, trace_events):
         needs_grad = classifications.requires_grad or regressions.requires_grad
-        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=needs_grad)
+        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations,
+                                     grad_cls_expected=float(expected_grad) if needs_grad else None,
+                                     trace_events=trace_events if needs_grad else None)
         ctx.fwd = fwd
-        ctx.scale = scale
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
         ctx.mark_non_differentiable(fwd["per_image"], fwd["gt_count"])
         return fwd["losses"][:3].clone(), fwd["losses"][3:4].clone(), fwd["per_image"], fwd["gt_count"]
 
     @staticmethod
     def backward(ctx, g_losses, _g_ne, _g_pi, _g_gc):
-        g = g_losses.to(torch.float32)
-        if ctx.scale is not None:   # distributed: rescale local means to global ones (dist.py)
-            g = g * ctx.scale
-        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g.contiguous())
+        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g_losses.to(torch.float32).contiguous())
         ctx.fwd = None
-        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None
+        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None
 
 
-def focal_loss(classifications, regressions, anchors, annotations, grad_scale=None):
+def focal_loss(classifications, regressions, anchors, annotations, expected_grad=1.0, trace_events=None):
     """Functional form.  Returns (losses[3], n_nonempty[1], per_image[B,4], gt_count[B]); losses is differentiable
-    w.r.t. classifications and regressions."""
-    return _FocalLossFn.apply(classifications, regressions, anchors, annotations, grad_scale)
+    w.r.t. classifications and regressions.  expected_grad: the upstream gradient the caller expects for the
+    classification loss (a performance hint only - any upstream gradient gives the right result).  trace_events: see
+    ops.focal_loss_forward (per-kernel timing for bench.py)."""
+    return _FocalLossFn.apply(classifications, regressions, anchors, annotations, expected_grad, trace_events)
 
 
 class FocalLoss(nn.Module):
@@ -56,12 +59,13 @@ class FocalLoss(nn.Module):
     with check_empty=False the vp loss is NaN in that case and no synchronisation happens.
     """
 
-    def __init__(self, check_empty=True):
+    def __init__(self, check_empty=True, expected_grad=1.0):
         super().__init__()
         self.check_empty = check_empty
+        self.expected_grad = expected_grad   # e.g. 1/n_replicas under nn.DataParallel + .mean() (a hint, see focal_loss)
 
     def forward(self, classifications, regressions, anchors, annotations):
-        losses, n_nonempty, _, _ = focal_loss(classifications, regressions, anchors, annotations)
+        losses, n_nonempty, _, _ = focal_loss(classifications, regressions, anchors, annotations, self.expected_grad)
         if regressions.shape[-1] == 12:
             if self.check_empty and float(n_nonempty.item()) == 0.0:
                 raise RuntimeError("stack expects a non-empty TensorList")  # the reference's torch.stack(vp_losses)

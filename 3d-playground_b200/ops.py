@@ -124,9 +124,17 @@ def assign(anchors, annotations, variant=None):
 
 
 # ------------------------------------------------------------------------------------------------ a2-a6: fused loss
-def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True):
-    """Fused FocalLoss forward.  Returns dict(losses f32[4], per_image f32[B,4], assign i32[B,A]|None, gt_count i32[B],
-    plus the prepared contiguous inputs for the backward)."""
+def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True, grad_cls_expected=None,
+                       trace_events=None):
+    """FocalLoss forward (assignment launch + streaming loss launch).  Returns dict(losses f32[4], per_image f32[B,4],
+    assign i32[B,A], gt_count i32[B], plus the prepared contiguous inputs for the backward).
+
+    grad_cls_expected (host float, e.g. 1.0): ALSO write, in the same pass over the classification tensor, the
+    classification gradient for that upstream gradient and zero-fill the regression gradient (dict keys "dcls", "dreg",
+    "grad_cls_expected"); focal_loss_backward then confirms on the device that the upstream gradient is that one and
+    only adds the rows of the positive anchors.  `want_assign` is kept for API compatibility: the codes are always
+    produced (they link the two launches).  trace_events: 3 torch.cuda.Event(enable_timing=True) recorded before /
+    between / after the two launches (needs grad_cls_expected)."""
     dev = _need_cuda(classifications, regressions, anchors, annotations)
     cls = _prep(classifications, torch.float32)
     reg = _prep(regressions, torch.float32)
@@ -146,30 +154,52 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     ws = _workspace(wbytes, dev)
     losses = torch.empty((4,), dtype=torch.float32, device=dev)
     per_image = torch.empty((B, 4), dtype=torch.float32, device=dev)
-    code = torch.empty((B, A), dtype=torch.int32, device=dev) if want_assign else None
+    code = torch.empty((B, A), dtype=torch.int32, device=dev)
     gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
-    check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses), _p(per_image),
-                               _p(code), _p(gt_count), _p(ws), ws.numel(), _idx(dev), _stream(dev)),
-          "g3d_focal_loss_fwd")
-    return dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
-                ann=ann, variant=variant)
+    out = dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
+               ann=ann, variant=variant)
+    if grad_cls_expected is None:
+        check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses),
+                                   _p(per_image), _p(code), _p(gt_count), _p(ws), ws.numel(), _idx(dev), _stream(dev)),
+              "g3d_focal_loss_fwd")
+    else:
+        ge = ctypes.c_float(float(grad_cls_expected))
+        dcls = torch.empty_like(cls)
+        dreg = torch.empty_like(reg)
+        ev = None
+        if trace_events is not None:
+            for e in trace_events:          # torch creates the CUDA event lazily, on its first record
+                if not e.cuda_event:
+                    e.record(torch.cuda.current_stream(dev))
+            ev = (ctypes.c_void_p * 3)(*[e.cuda_event for e in trace_events])
+        check(L.g3d_focal_loss_fwd_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, ge, _p(losses),
+                                       _p(per_image), _p(code), _p(gt_count), _p(dcls), _p(dreg), _p(ws), ws.numel(),
+                                       ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
+        out.update(dcls=dcls, dreg=dreg, grad_cls_expected=ge.value)
+    return out
 
 
 def focal_loss_backward(fwd, grad_out):
-    """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R])."""
+    """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R]).
+
+    If the forward already wrote dcls for `grad_cls_expected`, the kernel compares grad_out[0] with it on the device: when
+    they agree it only writes the positive anchors' rows of dreg, otherwise it recomputes dcls as well (no host
+    synchronisation either way)."""
     cls, reg, anc, ann = fwd["cls"], fwd["reg"], fwd["anchors"], fwd["ann"]
     dev = cls.device
-    if fwd["assign"] is None:
-        raise Geom3dError("focal_loss_backward needs the assignment codes: call the forward with want_assign=True")
     B, A, C = cls.shape
     R = reg.shape[2]
     G, W = ann.shape[1], ann.shape[2]
     g = _prep(grad_out, torch.float32)
-    dcls = torch.empty_like(cls)
-    dreg = torch.empty_like(reg)
-    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g),
-                                        _p(fwd["per_image"]), _p(fwd["losses"]), _p(fwd["assign"]), _p(dcls), _p(dreg),
-                                        _idx(dev), _stream(dev)), "g3d_focal_loss_bwd")
+    if g.numel() != 3:
+        raise ValueError("grad_out must have 3 elements (cls, reg, vp)")
+    if fwd.get("dcls") is not None:
+        dcls, dreg, have, ge = fwd["dcls"], fwd["dreg"], 1, fwd["grad_cls_expected"]
+    else:
+        dcls, dreg, have, ge = torch.empty_like(cls), torch.empty_like(reg), 0, 0.0
+    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g), have,
+                                        ctypes.c_float(ge), _p(fwd["per_image"]), _p(fwd["losses"]), _p(fwd["assign"]),
+                                        _p(dcls), _p(dreg), _idx(dev), _stream(dev)), "g3d_focal_loss_bwd")
     return dcls, dreg
 
 

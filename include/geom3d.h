@@ -74,7 +74,7 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
                int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * a2-a6  FocalLoss.forward fused: assignment + focal classification loss + regression loss (+ direction loss)
+ * a2-a6  FocalLoss.forward (+ backward) : assignment + focal classification loss + regression loss (+ direction loss)
  *        3D losses.py:27-362 ; 2D retinanet/losses.py:27-177
  * cls[B,A,C] (post-sigmoid), reg[B,A,R] (R = 12 for 3D, 4 for 2D), anchors[A,4], ann[B,Gmax,W]
  * (W >= 21 for 3D - only cols 0..20 are read -, W == 5 for 2D).
@@ -84,24 +84,45 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *                      (NaN if there is none: the reference raises there, the Python wrapper turns it into the raise);
  *                      2D variant: losses[2] = 0.  losses[3] = number of images with >= 1 GT row.
  *   per_image[B,4]   = (cls_j, reg_j, vp_j, num_pos_j) per image (vp_j = 0 and flagged by gt_count==0 for empty images)
- *   assign[B,A]      = assignment codes (nullable; needed by the backward)
+ *   assign[B,A]      = assignment codes (required: they are the hand-over between the two launches and the backward)
+ *   gt_count_out[B]  = number of GT rows (class != -1) per image (nullable)
  * workspace: g3d_focal_workspace_bytes(B, A, Gmax) bytes, 256-byte aligned, contents undefined on entry.
+ *
+ * g3d_focal_loss_fwd      : the losses only.
+ * g3d_focal_loss_fwd_bwd  : the losses AND, in the same pass over cls, the classification gradient dcls[B,A,C] of
+ *                           grad_cls_expected * losses[0]  (grad_cls_expected = the upstream gradient the caller
+ *                           expects for the classification loss: 1 for `(cls + reg + vp).backward()`), plus the
+ *                           zero-fill of dreg[B,A,R].  g3d_focal_loss_bwd(have_dcls = 1) completes the backward.
+ *                           dcls == dreg == NULL degrades to g3d_focal_loss_fwd.
+ *                           trace_events (nullable): 3 cudaEvent_t handles recorded on `stream` before the assignment
+ *                           launch, between the two launches and after the streaming launch (per-kernel timing
+ *                           without a profiler; bench.py's roofline figures come from these).
  */
 int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax);
 int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                        float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
                        void* workspace, int64_t workspace_bytes, int device, void* stream);
+int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
+                           int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
+                           float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
+                           int32_t* gt_count_out, float* dcls, float* dreg,
+                           void* workspace, int64_t workspace_bytes, void* const* trace_events, int device, void* stream);
 
-/* backward of the above (autograd of the reference graph, same file:lines).
+/* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
  * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory).
- * per_image / losses / assign = what the forward wrote.  dcls[B,A,C] is fully written; dreg[B,A,R] is fully
- * written (zeros on non-positive anchors).
+ * per_image / losses / assign = what the forward wrote.  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is
+ * zero on non-positive anchors).
+ * have_dcls = 0: dcls / dreg are uninitialised; everything is computed here.
+ * have_dcls = 1: they come from g3d_focal_loss_fwd_bwd(grad_cls_expected).  The kernel compares grad_out[0] with
+ *   grad_cls_expected ON THE DEVICE: equal (the usual training step) -> it only scans the codes and writes the
+ *   regression-gradient rows of the positive anchors; different -> it also recomputes dcls.  No host synchronisation
+ *   is needed to pick the path.
  */
 int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                       const float* grad_out, const float* per_image, const float* losses, const int32_t* assign,
-                       float* dcls, float* dreg, int device, void* stream);
+                       const float* grad_out, int have_dcls, float grad_cls_expected, const float* per_image,
+                       const float* losses, const int32_t* assign, float* dcls, float* dreg, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a7  3D BBoxTransform.forward     pytorch_retinanet_detector_directional/retinanet/utils.py:102-149

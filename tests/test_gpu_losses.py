@@ -121,6 +121,58 @@ def test_generic_class_count_and_gradients_vs_autograd_oracle():
     assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg")
 
 
+@pytest.mark.parametrize("three_d", [True, False])
+@pytest.mark.parametrize("upstream", [(1.0, 1.0, 1.0), (1.0, 0.25, 3.0), (0.5, 1.0, 1.0)])
+def test_forward_written_gradients_vs_autograd_oracle(three_d, upstream):
+    """the usual step - (cls + reg + vp).backward() - takes the classification gradient written during the forward pass;
+    other upstream gradients must give the autograd result as well (device-side check, then recompute)"""
+    _, li = _mods()
+    from oracle import losses_oracle as lo
+    g = synth.gen(31)
+    anc = synth.anchors(120, 160)
+    A = anc.shape[1]
+    maker = synth.gt_annotations_3d if three_d else synth.gt_annotations_2d
+    ann = maker(3, 12, 120, 160, g, n_pad=2, empty_images=(1,), **synth.TINY)
+    cls, reg = synth.head_outputs(3, A, 8, 12 if three_d else 4, g)
+    cls[0, :50] = torch.rand(50, 8, generator=g)            # probabilities beyond the series range and the clamp
+    cls[0, 50:60, 0] = 1e-5
+    cls[0, 60:70, 1] = 1.0 - 1e-6
+    n = 3 if three_d else 2
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref = lo.focal_loss(c0, r0, anc, ann)[:-1]
+    sum(upstream[i] * ref[i].sum() for i in range(n)).backward()
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    out = li.FocalLoss()(c1, r1, anc.cuda(), ann.cuda())
+    sum(upstream[i] * out[i].sum() for i in range(n)).backward()
+    assert_close_rel(torch.cat(out).detach().cpu(), torch.cat(ref).detach(), TOL, "losses")
+    assert_close_rel(c1.grad.cpu(), c0.grad, TOL, "dcls")
+    assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg")
+    assert torch.equal(c1.grad.cpu() == 0, c0.grad == 0)
+    assert torch.equal(r1.grad.cpu() == 0, r0.grad == 0)
+
+
+def test_backward_keeps_forward_written_dcls_only_when_upstream_matches():
+    """the device-side check: matching upstream gradient -> dcls untouched (poisoned here to see it); other -> recomputed"""
+    ops, _ = _mods()
+    g = synth.gen(32)
+    anc = synth.anchors(96, 96).cuda()
+    ann = synth.gt_annotations_3d(2, 6, 96, 96, g, **synth.TINY).cuda()
+    cls, reg = synth.head_outputs(2, anc.shape[1], 8, 12, g)
+    cls, reg = cls.cuda(), reg.cuda()
+    plain = ops.focal_loss_forward(cls, reg, anc, ann)
+    want_c, want_r = ops.focal_loss_backward(plain, torch.tensor([1.0, 2.0, 3.0]).cuda())
+    fwd = ops.focal_loss_forward(cls, reg, anc, ann, grad_cls_expected=1.0)
+    assert torch.equal(fwd["losses"], plain["losses"]) and torch.equal(fwd["assign"], plain["assign"])
+    assert torch.equal(fwd["dcls"], want_c) and int((fwd["dreg"] != 0).sum()) == 0
+    fwd["dcls"].fill_(7.0)
+    got_c, got_r = ops.focal_loss_backward(fwd, torch.tensor([1.0, 2.0, 3.0]).cuda())
+    assert bool((got_c == 7.0).all()), "upstream gradient matched: dcls must not be rewritten"
+    assert torch.equal(got_r, want_r)
+    got_c, got_r = ops.focal_loss_backward(fwd, torch.tensor([2.0, 2.0, 3.0]).cuda())
+    assert_close_rel(got_c.cpu(), (2 * want_c).cpu(), TOL, "recomputed dcls")
+    assert torch.equal(got_r, want_r)
+
+
 def test_all_empty_batch_raises_and_optional_nan():
     _, li = _mods()
     anc = synth.anchors(64, 64).cuda()
