@@ -42,7 +42,7 @@ SIGNATURES = {
                                       _f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _int,
                                       _c_ptr]),
     "g3d_focal_loss_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
-                                  _c_ptr, _int, _f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr]),
+                                  _c_ptr, _int, _f32, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_decode3d": (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_decode2d": (_int, [_c_ptr, _i64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _f32, _f32, _c_ptr, _int, _c_ptr]),
     "g3d_clip_boxes": (_int, [_c_ptr, _i64, _i64, _f32, _f32, _int, _c_ptr]),

@@ -61,9 +61,17 @@ __device__ __forceinline__ float focal_term(float p_raw, bool t) {
 //     -log(1 - pe) = 2 atanh(z) = 2 z (1 + z^2/3 + z^4/5 + z^6/7 + z^8/9 + ...),
 // truncated after z^8 (|z| < 1/7 for pe < 0.25: relative truncation error < 4e-10).  The series is evaluated on the
 // SAME rounded u the reference takes the log of, so it tracks torch.log(1.0 - classification) to ~2e-7 relative.
+// 1/x for x in a benign range (here [0.75, 2] and [1e-4, 1]): a single MUFU.RCP (<= 1 ulp).  __fdividef would add four
+// instructions of denormal-range scaling per quotient.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ float neg_log_u_series(float u) {   // valid for 1 - u < 0.25
     const float pe = 1.0f - u;
-    const float z = __fdividef(pe, 1.0f + u);
+    const float z = pe * rcp_fast(1.0f + u);
     const float z2 = z * z;
     float s = fmaf(z2, 1.0f / 9.0f, 1.0f / 7.0f);
     s = fmaf(z2, s, 0.2f);
@@ -78,7 +86,7 @@ __device__ __forceinline__ float neg_log_u(float u) {
 // N elements of NEGATIVE anchors (target 0): sum of 0.75 p^2 * -log(1-p) and, if GRAD, d/dp of each term times
 // `scale` (zero outside the clamp range: torch.clamp's backward passes min <= x <= max).  Straight-line code - the
 // series of all N elements first, so the dependency chains interleave - with a rare, separate fix-up for
-// probabilities >= 0.25 (which need the full logf).  The quotient p^2/u uses the 2-ulp fast division: gradients are
+// probabilities >= 0.25 (which need the full logf).  The quotient p^2/u uses the 1-ulp MUFU reciprocal: gradients are
 // compared at 1e-5 relative, nothing here is index-critical.
 template <int N, bool GRAD>
 __device__ __forceinline__ float focal_neg(const float* pv, float scale, float* g) {
@@ -102,7 +110,7 @@ __device__ __forceinline__ float focal_neg(const float* pv, float scale, float* 
         const float q = 0.75f * (p[c] * p[c]);
         acc = fmaf(q, nl[c], acc);
         if (GRAD) {
-            const float d = fmaf(1.5f * p[c], nl[c], __fdividef(q, 1.0f - p[c]));
+            const float d = fmaf(1.5f * p[c], nl[c], q * rcp_fast(1.0f - p[c]));
             g[c] = (p[c] == pv[c]) ? scale * d : 0.0f;   // p == p_raw  <=>  p_raw inside [min, max]
         }
     }
@@ -113,13 +121,13 @@ __device__ __forceinline__ float focal_neg(const float* pv, float scale, float* 
 __device__ __forceinline__ float focal_term_grad_neg(float p) {
     if (!(p >= G3D_PMIN && p <= G3D_PMAX)) return 0.0f;
     const float u = 1.0f - p;
-    return 1.5f * p * neg_log_u(u) + __fdividef(0.75f * (p * p), u);
+    return 1.5f * p * neg_log_u(u) + (0.75f * (p * p)) * rcp_fast(u);
 }
 __device__ __forceinline__ float focal_term_grad(float p, bool t) {
     if (!t) return focal_term_grad_neg(p);
     if (!(p >= G3D_PMIN && p <= G3D_PMAX)) return 0.0f;
     const float u = 1.0f - p;
-    return 0.5f * u * logf(p) - __fdividef(0.25f * (u * u), p);
+    return 0.5f * u * logf(p) - (0.25f * (u * u)) * rcp_fast(p);
 }
 
 __device__ __forceinline__ float smooth_l1(float d) {
@@ -268,6 +276,7 @@ struct AssignCodesArgs {
     const int32_t* gt_count;
     int32_t* assign;     // [B][A]
     int32_t* npos;       // [B], zero on entry
+    int32_t* pos_list;   // [B][A]: anchor indices of the positives of each image, in arrival order (first npos[b] valid)
     int B, A, Gmax;
 };
 
@@ -445,51 +454,143 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
         int code = G3D_ASSIGN_NEGATIVE;
         if (Gi > 0) code = assign_code(best, besti, p.gt_row + (int64_t)b * p.Gmax);
         if (valid) p.assign[(int64_t)b * p.A + a] = code;
-        const unsigned posmask = __ballot_sync(0xffffffffu, valid && code >= 0);
-        if (posmask && lane == 0) atomicAdd(p.npos + b, __popc(posmask));
+        // positives are appended to the image's list (integer atomics: the COUNT is deterministic, the order is not -
+        // everything downstream is order independent: per-row gradients, and loss sums in exact fixed point)
+        const bool is_pos = valid && code >= 0;
+        const unsigned posmask = __ballot_sync(0xffffffffu, is_pos);
+        if (posmask) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(p.npos + b, __popc(posmask));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (is_pos) p.pos_list[(int64_t)b * p.A + base + __popc(posmask & ((1u << lane) - 1u))] = a;
+        }
     }
 }
 
 // =====================================================================================================================
-// launch 2: the streaming loss (+ gradient) pass
+// launch 2: the positive anchors (dense: one thread per positive, from the lists launch 1 built)
 // =====================================================================================================================
-struct StreamArgs {
-    const float* cls;
+// Loss sums of the positives are accumulated in exact fixed point - two int64 limbs per sum, units 2^-20 and 2^-52 -
+// with integer atomics: integer addition is associative, so the result does not depend on the (non-deterministic)
+// order of the lists.  Range 2^43 per sum, absolute resolution 2^-52 per term.
+struct PosArgs {
     const float* reg;
     const float4* anchors;
+    const float* ann;
+    const int32_t* assign;
+    const int32_t* pos_list;
+    const int32_t* npos;
+    long long* acc;            // [B][4]: reg_hi, reg_lo, vp_hi, vp_lo (forward)
+    int32_t* nonfinite;        // [B]: set if a term was NaN / Inf / out of range (forward)
+    const float* grad_out;     // [3] device (backward)
+    const float* losses;       // [4] (backward: losses[3] = number of images with >= 1 GT row)
+    float* dreg;               // (backward)
+    int B, A, R, Gmax, W;
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void fixed_split(float t, long long& hi, long long& lo, bool& bad) {
+    bad = !(fabsf(t) < 1.0e12f);            // NaN, Inf, or beyond the 2^43 range of the high limb
+    const double td = bad ? 0.0 : (double)t;
+    const double h = floor(td * 1048576.0);                              // 2^20
+    hi = (long long)h;
+    lo = (long long)((td - h * (1.0 / 1048576.0)) * 4503599627370496.0);  // 2^52: in [0, 2^32)
+}
+
+template <int VARIANT, bool BWD>
+__global__ void __launch_bounds__(128) positives_kernel(const PosArgs p) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int n = min(__ldg(p.npos + b), p.A);
+    const float npos = (float)n;
+    float s_reg = 0.0f, s_vp = 0.0f;
+    if (BWD) {
+        const float per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0f : 4.0f;
+        s_reg = __ldg(p.grad_out + 1) / ((float)p.B * per_pos * npos);
+        if (VARIANT == G3D_VARIANT_3D) s_vp = __ldg(p.grad_out + 2) / (__ldg(p.losses + 3) * npos * 3.0f);
+    }
+    const int n_up = (n + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += gridDim.x * blockDim.x) {
+        float reg_sum = 0.0f, vp_term = 0.0f;
+        if (i < n) {
+            const int a = __ldg(p.pos_list + (int64_t)b * p.A + i);
+            const int64_t row = (int64_t)b * p.A + a;
+            const int code = __ldg(p.assign + row);
+            const float* grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
+            positive_row<VARIANT>(p.reg + row * p.R, grow, __ldg(p.anchors + a), s_reg, s_vp,
+                                  BWD ? p.dreg + row * p.R : nullptr, reg_sum, vp_term);
+        }
+        if (!BWD) {
+            long long rh, rl, vh, vl;
+            bool bad_r, bad_v;
+            fixed_split(reg_sum, rh, rl, bad_r);
+            fixed_split(vp_term, vh, vl, bad_v);
+            rh = warp_sum_ll(rh); rl = warp_sum_ll(rl);
+            if (VARIANT == G3D_VARIANT_3D) { vh = warp_sum_ll(vh); vl = warp_sum_ll(vl); }
+            const bool any_bad = __any_sync(0xffffffffu, bad_r || bad_v);
+            if (lane == 0) {
+                unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.acc + 4 * b);
+                atomicAdd(acc + 0, (unsigned long long)rh);
+                atomicAdd(acc + 1, (unsigned long long)rl);
+                if (VARIANT == G3D_VARIANT_3D) {
+                    atomicAdd(acc + 2, (unsigned long long)vh);
+                    atomicAdd(acc + 3, (unsigned long long)vl);
+                }
+                if (any_bad) atomicOr(p.nonfinite + b, 1);
+            }
+        }
+    }
+}
+
+// =====================================================================================================================
+// launch 3: the streaming classification pass (loss terms + gradient) - the dominant, HBM-bound kernel
+// =====================================================================================================================
+constexpr int kChunksPerWarp = 4;                            // 32-row chunks handled by one warp
+constexpr int kRowsPerCta = kWarps * 32 * kChunksPerWarp;    // 1024 (image, anchor) rows per CTA
+
+struct StreamArgs {
+    const float* cls;
     const float* ann;
     const int32_t* assign;     // [B][A]
     const int32_t* npos;       // [B]
     const int32_t* gt_count;   // [B]
+    const long long* acc;      // [B][4] fixed-point sums of the positives (launch 2)
+    const int32_t* nonfinite;  // [B]
     int32_t* gt_count_out;     // [B] or null: copy of gt_count for the caller
-    double* partials;          // [B][T][4] : cls_sum, -, reg_sum, vp_sum
-    int32_t* counters;         // [B+1], zero on entry
+    double* partials;          // [B][T]: classification partial sums, one per CTA
+    int32_t* counters;         // [B] image tickets + [1] batch ticket, zero on entry
     float* losses;             // [4] : cls, reg, vp, number of non-empty images
     float* per_image;          // [B][4]
     float* dcls;               // [B][A][C]  (GRAD only)
-    float* dreg;               // [B][A][R]  (GRAD only)
+    float* dreg;               // [B][A][R]  (GRAD only: zero-filled here)
     float g0;                  // upstream gradient of the classification loss that dcls is formed for
     int B, A, C, R, Gmax, W, T;
 };
 
-// Executed by ONE warp - the last tile of image b: reduce the image's T partials in a fixed order (lane-strided
+// Executed by ONE warp - the last CTA of image b: reduce the image's T partials in a fixed order (lane-strided
 // accumulation + shuffle tree), then (last image of the batch) the batch means.
 template <int VARIANT>
 __device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
     const int lane = threadIdx.x & 31;
     __threadfence();
-    double tc = 0.0, tr = 0.0, tv = 0.0;
-    const double2* src = reinterpret_cast<const double2*>(p.partials + (int64_t)b * p.T * 4);
+    double tc = 0.0;
+    const double* src = p.partials + (int64_t)b * p.T;
 #pragma unroll 4
-    for (int t = lane; t < p.T; t += 32) {
-        const double2 u = __ldcg(src + 2 * t), v = __ldcg(src + 2 * t + 1);
-        tc += u.x; tr += v.x; tv += v.y;
-    }
-    tc = warp_sum(tc); tr = warp_sum(tr); tv = warp_sum(tv);
+    for (int t = lane; t < p.T; t += 32) tc += __ldcg(src + t);
+    tc = warp_sum(tc);
     int last = 0;
     if (lane == 0) {
         const double tn = (double)__ldg(p.npos + b);
         const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
+        const long long* acc = p.acc + 4 * b;
+        const double lo_unit = 1.0 / 4503599627370496.0, hi_unit = 1.0 / 1048576.0;
+        double tr = (double)acc[0] * hi_unit + (double)acc[1] * lo_unit;
+        double tv = (double)acc[2] * hi_unit + (double)acc[3] * lo_unit;
+        if (__ldg(p.nonfinite + b)) tr = tv = __longlong_as_double(0x7ff8000000000000LL);   // NaN
         float4 o;
         o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
         o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
@@ -520,117 +621,135 @@ __device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
     }
 }
 
-// zero-fill the warp's rows of dreg (R floats each, contiguous across the warp) with coalesced 16-byte stores
-__device__ __forceinline__ void zero_rows(float* base, int nfloat, int lane) {
-    if (((uintptr_t)base & 15) == 0) {
-        const int nvec = nfloat >> 2;
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int i = lane; i < nvec; i += 32) st_stream(reinterpret_cast<float4*>(base) + i, z);
-        for (int i = (nvec << 2) + lane; i < nfloat; i += 32) base[i] = 0.0f;
+// zero-fill `nrows` consecutive rows of dreg (R floats each; 16-byte aligned because R is 4 or 12) with coalesced
+// 16-byte streaming stores
+template <int R>
+__device__ __forceinline__ void zero_rows(float* base, int nrows, int lane) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* b4 = reinterpret_cast<float4*>(base);
+    if (nrows == 32) {
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) st_stream(b4 + lane + 32 * k, z);
     } else {
-        for (int i = lane; i < nfloat; i += 32) base[i] = 0.0f;
+        for (int i = lane; i < nrows * (R / 4); i += 32) st_stream(b4 + i, z);
     }
 }
 
+// one 32-row chunk of the C == 8 path.  Lane l owns float4 l and l + 32 of the chunk's 64 (32 rows x 2): fully
+// coalesced in both directions.  Returns the lane's share of the chunk's focal sum.
+template <int VARIANT, bool GRAD>
+__device__ __forceinline__ float stream_chunk8(const StreamArgs& p, int b, int a0, int lane, float s_cls) {
+    const int nrows = min(32, p.A - a0);
+    if (nrows <= 0) return 0.0f;
+    const int64_t row0 = (int64_t)b * p.A + a0;
+    int code = G3D_ASSIGN_IGNORE;
+    if (lane < nrows) code = __ldg(p.assign + row0 + lane);
+    const float4* cp = reinterpret_cast<const float4*>(p.cls + row0 * 8);
+    float4* dp = reinterpret_cast<float4*>(p.dcls + row0 * 8);
+    const unsigned special = __ballot_sync(0xffffffffu, code != G3D_ASSIGN_NEGATIVE);   // missing rows count as special
+    float acc = 0.0f;
+    if (special == 0) {
+        const float4 v0 = ld_stream(cp + lane), v1 = ld_stream(cp + 32 + lane);
+        const float pv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+        float g[8];
+        acc = focal_neg<8, GRAD>(pv, s_cls, g);
+        if (GRAD) {
+            st_stream(dp + lane, make_float4(g[0], g[1], g[2], g[3]));
+            st_stream(dp + 32 + lane, make_float4(g[4], g[5], g[6], g[7]));
+        }
+    } else {
+        const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+        int pos_cls = -1;
+        if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h, r = j >> 1, c0 = (j & 1) * 4;
+            const int code_r = __shfl_sync(0xffffffffu, code, r);
+            const int pc_r = __shfl_sync(0xffffffffu, pos_cls, r);
+            if (r < nrows) {
+                const float4 v = ld_stream(cp + j);
+                const float pv[4] = {v.x, v.y, v.z, v.w};
+                float g[4];
+                if (code_r == G3D_ASSIGN_NEGATIVE) {
+                    acc += focal_neg<4, GRAD>(pv, s_cls, g);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        g[e] = 0.0f;
+                        if (code_r != G3D_ASSIGN_IGNORE) {
+                            acc += focal_term(pv[e], c0 + e == pc_r);
+                            if (GRAD) g[e] = s_cls * focal_term_grad(pv[e], c0 + e == pc_r);
+                        }
+                    }
+                }
+                if (GRAD) st_stream(dp + j, make_float4(g[0], g[1], g[2], g[3]));
+            }
+        }
+    }
+    if (GRAD) {
+        if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + row0 * 12, nrows, lane);
+        else                           zero_rows<4>(p.dreg + row0 * 4, nrows, lane);
+    }
+    return acc;
+}
+
+// generic class count: one thread per row, scalar accesses
+template <int VARIANT, bool GRAD>
+__device__ __forceinline__ float stream_chunk_any(const StreamArgs& p, int b, int a0, int lane, float s_cls) {
+    const int nrows = min(32, p.A - a0);
+    if (nrows <= 0) return 0.0f;
+    const int64_t row0 = (int64_t)b * p.A + a0;
+    float acc = 0.0f;
+    if (lane < nrows) {
+        const int code = __ldg(p.assign + row0 + lane);
+        const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
+        int pos_cls = -1;
+        if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
+        const int C = p.C;
+        const float* cp = p.cls + (row0 + lane) * C;
+        float* dp = p.dcls + (row0 + lane) * C;
+        const bool ign = (code == G3D_ASSIGN_IGNORE);
+        for (int c = 0; c < C; ++c) {
+            const float pr = __ldg(cp + c);
+            if (!ign) acc += focal_term(pr, c == pos_cls);
+            if (GRAD) dp[c] = ign ? 0.0f : s_cls * focal_term_grad(pr, c == pos_cls);
+        }
+    }
+    if (GRAD) {
+        if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + row0 * 12, nrows, lane);
+        else                           zero_rows<4>(p.dreg + row0 * 4, nrows, lane);
+    }
+    return acc;
+}
+
 struct StreamSmem {
-    double dred[3][kWarps];
+    double dred[kWarps];
     int arrive;
 };
 
 template <int VARIANT, int CS, bool GRAD>
-__global__ void __launch_bounds__(kTile, 6) focal_stream_kernel(const StreamArgs p) {
+__global__ void __launch_bounds__(kTile, 4) focal_stream_kernel(const StreamArgs p) {
     __shared__ StreamSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
-    const int a0 = blockIdx.x * kTile + warp * 32;   // first anchor of this warp
-    const int a = a0 + lane;
-    const bool valid = a < p.A;
-    const int64_t row0 = (int64_t)b * p.A + a0;
-    int code = G3D_ASSIGN_IGNORE;
-    if (valid) code = __ldg(p.assign + row0 + lane);
     if (tid == 0) sm.arrive = 0;
     __syncthreads();   // the ticket must be zero before the first warp finishes (all warps are still at the start: cheap)
     const float npos = (float)__ldg(p.npos + b);
     const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
-    const unsigned special = __ballot_sync(0xffffffffu, code != G3D_ASSIGN_NEGATIVE);   // invalid rows count as special
-    const int nrows = min(32, p.A - a0);
-
-    if (GRAD && nrows > 0) zero_rows(p.dreg + row0 * p.R, nrows * p.R, lane);
-
+    const int wa0 = blockIdx.x * kRowsPerCta + warp * (32 * kChunksPerWarp);   // first anchor of this warp
     float cls_acc = 0.0f;
-    const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
-    int pos_cls = -1;
-    const float* grow = nullptr;
-    if (code >= 0) {
-        grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
-        pos_cls = (int)(long long)grow[cls_col];
+#pragma unroll 2
+    for (int c = 0; c < kChunksPerWarp; ++c) {
+        if (CS == 8) cls_acc += stream_chunk8<VARIANT, GRAD>(p, b, wa0 + 32 * c, lane, s_cls);
+        else         cls_acc += stream_chunk_any<VARIANT, GRAD>(p, b, wa0 + 32 * c, lane, s_cls);
     }
-    if (CS == 8) {
-        // lane l owns float4 l and l + 32 of the warp's 64 (32 rows x 2): fully coalesced in both directions
-        const float4* cp = reinterpret_cast<const float4*>(p.cls + row0 * 8);
-        float4* dp = reinterpret_cast<float4*>(p.dcls + row0 * 8);
-        if (special == 0) {
-            const float4 v0 = ld_stream(cp + lane), v1 = ld_stream(cp + 32 + lane);
-            const float pv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            float g[8];
-            cls_acc = focal_neg<8, GRAD>(pv, s_cls, g);
-            if (GRAD) {
-                st_stream(dp + lane, make_float4(g[0], g[1], g[2], g[3]));
-                st_stream(dp + 32 + lane, make_float4(g[4], g[5], g[6], g[7]));
-            }
-        } else {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = lane + 32 * h, r = j >> 1, c0 = (j & 1) * 4;
-                const int code_r = __shfl_sync(0xffffffffu, code, r);
-                const int pc_r = __shfl_sync(0xffffffffu, pos_cls, r);
-                if (r < nrows) {
-                    const float4 v = ld_stream(cp + j);
-                    const float pv[4] = {v.x, v.y, v.z, v.w};
-                    float g[4];
-                    if (code_r == G3D_ASSIGN_NEGATIVE) {
-                        cls_acc += focal_neg<4, GRAD>(pv, s_cls, g);
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            g[e] = 0.0f;
-                            if (code_r != G3D_ASSIGN_IGNORE) {
-                                cls_acc += focal_term(pv[e], c0 + e == pc_r);
-                                if (GRAD) g[e] = s_cls * focal_term_grad(pv[e], c0 + e == pc_r);
-                            }
-                        }
-                    }
-                    if (GRAD) st_stream(dp + j, make_float4(g[0], g[1], g[2], g[3]));
-                }
-            }
-        }
-    } else if (valid) {
-        const int C = p.C;
-        const float* cp = p.cls + (row0 + lane) * C;
-        float* dp = p.dcls + (row0 + lane) * C;
-        for (int c = 0; c < C; ++c) {
-            const float pr = __ldg(cp + c);
-            const bool ign = (code == G3D_ASSIGN_IGNORE);
-            if (!ign) cls_acc += focal_term(pr, c == pos_cls);
-            if (GRAD) dp[c] = ign ? 0.0f : s_cls * focal_term_grad(pr, c == pos_cls);
-        }
-    }
-
-    // ---- positive anchors: regression / direction loss terms (their gradient rows are written by the backward)
-    float reg_acc = 0.0f, vp_acc = 0.0f;
-    const unsigned posmask = __ballot_sync(0xffffffffu, code >= 0);
-    if (code >= 0)
-        positive_row<VARIANT>(p.reg + (row0 + lane) * p.R, grow, __ldg(p.anchors + a), 0.0f, 0.0f, nullptr, reg_acc, vp_acc);
-
-    // ---- partial sums: FP32 inside the warp, FP64 from here on.  The last warp of the CTA to get here (shared-memory
-    // ticket, no block barrier: finished warps retire immediately) combines the 8 warp partials in warp order; the
-    // last tile of the image (global ticket) reduces that image.
+    // ---- partial sums: FP32 inside the warp (<= 1024 terms), FP64 from here on.  The last warp of the CTA to get here
+    // (shared-memory ticket, no block barrier: finished warps retire immediately) combines the 8 warp partials in warp
+    // order; the last CTA of the image (global ticket) reduces that image.
     const float cs = warp_sum_f(cls_acc);
-    float rs = 0.0f, vs = 0.0f;
-    if (posmask) { rs = warp_sum_f(reg_acc); vs = warp_sum_f(vp_acc); }
     int arrived = 0;
     if (lane == 0) {
-        sm.dred[0][warp] = (double)cs; sm.dred[1][warp] = (double)rs; sm.dred[2][warp] = (double)vs;
+        sm.dred[warp] = (double)cs;
         __threadfence_block();
         arrived = atomicAdd(&sm.arrive, 1);
     }
@@ -639,13 +758,11 @@ __global__ void __launch_bounds__(kTile, 6) focal_stream_kernel(const StreamArgs
     __threadfence_block();
     int is_last = 0;
     if (lane == 0) {
-        const volatile double* dr = &sm.dred[0][0];
-        double tc = 0.0, tr = 0.0, tv = 0.0;
+        const volatile double* dr = sm.dred;
+        double tc = 0.0;
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) { tc += dr[w]; tr += dr[kWarps + w]; tv += dr[2 * kWarps + w]; }
-        double* out = p.partials + ((int64_t)b * p.T + blockIdx.x) * 4;
-        __stcg(reinterpret_cast<double2*>(out), make_double2(tc, 0.0));
-        __stcg(reinterpret_cast<double2*>(out) + 1, make_double2(tr, tv));
+        for (int w = 0; w < kWarps; ++w) tc += dr[w];
+        __stcg(p.partials + (int64_t)b * p.T + blockIdx.x, tc);
         __threadfence();
         is_last = (atomicAdd(p.counters + b, 1) == p.T - 1);
     }
@@ -654,16 +771,13 @@ __global__ void __launch_bounds__(kTile, 6) focal_stream_kernel(const StreamArgs
 }
 
 // =====================================================================================================================
-// backward for upstream gradients other than the ones launch 2 was told to expect
+// backward, part 1: the classification gradient for upstream gradients other than the one launch 3 was told to expect
 // =====================================================================================================================
-struct FocalBwdArgs {
+struct ClsGradArgs {
     const float* cls;
-    const float* reg;
-    const float4* anchors;
     const float* ann;
     const float* grad_out;   // [3] device
-    const float* per_image;  // [B][4]
-    const float* losses;     // [4] (losses[3] = number of non-empty images)
+    const int32_t* npos;     // [B]
     const int32_t* assign;
     float* dcls;
     float* dreg;
@@ -672,13 +786,12 @@ struct FocalBwdArgs {
     int B, A, C, R, Gmax, W, T;
 };
 
-// Persistent grid-stride kernel over (image, tile) items, one thread per (image, anchor) row inside an item.
-// Usual training step (dcls already right): read the codes, write the few positive rows of dreg - ~50 MB of traffic.
+// Persistent grid-stride kernel over (image, 256-row tile) items, one thread per row.  The usual training step
+// (dcls already right) exits at once: one wave of CTAs.
 template <int VARIANT, int CS>
-__global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const FocalBwdArgs p) {
-    const float go0 = __ldg(p.grad_out + 0), go1 = __ldg(p.grad_out + 1);
-    const float go2 = (VARIANT == G3D_VARIANT_3D) ? __ldg(p.grad_out + 2) : 0.0f;
-    const bool cls_ok = p.have_dcls && go0 == p.e0;
+__global__ void __launch_bounds__(256, 4) focal_cls_grad_kernel(const ClsGradArgs p) {
+    const float go0 = __ldg(p.grad_out + 0);
+    if (p.have_dcls && go0 == p.e0) return;
     const int lane = threadIdx.x & 31;
     const int C = (CS > 0) ? CS : p.C;
     const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
@@ -688,51 +801,39 @@ __global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const FocalBwdArgs p)
         const int a = (int)(item - (int64_t)b * p.T) * 256 + threadIdx.x;
         const bool valid = a < p.A;
         const int64_t row = (int64_t)b * p.A + a;
-        int code = G3D_ASSIGN_IGNORE;
-        if (valid) code = __ldg(p.assign + row);
-        const float npos = __ldg(p.per_image + 4 * b + 3);
-        int pos_cls = -1;
-        const float* grow = nullptr;
-        if (code >= 0) {
-            grow = p.ann + ((int64_t)b * p.Gmax + code) * p.W;
-            pos_cls = (int)(long long)grow[cls_col];
-        }
         if (!p.have_dcls) {
             const int nrows = min(32, p.A - (a - lane));
-            if (nrows > 0) zero_rows(p.dreg + ((int64_t)b * p.A + (a - lane)) * p.R, nrows * p.R, lane);
-        }
-        if (!cls_ok && valid) {
-            const float s_cls = go0 / ((float)p.B * fmaxf(npos, 1.0f));
-            if (CS == 8) {
-                const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
-                const float4 c0 = ld_stream(cp), c1 = ld_stream(cp + 1);
-                const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                float g[8];
-                if (code == G3D_ASSIGN_NEGATIVE) {
-                    focal_neg<8, true>(pv, s_cls, g);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
-                }
-                float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
-                st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
-                st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
-            } else {
-                const float* cp = p.cls + row * C;
-                float* dp = p.dcls + row * C;
-                for (int c = 0; c < C; ++c)
-                    dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
+            if (nrows > 0) {
+                if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + (row - lane) * 12, nrows, lane);
+                else                           zero_rows<4>(p.dreg + (row - lane) * 4, nrows, lane);
             }
         }
-        __syncwarp();   // a zero-fill above is ordered before the positive rows written below
-        if (code >= 0) {
-            const float per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0f : 4.0f;
-            const float s_reg = go1 / ((float)p.B * per_pos * npos);
-            const float s_vp = (VARIANT == G3D_VARIANT_3D) ? go2 / (__ldg(p.losses + 3) * npos * 3.0f) : 0.0f;
-            float unused0, unused1;
-            positive_row<VARIANT>(p.reg + row * p.R, grow, __ldg(p.anchors + a), s_reg, s_vp, p.dreg + row * p.R, unused0,
-                                  unused1);
+        if (!valid) continue;
+        const int code = __ldg(p.assign + row);
+        const float npos = (float)__ldg(p.npos + b);
+        int pos_cls = -1;
+        if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
+        const float s_cls = go0 / ((float)p.B * fmaxf(npos, 1.0f));
+        if (CS == 8) {
+            const float4* cp = reinterpret_cast<const float4*>(p.cls + row * 8);
+            const float4 c0 = ld_stream(cp), c1 = ld_stream(cp + 1);
+            const float pv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            float g[8];
+            if (code == G3D_ASSIGN_NEGATIVE) {
+                focal_neg<8, true>(pv, s_cls, g);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    g[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(pv[c], c == pos_cls);
+            }
+            float4* dp = reinterpret_cast<float4*>(p.dcls + row * 8);
+            st_stream(dp, make_float4(g[0], g[1], g[2], g[3]));
+            st_stream(dp + 1, make_float4(g[4], g[5], g[6], g[7]));
+        } else {
+            const float* cp = p.cls + row * C;
+            float* dp = p.dcls + row * C;
+            for (int c = 0; c < C; ++c)
+                dp[c] = (code == G3D_ASSIGN_IGNORE) ? 0.0f : s_cls * focal_term_grad(__ldg(cp + c), c == pos_cls);
         }
     }
 }
@@ -741,24 +842,34 @@ struct FocalWorkspace {
     float4* gt_box;
     int32_t* gt_row;
     int32_t* gt_count;
-    double* partials;
-    int32_t* counters;   // [B] image tickets, [1] batch ticket, [B] positives per image
+    double* partials;    // [B][T]
+    int32_t* pos_list;   // [B][A]
+    int32_t* counters;   // zeroed per call: [B] image tickets, [1] batch ticket, [B] npos, [B] nonfinite flags, then
+                         // (8-byte aligned) [B][4] int64 fixed-point sums
+    int64_t n_counters;  // number of int32 words to zero
     int64_t bytes;
 };
 
 static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
     FocalWorkspace w;
-    const int64_t T = ceil_div(A, kTile);
+    const int64_t T = ceil_div(A, kRowsPerCta);
     int64_t off = 0;
     char* p = (char*)base;
     w.gt_box = (float4*)(p + off);   off += align_up(B * Gmax * 16, 256);
     w.gt_row = (int32_t*)(p + off);  off += align_up(B * Gmax * 4, 256);
     w.gt_count = (int32_t*)(p + off); off += align_up(B * 4, 256);
-    w.partials = (double*)(p + off); off += align_up(B * T * 32, 256);
-    w.counters = (int32_t*)(p + off); off += align_up((2 * B + 1) * 4, 256);
+    w.partials = (double*)(p + off); off += align_up(B * T * 8, 256);
+    w.pos_list = (int32_t*)(p + off); off += align_up(B * A * 4, 256);
+    w.counters = (int32_t*)(p + off);
+    const int64_t head = align_up(3 * B + 1, 2);          // int32 words before the int64 sums
+    w.n_counters = head + 8 * B;
+    off += align_up(w.n_counters * 4, 256);
     w.bytes = off;
     return w;
 }
+static inline int32_t* ws_npos(const FocalWorkspace& w, int64_t B) { return w.counters + B + 1; }
+static inline int32_t* ws_nonfinite(const FocalWorkspace& w, int64_t B) { return w.counters + 2 * B + 1; }
+static inline long long* ws_acc(const FocalWorkspace& w, int64_t B) { return (long long*)(w.counters + align_up(3 * B + 1, 2)); }
 
 }  // namespace g3d
 
@@ -772,7 +883,7 @@ extern "C" int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax)
 static int check_focal_shapes(int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant) {
     G3D_REQUIRE(variant == G3D_VARIANT_2D || variant == G3D_VARIANT_3D, "unknown variant");
     G3D_REQUIRE(B >= 1 && A >= 1 && C >= 1 && Gmax >= 0, "sizes must be positive");
-    G3D_REQUIRE(B <= 65535 && A < ((int64_t)1 << 31) - kTile && Gmax < (1 << 30) && C < (1 << 20), "size out of range");
+    G3D_REQUIRE(B <= 65535 && A < ((int64_t)1 << 31) - kRowsPerCta && Gmax < (1 << 30) && C < (1 << 20), "size out of range");
     if (variant == G3D_VARIANT_3D) {
         G3D_REQUIRE(R == 12, "3D variant needs 12 regression outputs per anchor");
         G3D_REQUIRE(W >= 21, "3D variant needs >= 21 annotation columns");
@@ -789,6 +900,8 @@ static void launch_stream(const StreamArgs& p, bool grad, dim3 grid, cudaStream_
     else      focal_stream_kernel<VARIANT, CS, false><<<grid, kTile, 0, st>>>(p);
 }
 
+static dim3 positives_grid(int64_t B) { return dim3(64, (unsigned)B); }
+
 extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                       int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                                       float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
@@ -802,33 +915,41 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     FocalWorkspace w = carve(workspace, B, A, Gmax);
     G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see g3d_focal_workspace_bytes)");
     G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)anchors % 16) == 0 && ((uintptr_t)workspace % 256) == 0 &&
-                    ((uintptr_t)per_image % 16) == 0 && ((uintptr_t)dcls % 16) == 0,
-                "cls/dcls/anchors/per_image must be 16-byte aligned and the workspace 256-byte aligned");
+                    ((uintptr_t)per_image % 16) == 0 && ((uintptr_t)dcls % 16) == 0 && ((uintptr_t)dreg % 16) == 0,
+                "cls/dcls/dreg/anchors/per_image must be 16-byte aligned and the workspace 256-byte aligned");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
-    // launch 0: GT prologue; the same kernel zeroes the tickets and the positive counters
-    rc = gt_prepare_launch(ann, B, Gmax, W, variant, (float*)w.gt_box, w.gt_row, w.gt_count, w.counters, 2 * B + 1, device,
-                           stream);
+    // launch 0: GT prologue; the same kernel zeroes the tickets, counters and fixed-point sums
+    rc = gt_prepare_launch(ann, B, Gmax, W, variant, (float*)w.gt_box, w.gt_row, w.gt_count, w.counters, w.n_counters,
+                           device, stream);
     if (rc != G3D_OK) return rc;
-    int32_t* npos = w.counters + B + 1;
+    int32_t* npos = ws_npos(w, B);
 
     if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[0], st));
     AssignCodesArgs q;
     q.anchors = (const float4*)anchors; q.gt_box = w.gt_box; q.gt_row = w.gt_row; q.gt_count = w.gt_count;
-    q.assign = assign; q.npos = npos; q.B = (int)B; q.A = (int)A; q.Gmax = (int)Gmax;
-    const int T = (int)ceil_div(A, kTile);
-    assign_codes_kernel<<<dim3((unsigned)T, (unsigned)ceil_div(B, kImgPerCta)), kTile, 0, st>>>(q);
+    q.assign = assign; q.npos = npos; q.pos_list = w.pos_list; q.B = (int)B; q.A = (int)A; q.Gmax = (int)Gmax;
+    assign_codes_kernel<<<dim3((unsigned)ceil_div(A, kTile), (unsigned)ceil_div(B, kImgPerCta)), kTile, 0, st>>>(q);
     G3D_LAUNCH_CHECK();
     if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));
 
+    PosArgs pp;
+    pp.reg = reg; pp.anchors = (const float4*)anchors; pp.ann = ann; pp.assign = assign; pp.pos_list = w.pos_list;
+    pp.npos = npos; pp.acc = ws_acc(w, B); pp.nonfinite = ws_nonfinite(w, B); pp.grad_out = nullptr; pp.losses = nullptr;
+    pp.dreg = nullptr; pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.W = (int)W;
+    if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+    else                           positives_kernel<G3D_VARIANT_2D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+    G3D_LAUNCH_CHECK();
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
+
     StreamArgs p;
-    p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
-    p.assign = assign; p.npos = npos; p.gt_count = w.gt_count; p.gt_count_out = gt_count_out;
+    p.cls = cls; p.ann = ann; p.assign = assign; p.npos = npos; p.gt_count = w.gt_count;
+    p.acc = ws_acc(w, B); p.nonfinite = ws_nonfinite(w, B); p.gt_count_out = gt_count_out;
     p.partials = w.partials; p.counters = w.counters; p.losses = losses; p.per_image = per_image;
-    p.dcls = dcls; p.dreg = dreg;
-    p.g0 = grad_cls_expected;
-    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W; p.T = T;
-    const dim3 grid((unsigned)T, (unsigned)B);
+    p.dcls = dcls; p.dreg = dreg; p.g0 = grad_cls_expected;
+    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
+    p.T = (int)ceil_div(A, kRowsPerCta);
+    const dim3 grid((unsigned)p.T, (unsigned)B);
     const bool grad = dcls != nullptr;
     if (variant == G3D_VARIANT_3D) {
         if (C == 8) launch_stream<G3D_VARIANT_3D, 8>(p, grad, grid, st);
@@ -838,7 +959,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
         else        launch_stream<G3D_VARIANT_2D, 0>(p, grad, grid, st);
     }
     G3D_LAUNCH_CHECK();
-    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[3], st));
     return G3D_OK;
 }
 
@@ -852,23 +973,23 @@ extern "C" int g3d_focal_loss_fwd(const float* cls, const float* reg, const floa
 
 extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                   int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                                  const float* grad_out, int have_dcls, float grad_cls_expected, const float* per_image,
-                                  const float* losses, const int32_t* assign, float* dcls, float* dreg, int device,
-                                  void* stream) {
+                                  const float* grad_out, int have_dcls, float grad_cls_expected, const float* losses,
+                                  const int32_t* assign, const void* workspace, int64_t workspace_bytes, float* dcls,
+                                  float* dreg, int device, void* stream) {
     int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
     if (rc != G3D_OK) return rc;
-    G3D_REQUIRE(cls && reg && anchors && grad_out && per_image && losses && assign && dcls && dreg, "null pointer");
+    G3D_REQUIRE(cls && reg && anchors && grad_out && losses && assign && workspace && dcls && dreg, "null pointer");
     G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
-    G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)dcls % 16) == 0 && ((uintptr_t)anchors % 16) == 0,
-                "cls/dcls/anchors must be 16-byte aligned");
+    G3D_REQUIRE(((uintptr_t)cls % 16) == 0 && ((uintptr_t)dcls % 16) == 0 && ((uintptr_t)dreg % 16) == 0 &&
+                    ((uintptr_t)anchors % 16) == 0 && ((uintptr_t)workspace % 256) == 0,
+                "cls/dcls/dreg/anchors must be 16-byte aligned and the workspace 256-byte aligned");
+    FocalWorkspace w = carve(const_cast<void*>(workspace), B, A, Gmax);
+    G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (pass the forward's workspace, untouched)");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
-    FocalBwdArgs p;
-    p.cls = cls; p.reg = reg; p.anchors = (const float4*)anchors; p.ann = ann;
-    p.grad_out = grad_out; p.per_image = per_image; p.losses = losses; p.assign = assign;
-    p.dcls = dcls; p.dreg = dreg;
-    p.have_dcls = have_dcls ? 1 : 0;
-    p.e0 = grad_cls_expected;
+    ClsGradArgs p;
+    p.cls = cls; p.ann = ann; p.grad_out = grad_out; p.npos = ws_npos(w, B); p.assign = assign;
+    p.dcls = dcls; p.dreg = dreg; p.e0 = grad_cls_expected; p.have_dcls = have_dcls ? 1 : 0;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
     p.T = (int)ceil_div(A, 256);
     int sms = 148;
@@ -876,12 +997,19 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     const int64_t items = (int64_t)p.T * B;
     const int grid = (int)(items < (int64_t)sms * 8 ? items : (int64_t)sms * 8);
     if (variant == G3D_VARIANT_3D) {
-        if (C == 8) focal_bwd_kernel<G3D_VARIANT_3D, 8><<<grid, 256, 0, st>>>(p);
-        else        focal_bwd_kernel<G3D_VARIANT_3D, 0><<<grid, 256, 0, st>>>(p);
+        if (C == 8) focal_cls_grad_kernel<G3D_VARIANT_3D, 8><<<grid, 256, 0, st>>>(p);
+        else        focal_cls_grad_kernel<G3D_VARIANT_3D, 0><<<grid, 256, 0, st>>>(p);
     } else {
-        if (C == 8) focal_bwd_kernel<G3D_VARIANT_2D, 8><<<grid, 256, 0, st>>>(p);
-        else        focal_bwd_kernel<G3D_VARIANT_2D, 0><<<grid, 256, 0, st>>>(p);
+        if (C == 8) focal_cls_grad_kernel<G3D_VARIANT_2D, 8><<<grid, 256, 0, st>>>(p);
+        else        focal_cls_grad_kernel<G3D_VARIANT_2D, 0><<<grid, 256, 0, st>>>(p);
     }
+    G3D_LAUNCH_CHECK();
+    PosArgs pp;
+    pp.reg = reg; pp.anchors = (const float4*)anchors; pp.ann = ann; pp.assign = assign; pp.pos_list = w.pos_list;
+    pp.npos = ws_npos(w, B); pp.acc = nullptr; pp.nonfinite = nullptr; pp.grad_out = grad_out; pp.losses = losses;
+    pp.dreg = dreg; pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.W = (int)W;
+    if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, true><<<positives_grid(B), 128, 0, st>>>(pp);
+    else                           positives_kernel<G3D_VARIANT_2D, true><<<positives_grid(B), 128, 0, st>>>(pp);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

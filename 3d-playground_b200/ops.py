@@ -133,8 +133,8 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     classification gradient for that upstream gradient and zero-fill the regression gradient (dict keys "dcls", "dreg",
     "grad_cls_expected"); focal_loss_backward then confirms on the device that the upstream gradient is that one and
     only adds the rows of the positive anchors.  `want_assign` is kept for API compatibility: the codes are always
-    produced (they link the two launches).  trace_events: 3 torch.cuda.Event(enable_timing=True) recorded before /
-    between / after the two launches (needs grad_cls_expected)."""
+    produced (they link the launches).  trace_events: 4 torch.cuda.Event(enable_timing=True) recorded before the
+    assignment launch, after it, after the positives launch and after the streaming launch (needs grad_cls_expected)."""
     dev = _need_cuda(classifications, regressions, anchors, annotations)
     cls = _prep(classifications, torch.float32)
     reg = _prep(regressions, torch.float32)
@@ -157,7 +157,7 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     code = torch.empty((B, A), dtype=torch.int32, device=dev)
     gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
     out = dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
-               ann=ann, variant=variant)
+               ann=ann, variant=variant, workspace=ws)   # the workspace holds the positive lists the backward reads
     if grad_cls_expected is None:
         check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses),
                                    _p(per_image), _p(code), _p(gt_count), _p(ws), ws.numel(), _idx(dev), _stream(dev)),
@@ -171,7 +171,7 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
             for e in trace_events:          # torch creates the CUDA event lazily, on its first record
                 if not e.cuda_event:
                     e.record(torch.cuda.current_stream(dev))
-            ev = (ctypes.c_void_p * 3)(*[e.cuda_event for e in trace_events])
+            ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in trace_events])
         check(L.g3d_focal_loss_fwd_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, ge, _p(losses),
                                        _p(per_image), _p(code), _p(gt_count), _p(dcls), _p(dreg), _p(ws), ws.numel(),
                                        ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
@@ -197,8 +197,9 @@ def focal_loss_backward(fwd, grad_out):
         dcls, dreg, have, ge = fwd["dcls"], fwd["dreg"], 1, fwd["grad_cls_expected"]
     else:
         dcls, dreg, have, ge = torch.empty_like(cls), torch.empty_like(reg), 0, 0.0
+    ws = fwd["workspace"]
     check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g), have,
-                                        ctypes.c_float(ge), _p(fwd["per_image"]), _p(fwd["losses"]), _p(fwd["assign"]),
+                                        ctypes.c_float(ge), _p(fwd["losses"]), _p(fwd["assign"]), _p(ws), ws.numel(),
                                         _p(dcls), _p(dreg), _idx(dev), _stream(dev)), "g3d_focal_loss_bwd")
     return dcls, dreg
 

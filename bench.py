@@ -307,7 +307,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]   # per-kernel events
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]   # per-kernel events
     for tr in kev:
         for e in tr:
             e.record()      # creates the CUDA events outside the timed region
@@ -326,10 +326,13 @@ def run_ours(args):
     ms_fwd = _event_ms([(e[0], e[1]) for e in evs]) / args.steps
     ms_bwd = _event_ms([(e[1], e[2]) for e in evs]) / args.steps
     ms_assign = _event_ms([(e[0], e[1]) for e in kev]) / args.steps
-    ms_stream = _event_ms([(e[1], e[2]) for e in kev]) / args.steps
+    ms_pos = _event_ms([(e[1], e[2]) for e in kev]) / args.steps
+    ms_stream = _event_ms([(e[2], e[3]) for e in kev]) / args.steps
     pairs_per_step = world * B * A * G_PER_IMG
     value = pairs_per_step / (ms_step * 1e-3) / 1e9
     loss_vals = [float(x) for x in losses.detach().cpu()]
+    with torch.no_grad():
+        per_image_vals = losses_impl.focal_loss(cls_d.detach(), reg_d.detach(), anc, ann_d)[2].cpu().tolist()
 
     # ---- end to end through the public module, from pinned host buffers
     cls_h = torch.empty((B, A, C_CLS), dtype=torch.float32).pin_memory()
@@ -370,12 +373,12 @@ def run_ours(args):
     del cls_h, reg_h, cls_in, reg_in
 
     if rank == 0:
-        # algorithmic bytes.  forward = assign_codes_kernel (anchors + GT in, codes out) followed by the
-        # dominant focal_stream_kernel: cls + codes in, dcls + zero-filled dreg out (regression / GT rows of the few
-        # positives are negligible).  backward (dcls already written): codes in, positive rows of dreg out.
+        # algorithmic bytes.  forward = assign_codes_kernel (anchors + GT in, codes out), the positives
+        # launch (negligible) and the dominant focal_stream_kernel: cls + codes in, dcls + zero-filled dreg out.
+        # backward (dcls already written): the positive rows only.
         stream_bytes = B * A * (C_CLS * 4 + 4 + C_CLS * 4 + R_REG * 4)
         fwd_bytes = stream_bytes + B * A * 4 + A * 16 + ann_h.numel() * 4
-        bwd_bytes = B * A * 4
+        bwd_bytes = int(sum(p[3] for p in per_image_vals)) * (R_REG * 4 * 2 + 4 + 21 * 4)
         dom, dom_bytes, dom_ms = "focal_stream_kernel", stream_bytes, ms_stream
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         line = {
@@ -389,11 +392,12 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": t_e2e * 1e3, "steps": e2e_steps},
-            "gpu_launches": 4 * args.steps,   # gt_prepare, assign_codes, focal_stream, focal_bwd per step
+            # gt_prepare, assign_codes, positives (fwd), focal_stream, focal_cls_grad, positives (bwd) per step
+            "gpu_launches": 6 * args.steps,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "ms": {"forward": ms_fwd, "backward": ms_bwd, "focal_stream_kernel": ms_stream,
-                                "assign_codes_kernel": ms_assign},
+                                "assign_codes_kernel": ms_assign, "positives_kernel": ms_pos},
                          "forward": {"bytes": fwd_bytes, "GBps": fwd_bytes / (ms_fwd * 1e-3) / 1e9,
                                      "frac": fwd_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak},
                          "backward": {"bytes": bwd_bytes, "GBps": bwd_bytes / (ms_bwd * 1e-3) / 1e9,

@@ -94,9 +94,9 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *                           expects for the classification loss: 1 for `(cls + reg + vp).backward()`), plus the
  *                           zero-fill of dreg[B,A,R].  g3d_focal_loss_bwd(have_dcls = 1) completes the backward.
  *                           dcls == dreg == NULL degrades to g3d_focal_loss_fwd.
- *                           trace_events (nullable): 3 cudaEvent_t handles recorded on `stream` before the assignment
- *                           launch, between the two launches and after the streaming launch (per-kernel timing
- *                           without a profiler; bench.py's roofline figures come from these).
+ *                           trace_events (nullable): 4 cudaEvent_t handles recorded on `stream` before the assignment
+ *                           launch, after it, after the positives launch and after the streaming launch (per-kernel
+ *                           timing without a profiler; bench.py's roofline figures come from these).
  */
 int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax);
 int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
@@ -111,18 +111,20 @@ int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anch
 
 /* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
  * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory).
- * per_image / losses / assign = what the forward wrote.  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is
- * zero on non-positive anchors).
+ * losses / assign / workspace = what the forward wrote (the workspace holds the per-image lists of positive anchors:
+ * keep it untouched between the two calls).  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is zero on
+ * non-positive anchors).
  * have_dcls = 0: dcls / dreg are uninitialised; everything is computed here.
  * have_dcls = 1: they come from g3d_focal_loss_fwd_bwd(grad_cls_expected).  The kernel compares grad_out[0] with
- *   grad_cls_expected ON THE DEVICE: equal (the usual training step) -> it only scans the codes and writes the
- *   regression-gradient rows of the positive anchors; different -> it also recomputes dcls.  No host synchronisation
- *   is needed to pick the path.
+ *   grad_cls_expected ON THE DEVICE: equal (the usual training step) -> only the regression-gradient rows of the
+ *   positive anchors are written (one thread per positive, from the lists); different -> dcls is recomputed as well.
+ *   No host synchronisation is needed to pick the path.
  */
 int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                       const float* grad_out, int have_dcls, float grad_cls_expected, const float* per_image,
-                       const float* losses, const int32_t* assign, float* dcls, float* dreg, int device, void* stream);
+                       const float* grad_out, int have_dcls, float grad_cls_expected, const float* losses,
+                       const int32_t* assign, const void* workspace, int64_t workspace_bytes,
+                       float* dcls, float* dreg, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a7  3D BBoxTransform.forward     pytorch_retinanet_detector_directional/retinanet/utils.py:102-149
