@@ -79,6 +79,7 @@ __device__ __forceinline__ float neg_log_u_series(float u) {   // valid for 1 - 
     s = fmaf(z2, s, 1.0f);
     return (z + z) * s;
 }
+__device__ __noinline__ float neg_log_full(float u) { return -logf(u); }   // rare: kept out of line (code size)
 __device__ __forceinline__ float neg_log_u(float u) {
     return (1.0f - u < 0.25f) ? neg_log_u_series(u) : -logf(u);
 }
@@ -102,7 +103,7 @@ __device__ __forceinline__ float focal_neg(const float* pv, float scale, float* 
     if (big) {
 #pragma unroll
         for (int c = 0; c < N; ++c)
-            if (!(1.0f - (1.0f - p[c]) < 0.25f)) nl[c] = -logf(1.0f - p[c]);
+            if (!(1.0f - (1.0f - p[c]) < 0.25f)) nl[c] = neg_log_full(1.0f - p[c]);
     }
     float acc = 0.0f;
 #pragma unroll
@@ -635,62 +636,83 @@ __device__ __forceinline__ void zero_rows(float* base, int nrows, int lane) {
     }
 }
 
-// one 32-row chunk of the C == 8 path.  Lane l owns float4 l and l + 32 of the chunk's 64 (32 rows x 2): fully
-// coalesced in both directions.  Returns the lane's share of the chunk's focal sum.
-template <int VARIANT, bool GRAD>
-__device__ __forceinline__ float stream_chunk8(const StreamArgs& p, int b, int a0, int lane, float s_cls) {
-    const int nrows = min(32, p.A - a0);
-    if (nrows <= 0) return 0.0f;
-    const int64_t row0 = (int64_t)b * p.A + a0;
-    int code = G3D_ASSIGN_IGNORE;
-    if (lane < nrows) code = __ldg(p.assign + row0 + lane);
+// Fix-up of one float4 (4 classes of row r) that belongs to a positive or ignored anchor.  Rare and divergent: compact
+// generic code (a real loop, full logf) instead of the straight-line negative path; arguments and result by value so
+// that nothing of the hot path is forced into local memory.
+struct QuadOut {
+    float4 g;
+    float acc;
+};
+template <bool GRAD>
+__device__ __noinline__ QuadOut special_quad(float4 v, int code_r, int pc_r, int c0, float s_cls) {
+    QuadOut o;
+    o.acc = 0.0f;
+    o.g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (code_r == G3D_ASSIGN_IGNORE) return o;
+    float gv[4];
+    const float pv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        o.acc += focal_term(pv[e], c0 + e == pc_r);
+        gv[e] = GRAD ? s_cls * focal_term_grad(pv[e], c0 + e == pc_r) : 0.0f;
+    }
+    o.g = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    return o;
+}
+
+// The data one lane holds of a 32-row chunk of the C == 8 path: lane l owns float4 l and l + 32 of the chunk's 64
+// (32 rows x 2 float4), i.e. classes (l & 1) * 4 .. + 3 of rows l >> 1 and 16 + (l >> 1) - fully coalesced in both
+// directions - plus the assignment code of row l.
+struct Chunk8 {
+    float4 v0, v1;
+    int code;
+};
+
+// all 32 rows of the chunk exist (the caller routes an image's ragged last chunk to stream_chunk_any)
+__device__ __forceinline__ Chunk8 load_chunk8(const StreamArgs& p, int64_t row0, int lane) {
+    Chunk8 c;
     const float4* cp = reinterpret_cast<const float4*>(p.cls + row0 * 8);
-    float4* dp = reinterpret_cast<float4*>(p.dcls + row0 * 8);
-    const unsigned special = __ballot_sync(0xffffffffu, code != G3D_ASSIGN_NEGATIVE);   // missing rows count as special
-    float acc = 0.0f;
-    if (special == 0) {
-        const float4 v0 = ld_stream(cp + lane), v1 = ld_stream(cp + 32 + lane);
-        const float pv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        float g[8];
-        acc = focal_neg<8, GRAD>(pv, s_cls, g);
-        if (GRAD) {
-            st_stream(dp + lane, make_float4(g[0], g[1], g[2], g[3]));
-            st_stream(dp + 32 + lane, make_float4(g[4], g[5], g[6], g[7]));
-        }
-    } else {
+    c.code = __ldg(p.assign + row0 + lane);
+    c.v0 = ld_stream(cp + lane);
+    c.v1 = ld_stream(cp + 32 + lane);
+    return c;
+}
+
+// Focal terms (+ gradient, + zero-fill of the dreg rows) of one loaded chunk; returns the lane's share of the sum.
+template <int VARIANT, bool GRAD>
+__device__ __forceinline__ float process_chunk8(const StreamArgs& p, int b, int64_t row0, int lane, float s_cls,
+                                                const Chunk8& c) {
+    // every element as if its anchor were negative (the overwhelmingly common case) ...
+    const float pa[4] = {c.v0.x, c.v0.y, c.v0.z, c.v0.w}, pb[4] = {c.v1.x, c.v1.y, c.v1.z, c.v1.w};
+    float ga[4], gb[4];
+    float acc0 = focal_neg<4, GRAD>(pa, s_cls, ga);
+    float acc1 = focal_neg<4, GRAD>(pb, s_cls, gb);
+    float4 g0 = make_float4(ga[0], ga[1], ga[2], ga[3]), g1 = make_float4(gb[0], gb[1], gb[2], gb[3]);
+    // ... then redo the float4s that belong to positive / ignored anchors
+    if (__any_sync(0xffffffffu, c.code != G3D_ASSIGN_NEGATIVE)) {
         const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
         int pos_cls = -1;
-        if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = lane + 32 * h, r = j >> 1, c0 = (j & 1) * 4;
-            const int code_r = __shfl_sync(0xffffffffu, code, r);
-            const int pc_r = __shfl_sync(0xffffffffu, pos_cls, r);
-            if (r < nrows) {
-                const float4 v = ld_stream(cp + j);
-                const float pv[4] = {v.x, v.y, v.z, v.w};
-                float g[4];
-                if (code_r == G3D_ASSIGN_NEGATIVE) {
-                    acc += focal_neg<4, GRAD>(pv, s_cls, g);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        g[e] = 0.0f;
-                        if (code_r != G3D_ASSIGN_IGNORE) {
-                            acc += focal_term(pv[e], c0 + e == pc_r);
-                            if (GRAD) g[e] = s_cls * focal_term_grad(pv[e], c0 + e == pc_r);
-                        }
-                    }
-                }
-                if (GRAD) st_stream(dp + j, make_float4(g[0], g[1], g[2], g[3]));
-            }
+        if (c.code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + c.code) * p.W + cls_col];
+        const int r0 = lane >> 1, r1 = 16 + (lane >> 1), c0 = (lane & 1) * 4;
+        const int code0 = __shfl_sync(0xffffffffu, c.code, r0), pc0 = __shfl_sync(0xffffffffu, pos_cls, r0);
+        const int code1 = __shfl_sync(0xffffffffu, c.code, r1), pc1 = __shfl_sync(0xffffffffu, pos_cls, r1);
+        if (code0 != G3D_ASSIGN_NEGATIVE) {
+            const QuadOut o = special_quad<GRAD>(c.v0, code0, pc0, c0, s_cls);
+            acc0 = o.acc; g0 = o.g;
+        }
+        if (code1 != G3D_ASSIGN_NEGATIVE) {
+            const QuadOut o = special_quad<GRAD>(c.v1, code1, pc1, c0, s_cls);
+            acc1 = o.acc; g1 = o.g;
         }
     }
     if (GRAD) {
-        if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + row0 * 12, nrows, lane);
-        else                           zero_rows<4>(p.dreg + row0 * 4, nrows, lane);
+        float4* dp = reinterpret_cast<float4*>(p.dcls + row0 * 8);
+        st_stream(dp + lane, g0);
+        st_stream(dp + 32 + lane, g1);
+        if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + row0 * 12, 32, lane);
+        else                           zero_rows<4>(p.dreg + row0 * 4, 32, lane);
     }
-    return acc;
+    return acc0 + acc1;
 }
 
 // generic class count: one thread per row, scalar accesses
@@ -709,6 +731,7 @@ __device__ __forceinline__ float stream_chunk_any(const StreamArgs& p, int b, in
         const float* cp = p.cls + (row0 + lane) * C;
         float* dp = p.dcls + (row0 + lane) * C;
         const bool ign = (code == G3D_ASSIGN_IGNORE);
+#pragma unroll 1
         for (int c = 0; c < C; ++c) {
             const float pr = __ldg(cp + c);
             if (!ign) acc += focal_term(pr, c == pos_cls);
@@ -738,11 +761,25 @@ __global__ void __launch_bounds__(kTile, 4) focal_stream_kernel(const StreamArgs
     const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
     const int wa0 = blockIdx.x * kRowsPerCta + warp * (32 * kChunksPerWarp);   // first anchor of this warp
     float cls_acc = 0.0f;
-#pragma unroll 2
-    for (int c = 0; c < kChunksPerWarp; ++c) {
-        if (CS == 8) cls_acc += stream_chunk8<VARIANT, GRAD>(p, b, wa0 + 32 * c, lane, s_cls);
-        else         cls_acc += stream_chunk_any<VARIANT, GRAD>(p, b, wa0 + 32 * c, lane, s_cls);
+    int c = 0;
+    if (CS == 8) {
+        // full 32-row chunks: software pipeline, the loads of chunk c + 1 are in flight while chunk c is evaluated
+        const int nfull = max(0, min(kChunksPerWarp, (p.A - wa0) >> 5));
+        if (nfull > 0) {
+            int64_t row0 = (int64_t)b * p.A + wa0;
+            Chunk8 cur = load_chunk8(p, row0, lane);
+#pragma unroll 1
+            for (; c < nfull; ++c, row0 += 32) {
+                Chunk8 nxt = cur;
+                if (c + 1 < nfull) nxt = load_chunk8(p, row0 + 32, lane);
+                cls_acc += process_chunk8<VARIANT, GRAD>(p, b, row0, lane, s_cls, cur);
+                cur = nxt;
+            }
+        }
     }
+    // generic class count, and the ragged last chunk of an image: one thread per row
+#pragma unroll 1
+    for (; c < kChunksPerWarp; ++c) cls_acc += stream_chunk_any<VARIANT, GRAD>(p, b, wa0 + 32 * c, lane, s_cls);
     // ---- partial sums: FP32 inside the warp (<= 1024 terms), FP64 from here on.  The last warp of the CTA to get here
     // (shared-memory ticket, no block barrier: finished warps retire immediately) combines the 8 warp partials in warp
     // order; the last CTA of the image (global ticket) reduces that image.
