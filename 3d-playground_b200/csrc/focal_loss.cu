@@ -39,6 +39,7 @@ int gt_prepare_launch(const float* ann, int64_t B, int64_t Gmax, int64_t W, int 
 namespace g3d {
 
 constexpr int kImgPerCta = 4;  // images processed per CTA of assign_codes_kernel (anchors / statistics loaded once)
+constexpr int kStageGroup = 4; // images staged behind one pair of barriers
 
 // clamp bounds of losses.py:56: torch.clamp(classification, 1e-4, 1.0 - 1e-4) - python doubles cast to f32
 #define G3D_PMIN ((float)1e-4)
@@ -283,9 +284,10 @@ struct AssignCodesArgs {
 
 struct StageSmem {
     float4 box[kImgPerCta][kTile];
-    float area[kImgPerCta][kTile];
     int idx[kImgPerCta][kTile];
     float red[8][kWarps];
+    float tile[8];
+    int tile_wf;
     int wcount[kImgPerCta][kWarps];
     int total[kImgPerCta];
 };
@@ -346,48 +348,55 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
             sm.wcount[0][warp] = wf ? 1 : 0;
         }
         __syncthreads();
-        float t[8];
-        bool twf = true;
+        if (warp == 0) {     // tile statistics: lane k < 8 reduces statistic k over the warps
+            if (lane < 8) {
+                float t = sm.red[lane][0];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = sm.red[k][0];
+                for (int w2 = 1; w2 < kWarps; ++w2) t = fmaxf(t, sm.red[lane][w2]);
+                sm.tile[lane] = t;
+            }
+            if (lane == 8) {
+                int twf = 1;
 #pragma unroll
-        for (int w2 = 1; w2 < kWarps; ++w2) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = fmaxf(t[k], sm.red[k][w2]);
+                for (int w2 = 0; w2 < kWarps; ++w2) twf &= sm.wcount[0][w2];
+                sm.tile_wf = twf;
+            }
         }
-#pragma unroll
-        for (int w2 = 0; w2 < kWarps; ++w2) twf &= (sm.wcount[0][w2] != 0);
-        ts.bb = make_float4(-t[0], -t[1], t[2], t[3]);
-        ts.wmax = t[4]; ts.hmax = t[5]; ts.amin = -t[6]; ts.amax = t[7];
-        ts.wellformed = twf;
+        __syncthreads();
+        ts.bb = make_float4(-sm.tile[0], -sm.tile[1], sm.tile[2], sm.tile[3]);
+        ts.wmax = sm.tile[4]; ts.hmax = sm.tile[5]; ts.amin = -sm.tile[6]; ts.amax = sm.tile[7];
+        ts.wellformed = sm.tile_wf != 0;
         __syncthreads();   // sm.wcount[0] is reused below
     }
 
     // ---- stage the GT boxes of the group's images: cull against the tile with an ordered compaction (ascending GT
     // index), all images behind the same two barriers.  An image with more than kTile GT rows keeps its first kTile
     // candidates here and is finished by the (rare) overflow loop further down.
-    {
+#pragma unroll 1
+    for (int i0 = 0; i0 < nimg; i0 += kStageGroup) {
         const int g = tid;
-        float4 gb[kImgPerCta];
-        unsigned bal[kImgPerCta];
+        float4 gb[kStageGroup];
+        unsigned bal[kStageGroup];
 #pragma unroll
-        for (int i = 0; i < kImgPerCta; ++i) {
+        for (int j = 0; j < kStageGroup; ++j) {
+            const int i = i0 + j;
             bool hit = false;
-            gb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             const int Gi = (i < nimg) ? __ldg(p.gt_count + b0 + i) : 0;
             if (g < Gi) {
-                gb[i] = __ldg(p.gt_box + (int64_t)(b0 + i) * p.Gmax + g);
-                hit = can_touch(gb[i], ts);
+                gb[j] = __ldg(p.gt_box + (int64_t)(b0 + i) * p.Gmax + g);
+                hit = can_touch(gb[j], ts);
             }
-            bal[i] = __ballot_sync(0xffffffffu, hit);
+            bal[j] = __ballot_sync(0xffffffffu, hit);
         }
         if (lane == 0) {
 #pragma unroll
-            for (int i = 0; i < kImgPerCta; ++i) sm.wcount[i][warp] = __popc(bal[i]);
+            for (int j = 0; j < kStageGroup; ++j) sm.wcount[i0 + j][warp] = __popc(bal[j]);
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < kImgPerCta; ++i) {
+        for (int j = 0; j < kStageGroup; ++j) {
+            const int i = i0 + j;
             int off = 0, tot = 0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
@@ -396,15 +405,14 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
                 tot += c;
             }
             if (tid == 0) sm.total[i] = tot;
-            if ((bal[i] >> lane) & 1u) {
-                const int pos = off + __popc(bal[i] & ((1u << lane) - 1u));
-                sm.box[i][pos] = gb[i];
-                sm.area[i][pos] = box_area_rn(gb[i].x, gb[i].y, gb[i].z, gb[i].w);
+            if ((bal[j] >> lane) & 1u) {
+                const int pos = off + __popc(bal[j] & ((1u << lane) - 1u));
+                sm.box[i][pos] = gb[j];
                 sm.idx[i][pos] = g;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- per image: IoU max / first argmax over the staged survivors that can still matter.  No barriers.
 #pragma unroll 1
@@ -428,7 +436,7 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
                 // a disjoint pair has IoU == +0.0 exactly and can never beat `best` under the strict '>' rule
                 if (iw > 0.0f && ih > 0.0f) {
                     const float inter = __fmul_rn(iw, ih);
-                    const float ua0 = __fsub_rn(__fadd_rn(area_a, sm.area[i][k]), inter);
+                    const float ua0 = __fsub_rn(__fadd_rn(area_a, box_area_rn(gk.x, gk.y, gk.z, gk.w)), inter);
                     // inter <= ua0 / 2.6  =>  IoU <= 0.3847 < 0.4: cannot change the code of this anchor, skip the
                     // division (the clamp of the union only matters below 1e-8, where this test passes)
                     if (__fmul_rn(inter, 2.6f) > ua0) {
