@@ -316,6 +316,17 @@ __device__ __forceinline__ bool can_touch(const float4& g, const GroupStats& s) 
     return true;
 }
 
+// warp maximum through the integer redux unit: IEEE floats order like sign-magnitude integers, so flipping the low 31
+// bits of negative values gives two's-complement keys with the same order (NaN keys sort beyond +-inf: a NaN anchor
+// only disables culling, it never matches anything)
+__device__ __forceinline__ float warp_max_redux(float x) {
+    int k = __float_as_int(x);
+    k ^= (k >> 31) & 0x7fffffff;
+    k = __reduce_max_sync(0xffffffffu, k);
+    k ^= (k >> 31) & 0x7fffffff;
+    return __int_as_float(k);
+}
+
 __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCodesArgs p) {
     __shared__ StageSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -337,7 +348,7 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
         v[4] = valid ? w : -INFINITY;     v[5] = valid ? h : -INFINITY;
         v[6] = valid ? -area_a : -INFINITY; v[7] = valid ? area_a : -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = warp_max(v[k]);
+        for (int k = 0; k < 8; ++k) v[k] = warp_max_redux(v[k]);
         const bool wf = __all_sync(0xffffffffu, !valid || (w > 0.0f && h > 0.0f));
         ws.bb = make_float4(-v[0], -v[1], v[2], v[3]);
         ws.wmax = v[4]; ws.hmax = v[5]; ws.amin = -v[6]; ws.amax = v[7];
@@ -347,6 +358,7 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
             for (int k = 0; k < 8; ++k) sm.red[k][warp] = v[k];
             sm.wcount[0][warp] = wf ? 1 : 0;
         }
+        if (tid < kImgPerCta) sm.total[tid] = 0;
         __syncthreads();
         if (warp == 0) {     // tile statistics: lane k < 8 reduces statistic k over the warps
             if (lane < 8) {
@@ -369,9 +381,8 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
         __syncthreads();   // sm.wcount[0] is reused below
     }
 
-    // ---- stage the GT boxes of the group's images: cull against the tile with an ordered compaction (ascending GT
-    // index), all images behind the same two barriers.  An image with more than kTile GT rows keeps its first kTile
-    // candidates here and is finished by the (rare) overflow loop further down.
+    // ---- stage the GT boxes of the group's images, culled against the tile.  An image with more than kTile GT rows
+    // keeps its first kTile candidates here and is finished by the (rare) overflow loop further down.
 #pragma unroll 1
     for (int i0 = 0; i0 < nimg; i0 += kStageGroup) {
         const int g = tid;
@@ -389,26 +400,22 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
             }
             bal[j] = __ballot_sync(0xffffffffu, hit);
         }
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < kStageGroup; ++j) sm.wcount[i0 + j][warp] = __popc(bal[j]);
-        }
-        __syncthreads();
+        // unordered compaction (one shared-memory atomic per warp and image): the candidate loop below breaks ties by
+        // GT index explicitly, so the order of the survivors does not matter
+        int base[kStageGroup];
 #pragma unroll
         for (int j = 0; j < kStageGroup; ++j) {
-            const int i = i0 + j;
-            int off = 0, tot = 0;
+            base[j] = 0;
+            if (lane == 0 && bal[j]) base[j] = atomicAdd(&sm.total[i0 + j], __popc(bal[j]));
+        }
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const int c = sm.wcount[i][w];
-                off += (w < warp) ? c : 0;
-                tot += c;
-            }
-            if (tid == 0) sm.total[i] = tot;
+        for (int j = 0; j < kStageGroup; ++j) {
+            if (bal[j] == 0) continue;
+            const int bs = __shfl_sync(0xffffffffu, base[j], 0);
             if ((bal[j] >> lane) & 1u) {
-                const int pos = off + __popc(bal[j] & ((1u << lane) - 1u));
-                sm.box[i][pos] = gb[j];
-                sm.idx[i][pos] = g;
+                const int pos = bs + __popc(bal[j] & ((1u << lane) - 1u));
+                sm.box[i0 + j][pos] = gb[j];
+                sm.idx[i0 + j][pos] = g;
             }
         }
     }
@@ -425,7 +432,10 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
         for (int k0 = 0; k0 < total; k0 += 32) {
             // warp-level refinement: which of these (up to 32) tile survivors matter for this warp's anchors?
             bool near = false;
-            if (k0 + lane < total) near = can_touch(sm.box[i][k0 + lane], ws);
+            if (k0 + lane < total) {   // the size test was already applied with the tile's statistics
+                const float4 t = sm.box[i][k0 + lane];
+                near = !(t.z <= ws.bb.x || t.x >= ws.bb.z || t.w <= ws.bb.y || t.y >= ws.bb.w);
+            }
             unsigned m = __ballot_sync(0xffffffffu, near);
             while (m) {
                 const int k = k0 + __ffs(m) - 1;
@@ -441,7 +451,8 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
                     // division (the clamp of the union only matters below 1e-8, where this test passes)
                     if (__fmul_rn(inter, 2.6f) > ua0) {
                         const float v = __fdiv_rn(inter, fmaxf(ua0, 1e-8f));
-                        if (v > best) { best = v; besti = sm.idx[i][k]; }
+                        const int gi = sm.idx[i][k];
+                        if (v > best || (v == best && gi < besti)) { best = v; besti = gi; }   // first maximal index
                     }
                 }
             }
@@ -458,8 +469,8 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
                 if (v > best) { best = v; besti = g; }
             }
         }
-        // `best` is exact whenever it is >= 0.4 (every pair that can reach 0.3847 was evaluated exactly, in ascending
-        // GT order with the strict '>' rule = torch.max's first-maximal-index); below that only "< 0.4" is used.
+        // `best` is exact whenever it is >= 0.4 (every pair that can reach 0.3847 was evaluated exactly; ties go to the
+        // lower GT index = torch.max's first-maximal-index); below that only "< 0.4" is used.
         int code = G3D_ASSIGN_NEGATIVE;
         if (Gi > 0) code = assign_code(best, besti, p.gt_row + (int64_t)b * p.Gmax);
         if (valid) p.assign[(int64_t)b * p.A + a] = code;

@@ -35,6 +35,20 @@ METRIC = "IoU-assign+loss G anchor-GT pairs/s"
 UNIT = "G pairs/s"
 
 
+def _traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the newest committed ncu capture"""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for rnd in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        f = os.path.join(pdir, rnd, "traffic.json")
+        if os.path.exists(f):
+            with open(f) as fh:
+                for name, rec in json.load(fh).items():
+                    if name.startswith(kernel):
+                        best = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    return best
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -395,7 +409,7 @@ def run_ours(args):
             # gt_prepare, assign_codes, positives (fwd), focal_stream, focal_cls_grad, positives (bwd) per step
             "gpu_launches": 6 * args.steps,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": _traffic(dom), "peak_source": peak_src,
                          "ms": {"forward": ms_fwd, "backward": ms_bwd, "focal_stream_kernel": ms_stream,
                                 "assign_codes_kernel": ms_assign, "positives_kernel": ms_pos},
                          "forward": {"bytes": fwd_bytes, "GBps": fwd_bytes / (ms_fwd * 1e-3) / 1e9,
