@@ -39,10 +39,11 @@ SIGNATURES = {
     "g3d_focal_loss_fwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
                                   _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _int, _c_ptr]),
     "g3d_focal_loss_fwd_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
-                                      _f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _int,
-                                      _c_ptr]),
+                                      _f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr,
+                                      _int, _c_ptr]),
     "g3d_focal_loss_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
-                                  _c_ptr, _int, _f32, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
+                                  _c_ptr, _c_ptr, _int, _f32, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
+    "g3d_combine_shard_stats": (_int, [_c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_decode3d": (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_decode2d": (_int, [_c_ptr, _i64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _f32, _f32, _c_ptr, _int, _c_ptr]),
     "g3d_clip_boxes": (_int, [_c_ptr, _i64, _i64, _f32, _f32, _int, _c_ptr]),

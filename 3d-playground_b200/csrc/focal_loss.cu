@@ -503,6 +503,7 @@ struct PosArgs {
     long long* acc;            // [B][4]: reg_hi, reg_lo, vp_hi, vp_lo (forward)
     int32_t* nonfinite;        // [B]: set if a term was NaN / Inf / out of range (forward)
     const float* grad_out;     // [3] device (backward)
+    const float* grad_scale;   // [3] device or null (backward): multiplies grad_out (dist.py: local -> global means)
     const float* losses;       // [4] (backward: losses[3] = number of images with >= 1 GT row)
     float* dreg;               // (backward)
     int B, A, R, Gmax, W;
@@ -530,8 +531,12 @@ __global__ void __launch_bounds__(128) positives_kernel(const PosArgs p) {
     float s_reg = 0.0f, s_vp = 0.0f;
     if (BWD) {
         const float per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0f : 4.0f;
-        s_reg = __ldg(p.grad_out + 1) / ((float)p.B * per_pos * npos);
-        if (VARIANT == G3D_VARIANT_3D) s_vp = __ldg(p.grad_out + 2) / (__ldg(p.losses + 3) * npos * 3.0f);
+        const float go1 = __ldg(p.grad_out + 1) * (p.grad_scale ? __ldg(p.grad_scale + 1) : 1.0f);
+        s_reg = go1 / ((float)p.B * per_pos * npos);
+        if (VARIANT == G3D_VARIANT_3D) {
+            const float go2 = __ldg(p.grad_out + 2) * (p.grad_scale ? __ldg(p.grad_scale + 2) : 1.0f);
+            s_vp = go2 / (__ldg(p.losses + 3) * npos * 3.0f);
+        }
     }
     const int n_up = (n + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += gridDim.x * blockDim.x) {
@@ -585,6 +590,7 @@ struct StreamArgs {
     int32_t* counters;         // [B] image tickets + [1] batch ticket, zero on entry
     float* losses;             // [4] : cls, reg, vp, number of non-empty images
     float* per_image;          // [B][4]
+    double* shard_stats;       // [5] or null: sum cls_j, sum reg_j, sum vp_j (images with GT), B, #images with GT
     float* dcls;               // [B][A][C]  (GRAD only)
     float* dreg;               // [B][A][R]  (GRAD only: zero-filled here)
     float g0;                  // upstream gradient of the classification loss that dcls is formed for
@@ -637,6 +643,10 @@ __device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
             p.losses[1] = (float)(sr / p.B);
             p.losses[2] = (VARIANT == G3D_VARIANT_3D) ? (float)(sv / ne) : 0.0f;  // 0/0 -> NaN when all empty
             p.losses[3] = (float)ne;
+            if (p.shard_stats) {
+                p.shard_stats[0] = sc; p.shard_stats[1] = sr; p.shard_stats[2] = (VARIANT == G3D_VARIANT_3D) ? sv : 0.0;
+                p.shard_stats[3] = (double)p.B; p.shard_stats[4] = ne;
+            }
         }
     }
 }
@@ -833,6 +843,7 @@ struct ClsGradArgs {
     const float* cls;
     const float* ann;
     const float* grad_out;   // [3] device
+    const float* grad_scale; // [3] device or null
     const int32_t* npos;     // [B]
     const int32_t* assign;
     float* dcls;
@@ -846,7 +857,7 @@ struct ClsGradArgs {
 // (dcls already right) exits at once: one wave of CTAs.
 template <int VARIANT, int CS>
 __global__ void __launch_bounds__(256, 4) focal_cls_grad_kernel(const ClsGradArgs p) {
-    const float go0 = __ldg(p.grad_out + 0);
+    const float go0 = __ldg(p.grad_out + 0) * (p.grad_scale ? __ldg(p.grad_scale + 0) : 1.0f);
     if (p.have_dcls && go0 == p.e0) return;
     const int lane = threadIdx.x & 31;
     const int C = (CS > 0) ? CS : p.C;
@@ -927,9 +938,36 @@ static inline int32_t* ws_npos(const FocalWorkspace& w, int64_t B) { return w.co
 static inline int32_t* ws_nonfinite(const FocalWorkspace& w, int64_t B) { return w.counters + 2 * B + 1; }
 static inline long long* ws_acc(const FocalWorkspace& w, int64_t B) { return (long long*)(w.counters + align_up(3 * B + 1, 2)); }
 
+// multi-GPU: the [world][5] shard statistics (all-gathered) -> global batch means and this rank's gradient scales.
+// Fixed (rank) summation order: the same bits on every rank and from run to run.
+__global__ void combine_shard_stats_kernel(const double* __restrict__ gathered, int world, int rank,
+                                           float* __restrict__ losses, float* __restrict__ scale) {
+    if (threadIdx.x != 0) return;
+    double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int r = 0; r < world; ++r)
+        for (int k = 0; k < 5; ++k) t[k] += gathered[r * 5 + k];
+    losses[0] = (float)(t[0] / t[3]);
+    losses[1] = (float)(t[1] / t[3]);
+    losses[2] = (float)(t[2] / t[4]);                       // 0/0 -> NaN when no image of the global batch has GT
+    const double bl = gathered[rank * 5 + 3], nl = gathered[rank * 5 + 4];
+    // d(global mean) / d(local mean): B_l / B_g for cls and reg, NE_l / NE_g for vp (0 when the shard has no GT at all)
+    scale[0] = scale[1] = (float)(bl / t[3]);
+    scale[2] = nl > 0.0 ? (float)(nl / t[4]) : 0.0f;
+}
+
 }  // namespace g3d
 
 using namespace g3d;
+
+extern "C" int g3d_combine_shard_stats(const double* gathered, int64_t world, int64_t rank, float* losses, float* scale,
+                                       int device, void* stream) {
+    G3D_REQUIRE(gathered && losses && scale, "null pointer");
+    G3D_REQUIRE(world >= 1 && rank >= 0 && rank < world && world < (1 << 20), "bad world / rank");
+    G3D_GUARD(device);
+    combine_shard_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered, (int)world, (int)rank, losses, scale);
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}
 
 extern "C" int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax) {
     if (B < 0 || A < 0 || Gmax < 0) return G3D_ERR_INVALID;
@@ -961,8 +999,9 @@ static dim3 positives_grid(int64_t B) { return dim3(64, (unsigned)B); }
 extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                       int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                                       float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
-                                      int32_t* gt_count_out, float* dcls, float* dreg, void* workspace,
-                                      int64_t workspace_bytes, void* const* trace_events, int device, void* stream) {
+                                      int32_t* gt_count_out, double* shard_stats, float* dcls, float* dreg,
+                                      void* workspace, int64_t workspace_bytes, void* const* trace_events, int device,
+                                      void* stream) {
     int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
     if (rc != G3D_OK) return rc;
     G3D_REQUIRE(cls && reg && anchors && losses && per_image && assign && workspace, "null pointer");
@@ -991,7 +1030,8 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
 
     PosArgs pp;
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.ann = ann; pp.assign = assign; pp.pos_list = w.pos_list;
-    pp.npos = npos; pp.acc = ws_acc(w, B); pp.nonfinite = ws_nonfinite(w, B); pp.grad_out = nullptr; pp.losses = nullptr;
+    pp.npos = npos; pp.acc = ws_acc(w, B); pp.nonfinite = ws_nonfinite(w, B); pp.grad_out = nullptr; pp.grad_scale = nullptr;
+    pp.losses = nullptr;
     pp.dreg = nullptr; pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.W = (int)W;
     if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, false><<<positives_grid(B), 128, 0, st>>>(pp);
     else                           positives_kernel<G3D_VARIANT_2D, false><<<positives_grid(B), 128, 0, st>>>(pp);
@@ -1002,6 +1042,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     p.cls = cls; p.ann = ann; p.assign = assign; p.npos = npos; p.gt_count = w.gt_count;
     p.acc = ws_acc(w, B); p.nonfinite = ws_nonfinite(w, B); p.gt_count_out = gt_count_out;
     p.partials = w.partials; p.counters = w.counters; p.losses = losses; p.per_image = per_image;
+    p.shard_stats = shard_stats;
     p.dcls = dcls; p.dreg = dreg; p.g0 = grad_cls_expected;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
     p.T = (int)ceil_div(A, kRowsPerCta);
@@ -1024,12 +1065,14 @@ extern "C" int g3d_focal_loss_fwd(const float* cls, const float* reg, const floa
                                   float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
                                   void* workspace, int64_t workspace_bytes, int device, void* stream) {
     return g3d_focal_loss_fwd_bwd(cls, reg, anchors, ann, B, A, C, R, Gmax, W, variant, 0.0f, losses, per_image,
-                                  assign, gt_count_out, nullptr, nullptr, workspace, workspace_bytes, nullptr, device, stream);
+                                  assign, gt_count_out, nullptr, nullptr, nullptr, workspace, workspace_bytes, nullptr, device,
+                                  stream);
 }
 
 extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                   int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                                  const float* grad_out, int have_dcls, float grad_cls_expected, const float* losses,
+                                  const float* grad_out, const float* grad_scale, int have_dcls, float grad_cls_expected,
+                                  const float* losses,
                                   const int32_t* assign, const void* workspace, int64_t workspace_bytes, float* dcls,
                                   float* dreg, int device, void* stream) {
     int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
@@ -1044,7 +1087,7 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
     ClsGradArgs p;
-    p.cls = cls; p.ann = ann; p.grad_out = grad_out; p.npos = ws_npos(w, B); p.assign = assign;
+    p.cls = cls; p.ann = ann; p.grad_out = grad_out; p.grad_scale = grad_scale; p.npos = ws_npos(w, B); p.assign = assign;
     p.dcls = dcls; p.dreg = dreg; p.e0 = grad_cls_expected; p.have_dcls = have_dcls ? 1 : 0;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
     p.T = (int)ceil_div(A, 256);
@@ -1062,7 +1105,8 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     G3D_LAUNCH_CHECK();
     PosArgs pp;
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.ann = ann; pp.assign = assign; pp.pos_list = w.pos_list;
-    pp.npos = ws_npos(w, B); pp.acc = nullptr; pp.nonfinite = nullptr; pp.grad_out = grad_out; pp.losses = losses;
+    pp.npos = ws_npos(w, B); pp.acc = nullptr; pp.nonfinite = nullptr; pp.grad_out = grad_out; pp.grad_scale = grad_scale;
+    pp.losses = losses;
     pp.dreg = dreg; pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.W = (int)W;
     if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, true><<<positives_grid(B), 128, 0, st>>>(pp);
     else                           positives_kernel<G3D_VARIANT_2D, true><<<positives_grid(B), 128, 0, st>>>(pp);

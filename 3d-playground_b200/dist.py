@@ -46,29 +46,38 @@ def combine_stats(stats, group=None):
 
 
 class _ShardedFocalLossFn(torch.autograd.Function):
+    """forward: local fused loss (+ gradients for the expected upstream value) -> all-gather of the 5 shard statistics
+    the kernel wrote -> one tiny kernel forms the global means and this rank's gradient scales.  Two extra launches and
+    one collective per step; the backward adds none (the scale is applied inside the gradient kernels)."""
+
     @staticmethod
     def forward(ctx, classifications, regressions, anchors, annotations, group, trace_events=None):
         from . import ops
+        on = dist.is_available() and dist.is_initialized()
+        world = dist.get_world_size(group) if on else 1
+        rank = dist.get_rank(group) if on else 0
         # expected upstream gradient of the LOCAL classification mean: B_local / B_global = 1 / world for equal shards
         # (a hint: the backward kernel checks it against the real value on the device and recomputes if it is off)
-        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         needs_grad = classifications.requires_grad or regressions.requires_grad
         fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations,
                                      grad_cls_expected=(1.0 / world) if needs_grad else None,
-                                     trace_events=trace_events if needs_grad else None)
-        stats = local_stats(fwd["per_image"], fwd["gt_count"])
-        losses, total = combine_stats(stats, group)
-        ctx.fwd = fwd
-        # d(global mean)/d(local mean): B_l / B_g for cls and reg, NE_l / NE_g for vp (0 when the shard has no GT at all)
-        ne_ratio = torch.where(stats[4] > 0, stats[4] / total[4], torch.zeros_like(stats[4]))
-        ctx.scale = torch.stack((stats[3] / total[3], stats[3] / total[3], ne_ratio)).to(torch.float32)
+                                     trace_events=trace_events if needs_grad else None, want_shard_stats=True)
+        stats = fwd["shard_stats"]
+        if world > 1:
+            gathered = torch.empty((world, 5), dtype=torch.float64, device=stats.device)
+            dist.all_gather_into_tensor(gathered, stats, group=group)
+        else:
+            gathered = stats.reshape(1, 5)
+        losses, scale = ops.combine_shard_stats(gathered, rank)
+        ctx.fwd, ctx.scale = fwd, scale
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
         return losses
 
     @staticmethod
     def backward(ctx, g):
         from . import ops
-        dcls, dreg = ops.focal_loss_backward(ctx.fwd, (g.to(torch.float32) * ctx.scale).contiguous())
+        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g.to(torch.float32), grad_scale=ctx.scale)
+        ctx.fwd = None
         return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None
 
 

@@ -125,7 +125,7 @@ def assign(anchors, annotations, variant=None):
 
 # ------------------------------------------------------------------------------------------------ a2-a6: fused loss
 def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True, grad_cls_expected=None,
-                       trace_events=None):
+                       trace_events=None, want_shard_stats=False):
     """FocalLoss forward (assignment launch + streaming loss launch).  Returns dict(losses f32[4], per_image f32[B,4],
     assign i32[B,A], gt_count i32[B], plus the prepared contiguous inputs for the backward).
 
@@ -158,14 +158,17 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
     out = dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
                ann=ann, variant=variant, workspace=ws)   # the workspace holds the positive lists the backward reads
-    if grad_cls_expected is None:
+    stats = torch.empty((5,), dtype=torch.float64, device=dev) if want_shard_stats else None
+    out["shard_stats"] = stats
+    if grad_cls_expected is None and not want_shard_stats:
         check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses),
                                    _p(per_image), _p(code), _p(gt_count), _p(ws), ws.numel(), _idx(dev), _stream(dev)),
               "g3d_focal_loss_fwd")
     else:
-        ge = ctypes.c_float(float(grad_cls_expected))
-        dcls = torch.empty_like(cls)
-        dreg = torch.empty_like(reg)
+        grads = grad_cls_expected is not None
+        ge = ctypes.c_float(float(grad_cls_expected) if grads else 0.0)
+        dcls = torch.empty_like(cls) if grads else None
+        dreg = torch.empty_like(reg) if grads else None
         ev = None
         if trace_events is not None:
             for e in trace_events:          # torch creates the CUDA event lazily, on its first record
@@ -173,13 +176,26 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
                     e.record(torch.cuda.current_stream(dev))
             ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in trace_events])
         check(L.g3d_focal_loss_fwd_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, ge, _p(losses),
-                                       _p(per_image), _p(code), _p(gt_count), _p(dcls), _p(dreg), _p(ws), ws.numel(),
-                                       ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
-        out.update(dcls=dcls, dreg=dreg, grad_cls_expected=ge.value)
+                                       _p(per_image), _p(code), _p(gt_count), _p(stats), _p(dcls), _p(dreg), _p(ws),
+                                       ws.numel(), ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
+        if grads:
+            out.update(dcls=dcls, dreg=dreg, grad_cls_expected=ge.value)
     return out
 
 
-def focal_loss_backward(fwd, grad_out):
+def combine_shard_stats(gathered, rank):
+    """gathered f64[world,5] (every rank's shard_stats) -> (losses f32[3] global means, scale f32[3] for the backward)."""
+    dev = _need_cuda(gathered)
+    gathered = _prep(gathered, torch.float64)
+    world = gathered.numel() // 5
+    losses = torch.empty((3,), dtype=torch.float32, device=dev)
+    scale = torch.empty((3,), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_combine_shard_stats(_p(gathered), world, int(rank), _p(losses), _p(scale), _idx(dev), _stream(dev)),
+          "g3d_combine_shard_stats")
+    return losses, scale
+
+
+def focal_loss_backward(fwd, grad_out, grad_scale=None):
     """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R]).
 
     If the forward already wrote dcls for `grad_cls_expected`, the kernel compares grad_out[0] with it on the device: when
@@ -193,13 +209,14 @@ def focal_loss_backward(fwd, grad_out):
     g = _prep(grad_out, torch.float32)
     if g.numel() != 3:
         raise ValueError("grad_out must have 3 elements (cls, reg, vp)")
+    gs = _prep(grad_scale, torch.float32) if grad_scale is not None else None
     if fwd.get("dcls") is not None:
         dcls, dreg, have, ge = fwd["dcls"], fwd["dreg"], 1, fwd["grad_cls_expected"]
     else:
         dcls, dreg, have, ge = torch.empty_like(cls), torch.empty_like(reg), 0, 0.0
     ws = fwd["workspace"]
-    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g), have,
-                                        ctypes.c_float(ge), _p(fwd["losses"]), _p(fwd["assign"]), _p(ws), ws.numel(),
+    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g), _p(gs),
+                                        have, ctypes.c_float(ge), _p(fwd["losses"]), _p(fwd["assign"]), _p(ws), ws.numel(),
                                         _p(dcls), _p(dreg), _idx(dev), _stream(dev)), "g3d_focal_loss_bwd")
     return dcls, dreg
 

@@ -334,9 +334,44 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     if world > 1:
         torch.distributed.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    losses = losses.detach().clone()    # drop the autograd graph (its AccumulateGrad nodes would pin the legacy stream)
     ms_total = _max_over_ranks(e0.elapsed_time(e1), world, dev)
-    ms_step = ms_total / args.steps
+    ms_step_eager = ms_total / args.steps
+    # ---- the same K steps as ONE CUDA graph launch per step (forward + backward, all kernels and the small torch ops):
+    # removes the host-side launch gaps between the six short kernels.  Falls back to the eager figure if capture fails.
+    ms_step, mode = ms_step_eager, "eager (one Python call per step)"
+    if not args.no_graph and world == 1:   # NCCL inside a capture: a failure on one rank only would deadlock the others
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_device()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_losses = step_device().detach()
+            for _ in range(args.warmup):
+                graph.replay()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                torch.distributed.barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                graph.replay()
+            g1.record()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                torch.distributed.barrier()
+            ms_graph = _max_over_ranks(g0.elapsed_time(g1), world, dev) / args.steps
+            same = torch.equal(g_losses, losses)
+            if same and ms_graph < ms_step:
+                ms_step, mode = ms_graph, "CUDA graph replay (one launch per step)"
+        except Exception as e:   # noqa: BLE001 - any capture problem: keep the eager number
+            mode = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:300]})"
+    clocks = sampler.stop() if rank == 0 else None
     ms_fwd = _event_ms([(e[0], e[1]) for e in evs]) / args.steps
     ms_bwd = _event_ms([(e[1], e[2]) for e in evs]) / args.steps
     ms_assign = _event_ms([(e[0], e[1]) for e in kev]) / args.steps
@@ -402,7 +437,8 @@ def run_ours(args):
             "config": {"workload": "training-loss path (BASELINE configs[1]): FocalLoss fwd+bwd, 1080p, A=389205, "
                                    "G=200 GT/img, C=8, 12-d regression", "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"images sharded over {world} GPU(s), 5-scalar all-gather only",
-                       "l2": "inputs (1.0 GB/step) exceed the 126 MB L2; no flush needed"},
+                       "l2": "inputs (1.0 GB/step) exceed the 126 MB L2; no flush needed",
+                       "launch_mode": mode, "ms_per_step_eager": ms_step_eager},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": t_e2e * 1e3, "steps": e2e_steps},
@@ -443,6 +479,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3-5 workloads")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step only (no CUDA graph replay)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,6 +94,9 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *                           expects for the classification loss: 1 for `(cls + reg + vp).backward()`), plus the
  *                           zero-fill of dreg[B,A,R].  g3d_focal_loss_bwd(have_dcls = 1) completes the backward.
  *                           dcls == dreg == NULL degrades to g3d_focal_loss_fwd.
+ *                           shard_stats (nullable, double[5]): sum_j cls_j, sum_j reg_j, sum over images with GT of
+ *                           vp_j, B, number of images with GT - what a rank contributes to the global batch means
+ *                           when the images are sharded over several GPUs (see g3d_combine_shard_stats).
  *                           trace_events (nullable): 4 cudaEvent_t handles recorded on `stream` before the assignment
  *                           launch, after it, after the positives launch and after the streaming launch (per-kernel
  *                           timing without a profiler; bench.py's roofline figures come from these).
@@ -106,11 +109,12 @@ int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors,
 int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                            int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                            float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
-                           int32_t* gt_count_out, float* dcls, float* dreg,
+                           int32_t* gt_count_out, double* shard_stats, float* dcls, float* dreg,
                            void* workspace, int64_t workspace_bytes, void* const* trace_events, int device, void* stream);
 
 /* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
- * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory).
+ * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory); grad_scale[3] (nullable, device)
+ * multiplies them element-wise (multi-GPU: local -> global mean, from g3d_combine_shard_stats).
  * losses / assign / workspace = what the forward wrote (the workspace holds the per-image lists of positive anchors:
  * keep it untouched between the two calls).  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is zero on
  * non-positive anchors).
@@ -122,9 +126,18 @@ int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anch
  */
 int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                       const float* grad_out, int have_dcls, float grad_cls_expected, const float* losses,
+                       const float* grad_out, const float* grad_scale, int have_dcls, float grad_cls_expected,
+                       const float* losses,
                        const int32_t* assign, const void* workspace, int64_t workspace_bytes,
                        float* dcls, float* dreg, int device, void* stream);
+
+/* multi-GPU reduction of the loss (replaces nn.DataParallel + .mean(), train_detector_3D_angle.py:316-318,374-378):
+ * gathered[world][5] = the shard_stats of every rank (all-gathered by the host, e.g. NCCL), summed in rank order ->
+ * losses[3] = global (cls, reg, vp) means as the reference forms them on one device, scale[3] = this rank's
+ * d(global mean)/d(local mean) for g3d_focal_loss_bwd's grad_scale.
+ */
+int g3d_combine_shard_stats(const double* gathered, int64_t world, int64_t rank, float* losses, float* scale,
+                            int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a7  3D BBoxTransform.forward     pytorch_retinanet_detector_directional/retinanet/utils.py:102-149

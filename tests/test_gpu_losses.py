@@ -232,3 +232,23 @@ def test_full_size_properties_1080p():
     flip = ops.focal_loss_forward(cls.flip(0).contiguous(), reg.flip(0).contiguous(), anc, ann.flip(0).contiguous())
     assert torch.equal(flip["per_image"].flip(0), fwd["per_image"])
     assert bool(torch.isfinite(fwd["losses"]).all()) and int(npos.min()) > 0
+
+
+def test_sharded_loss_single_rank_equals_plain_loss_and_gradients():
+    """dist.sharded_focal_loss without a process group (world 1): same losses and gradients as the plain module"""
+    _, li = _mods()
+    from geom3d_b200 import dist as gdist
+    g = synth.gen(41)
+    anc = synth.anchors(96, 128).cuda()
+    ann = synth.gt_annotations_3d(3, 7, 96, 128, g, n_pad=1, empty_images=(2,), **synth.TINY).cuda()
+    cls, reg = synth.head_outputs(3, anc.shape[1], 8, 12, g)
+    c0, r0 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    want = li.focal_loss(c0, r0, anc, ann)[0]
+    w = torch.tensor([1.0, 2.0, 0.5]).cuda()
+    (want * w).sum().backward()
+    got = gdist.sharded_focal_loss(c1, r1, anc, ann)
+    (got * w).sum().backward()
+    assert_close_rel(got.cpu(), want.detach().cpu(), 1e-6, "losses")
+    assert_close_rel(c1.grad.cpu(), c0.grad.cpu(), 1e-6, "dcls")
+    assert_close_rel(r1.grad.cpu(), r0.grad.cpu(), 1e-6, "dreg")
