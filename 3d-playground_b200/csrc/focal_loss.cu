@@ -15,8 +15,9 @@
 //        grid (anchor tiles, images), one warp per 32 consecutive (image, anchor) rows.  Streams the classification
 //        rows (fully coalesced 16-byte loads: lane l takes float4 l and l+32 of the warp's 1 KB - the focal term of a
 //        negative anchor does not depend on which row an element belongs to), evaluates the focal terms AND their
-//        gradients from the same -log(1-p), streams the gradient rows out, zero-fills the regression-gradient rows
-//        and lets the (rare) positive anchors add their corner / direction loss terms.
+//        gradients from the same -log(1-p) and streams the gradient rows out.  (The zero-fill of the regression
+//        gradient - 41 % of the bytes this pass would otherwise move - is done by launch 1, which is issue-bound and
+//        leaves HBM idle.)
 //        The per-image normaliser 1/num_pos is already known from launch 1, so forward and backward of the whole
 //        loss are ONE pass over the data: cls is read once, -log once, dcls / dreg are written once.
 //        Partial sums: FP32 inside a warp (<= 256 terms), FP64 across warps / tiles, fixed order; the last CTA of an
@@ -271,6 +272,20 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // =====================================================================================================================
 // launch 1: assignment codes
 // =====================================================================================================================
+// zero-fill `nrows` consecutive rows of dreg (R floats each; 16-byte aligned because R is 4 or 12) with coalesced
+// 16-byte streaming stores
+template <int R>
+__device__ __forceinline__ void zero_rows(float* base, int nrows, int lane) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* b4 = reinterpret_cast<float4*>(base);
+    if (nrows == 32) {
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) st_stream(b4 + lane + 32 * k, z);
+    } else {
+        for (int i = lane; i < nrows * (R / 4); i += 32) st_stream(b4 + i, z);
+    }
+}
+
 struct AssignCodesArgs {
     const float4* anchors;
     const float4* gt_box;
@@ -279,7 +294,8 @@ struct AssignCodesArgs {
     int32_t* assign;     // [B][A]
     int32_t* npos;       // [B], zero on entry
     int32_t* pos_list;   // [B][A]: anchor indices of the positives of each image, in arrival order (first npos[b] valid)
-    int B, A, Gmax;
+    float* dreg;         // [B][A][R] or null: zero-filled here (see the kernel)
+    int B, A, Gmax, R;
 };
 
 struct StageSmem {
@@ -426,6 +442,16 @@ __global__ void __launch_bounds__(kTile, 4) assign_codes_kernel(const AssignCode
     for (int i = 0; i < nimg; ++i) {
         const int b = b0 + i;
         const int Gi = __ldg(p.gt_count + b);
+        // The regression gradient is zero except on the few positive rows.  This kernel is issue-bound and leaves HBM
+        // idle, so the 48 bytes / row of zeros are written from here (3 coalesced 16-byte stores per lane, drained in
+        // the background) instead of costing the HBM-bound streaming kernel 41 % more traffic.
+        if (p.dreg) {
+            const int wa0 = blockIdx.x * kTile + warp * 32, nrows = min(32, p.A - wa0);
+            if (nrows > 0) {
+                if (p.R == 12) zero_rows<12>(p.dreg + ((int64_t)b * p.A + wa0) * 12, nrows, lane);
+                else           zero_rows<4>(p.dreg + ((int64_t)b * p.A + wa0) * 4, nrows, lane);
+            }
+        }
         float best = 0.0f;
         int besti = 0;
         const int total = sm.total[i];
@@ -592,7 +618,7 @@ struct StreamArgs {
     float* per_image;          // [B][4]
     double* shard_stats;       // [5] or null: sum cls_j, sum reg_j, sum vp_j (images with GT), B, #images with GT
     float* dcls;               // [B][A][C]  (GRAD only)
-    float* dreg;               // [B][A][R]  (GRAD only: zero-filled here)
+    float* dreg;               // [B][A][R]  (GRAD only; zero-filled by launch 1)
     float g0;                  // upstream gradient of the classification loss that dcls is formed for
     int B, A, C, R, Gmax, W, T;
 };
@@ -651,20 +677,6 @@ __device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
     }
 }
 
-// zero-fill `nrows` consecutive rows of dreg (R floats each; 16-byte aligned because R is 4 or 12) with coalesced
-// 16-byte streaming stores
-template <int R>
-__device__ __forceinline__ void zero_rows(float* base, int nrows, int lane) {
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4* b4 = reinterpret_cast<float4*>(base);
-    if (nrows == 32) {
-#pragma unroll
-        for (int k = 0; k < R / 4; ++k) st_stream(b4 + lane + 32 * k, z);
-    } else {
-        for (int i = lane; i < nrows * (R / 4); i += 32) st_stream(b4 + i, z);
-    }
-}
-
 // Fix-up of one float4 (4 classes of row r) that belongs to a positive or ignored anchor.  Rare and divergent: compact
 // generic code (a real loop, full logf) instead of the straight-line negative path; arguments and result by value so
 // that nothing of the hot path is forced into local memory.
@@ -707,7 +719,7 @@ __device__ __forceinline__ Chunk8 load_chunk8(const StreamArgs& p, int64_t row0,
     return c;
 }
 
-// Focal terms (+ gradient, + zero-fill of the dreg rows) of one loaded chunk; returns the lane's share of the sum.
+// Focal terms (+ gradient) of one loaded chunk; returns the lane's share of the sum.
 template <int VARIANT, bool GRAD>
 __device__ __forceinline__ float process_chunk8(const StreamArgs& p, int b, int64_t row0, int lane, float s_cls,
                                                 const Chunk8& c) {
@@ -738,8 +750,6 @@ __device__ __forceinline__ float process_chunk8(const StreamArgs& p, int b, int6
         float4* dp = reinterpret_cast<float4*>(p.dcls + row0 * 8);
         st_stream(dp + lane, g0);
         st_stream(dp + 32 + lane, g1);
-        if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + row0 * 12, 32, lane);
-        else                           zero_rows<4>(p.dreg + row0 * 4, 32, lane);
     }
     return acc0 + acc1;
 }
@@ -766,10 +776,6 @@ __device__ __forceinline__ float stream_chunk_any(const StreamArgs& p, int b, in
             if (!ign) acc += focal_term(pr, c == pos_cls);
             if (GRAD) dp[c] = ign ? 0.0f : s_cls * focal_term_grad(pr, c == pos_cls);
         }
-    }
-    if (GRAD) {
-        if (VARIANT == G3D_VARIANT_3D) zero_rows<12>(p.dreg + row0 * 12, nrows, lane);
-        else                           zero_rows<4>(p.dreg + row0 * 4, nrows, lane);
     }
     return acc;
 }
@@ -1023,7 +1029,8 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[0], st));
     AssignCodesArgs q;
     q.anchors = (const float4*)anchors; q.gt_box = w.gt_box; q.gt_row = w.gt_row; q.gt_count = w.gt_count;
-    q.assign = assign; q.npos = npos; q.pos_list = w.pos_list; q.B = (int)B; q.A = (int)A; q.Gmax = (int)Gmax;
+    q.assign = assign; q.npos = npos; q.pos_list = w.pos_list; q.dreg = dreg; q.B = (int)B; q.A = (int)A; q.Gmax = (int)Gmax;
+    q.R = (int)R;
     assign_codes_kernel<<<dim3((unsigned)ceil_div(A, kTile), (unsigned)ceil_div(B, kImgPerCta)), kTile, 0, st>>>(q);
     G3D_LAUNCH_CHECK();
     if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));

@@ -422,11 +422,12 @@ def run_ours(args):
     del cls_h, reg_h, cls_in, reg_in
 
     if rank == 0:
-        # algorithmic bytes.  forward = assign_codes_kernel (anchors + GT in, codes out), the positives
-        # launch (negligible) and the dominant focal_stream_kernel: cls + codes in, dcls + zero-filled dreg out.
-        # backward (dcls already written): the positive rows only.
-        stream_bytes = B * A * (C_CLS * 4 + 4 + C_CLS * 4 + R_REG * 4)
-        fwd_bytes = stream_bytes + B * A * 4 + A * 16 + ann_h.numel() * 4
+        # algorithmic bytes.  forward = assign_codes_kernel (issue-bound; anchors + GT in, codes and the
+        # zero-filled dreg out), the positives launch (negligible) and the HBM-bound focal_stream_kernel: cls + codes in,
+        # dcls out.  backward (dcls already written): the positive rows only.
+        stream_bytes = B * A * (C_CLS * 4 + 4 + C_CLS * 4)          # cls + codes in, dcls out
+        assign_bytes = B * A * (4 + R_REG * 4) + A * 16             # codes + the zero-filled dreg out, anchors in
+        fwd_bytes = stream_bytes + assign_bytes + ann_h.numel() * 4
         bwd_bytes = int(sum(p[3] for p in per_image_vals)) * (R_REG * 4 * 2 + 4 + 21 * 4)
         dom, dom_bytes, dom_ms = "focal_stream_kernel", stream_bytes, ms_stream
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
