@@ -163,7 +163,8 @@ def test_backward_keeps_forward_written_dcls_only_when_upstream_matches():
     want_c, want_r = ops.focal_loss_backward(plain, torch.tensor([1.0, 2.0, 3.0]).cuda())
     fwd = ops.focal_loss_forward(cls, reg, anc, ann, grad_cls_expected=1.0)
     assert torch.equal(fwd["losses"], plain["losses"]) and torch.equal(fwd["assign"], plain["assign"])
-    assert torch.equal(fwd["dcls"], want_c) and int((fwd["dreg"] != 0).sum()) == 0
+    assert_close_rel(fwd["dcls"].cpu(), want_c.cpu(), 1e-6, "forward-written dcls")   # two kernels, same formulas
+    assert int((fwd["dreg"] != 0).sum()) == 0
     fwd["dcls"].fill_(7.0)
     got_c, got_r = ops.focal_loss_backward(fwd, torch.tensor([1.0, 2.0, 3.0]).cuda())
     assert bool((got_c == 7.0).all()), "upstream gradient matched: dcls must not be rewritten"
