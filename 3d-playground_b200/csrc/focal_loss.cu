@@ -30,6 +30,7 @@
 // only scans the assignment codes and writes the regression-gradient rows of the positive anchors (for whatever the
 // real upstream gradients of the regression / direction losses are); otherwise it also recomputes dcls.  No host
 // synchronisation either way.
+#include <stdlib.h>
 #include "assign_tile.cuh"
 
 namespace g3d {
@@ -346,15 +347,16 @@ __device__ __forceinline__ float warp_max_redux(float x) {
     return __int_as_float(k);
 }
 
-__global__ void __launch_bounds__(kTile, 5) assign_codes_kernel(const AssignCodesArgs p) {
-    __shared__ StageSmem sm;
+// One work item of the assignment: anchor tile `tile` (kTile consecutive anchors) x image group `group` (kImgPerCta
+// images).  All kTile threads of the CTA take part (barriers inside).
+__device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem& sm, int tile, int group) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int a = blockIdx.x * kTile + tid;
+    const int a = tile * kTile + tid;
     const bool valid = a < p.A;
     float4 an = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) an = __ldg(p.anchors + a);
     const float area_a = box_area_rn(an.x, an.y, an.z, an.w);
-    const int b0 = blockIdx.y * kImgPerCta;
+    const int b0 = group * kImgPerCta;
     const int nimg = min(kImgPerCta, p.B - b0);
 
     // ---- statistics of the warp's and of the tile's anchors (one barrier)
@@ -449,7 +451,7 @@ __global__ void __launch_bounds__(kTile, 5) assign_codes_kernel(const AssignCode
         // idle, so the 48 bytes / row of zeros are written from here (3 coalesced 16-byte stores per lane, drained in
         // the background) instead of costing the HBM-bound streaming kernel 41 % more traffic.
         if (p.dreg) {
-            const int wa0 = blockIdx.x * kTile + warp * 32, nrows = min(32, p.A - wa0);
+            const int wa0 = tile * kTile + warp * 32, nrows = min(32, p.A - wa0);
             if (nrows > 0) {
                 if (p.R == 12) zero_rows<12>(p.dreg + ((int64_t)b * p.A + wa0) * 12, nrows, lane);
                 else           zero_rows<4>(p.dreg + ((int64_t)b * p.A + wa0) * 4, nrows, lane);
@@ -514,6 +516,11 @@ __global__ void __launch_bounds__(kTile, 5) assign_codes_kernel(const AssignCode
             if (is_pos) p.pos_list[(int64_t)b * p.A + base + __popc(posmask & ((1u << lane) - 1u))] = a;
         }
     }
+}
+
+__global__ void __launch_bounds__(kTile, 5) assign_codes_kernel(const AssignCodesArgs p) {
+    __shared__ StageSmem sm;
+    assign_item(p, sm, blockIdx.x, blockIdx.y);
 }
 
 // =====================================================================================================================
@@ -713,10 +720,13 @@ struct Chunk8 {
 };
 
 // all 32 rows of the chunk exist (the caller routes an image's ragged last chunk to stream_chunk_any)
+// COHERENT: the codes were written earlier in the SAME launch (fused kernel) - they must not come through the
+// non-coherent read-only path
+template <bool COHERENT>
 __device__ __forceinline__ Chunk8 load_chunk8(const StreamArgs& p, int64_t row0, int lane) {
     Chunk8 c;
     const float4* cp = reinterpret_cast<const float4*>(p.cls + row0 * 8);
-    c.code = __ldg(p.assign + row0 + lane);
+    c.code = COHERENT ? __ldcg(p.assign + row0 + lane) : __ldg(p.assign + row0 + lane);
     c.v0 = ld_stream(cp + lane);
     c.v1 = ld_stream(cp + 32 + lane);
     return c;
@@ -758,14 +768,14 @@ __device__ __forceinline__ float process_chunk8(const StreamArgs& p, int b, int6
 }
 
 // generic class count: one thread per row, scalar accesses
-template <int VARIANT, bool GRAD>
+template <int VARIANT, bool GRAD, bool COHERENT>
 __device__ __forceinline__ float stream_chunk_any(const StreamArgs& p, int b, int a0, int lane, float s_cls) {
     const int nrows = min(32, p.A - a0);
     if (nrows <= 0) return 0.0f;
     const int64_t row0 = (int64_t)b * p.A + a0;
     float acc = 0.0f;
     if (lane < nrows) {
-        const int code = __ldg(p.assign + row0 + lane);
+        const int code = COHERENT ? __ldcg(p.assign + row0 + lane) : __ldg(p.assign + row0 + lane);
         const int cls_col = (VARIANT == G3D_VARIANT_3D) ? 20 : 4;
         int pos_cls = -1;
         if (code >= 0) pos_cls = (int)(long long)p.ann[((int64_t)b * p.Gmax + code) * p.W + cls_col];
@@ -788,16 +798,14 @@ struct StreamSmem {
     int arrive;
 };
 
-template <int VARIANT, int CS, bool GRAD>
-__global__ void __launch_bounds__(kTile, 5) focal_stream_kernel(const StreamArgs p) {
-    __shared__ StreamSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    if (tid == 0) sm.arrive = 0;
-    __syncthreads();   // the ticket must be zero before the first warp finishes (all warps are still at the start: cheap)
-    const float npos = (float)__ldg(p.npos + b);
+// One work item of the streaming pass: rows [tile * kRowsPerCta, +kRowsPerCta) of image b, 4 chunks of 32 rows per warp.
+// Returns this warp's share of the focal sum (valid in every lane).
+template <int VARIANT, int CS, bool GRAD, bool COHERENT>
+__device__ __forceinline__ float stream_item(const StreamArgs& p, int tile, int b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float npos = (float)(COHERENT ? __ldcg(p.npos + b) : __ldg(p.npos + b));
     const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
-    const int wa0 = blockIdx.x * kRowsPerCta + warp * (32 * kChunksPerWarp);   // first anchor of this warp
+    const int wa0 = tile * kRowsPerCta + warp * (32 * kChunksPerWarp);   // first anchor of this warp
     float cls_acc = 0.0f;
     int c = 0;
     if (CS == 8) {
@@ -805,11 +813,11 @@ __global__ void __launch_bounds__(kTile, 5) focal_stream_kernel(const StreamArgs
         const int nfull = max(0, min(kChunksPerWarp, (p.A - wa0) >> 5));
         if (nfull > 0) {
             int64_t row0 = (int64_t)b * p.A + wa0;
-            Chunk8 cur = load_chunk8(p, row0, lane);
+            Chunk8 cur = load_chunk8<COHERENT>(p, row0, lane);
 #pragma unroll 1
             for (; c < nfull; ++c, row0 += 32) {
                 Chunk8 nxt = cur;
-                if (c + 1 < nfull) nxt = load_chunk8(p, row0 + 32, lane);
+                if (c + 1 < nfull) nxt = load_chunk8<COHERENT>(p, row0 + 32, lane);
                 cls_acc += process_chunk8<VARIANT, GRAD>(p, b, row0, lane, s_cls, cur);
                 cur = nxt;
             }
@@ -817,11 +825,21 @@ __global__ void __launch_bounds__(kTile, 5) focal_stream_kernel(const StreamArgs
     }
     // generic class count, and the ragged last chunk of an image: one thread per row
 #pragma unroll 1
-    for (; c < kChunksPerWarp; ++c) cls_acc += stream_chunk_any<VARIANT, GRAD>(p, b, wa0 + 32 * c, lane, s_cls);
-    // ---- partial sums: FP32 inside the warp (<= 1024 terms), FP64 from here on.  The last warp of the CTA to get here
-    // (shared-memory ticket, no block barrier: finished warps retire immediately) combines the 8 warp partials in warp
-    // order; the last CTA of the image (global ticket) reduces that image.
-    const float cs = warp_sum_f(cls_acc);
+    for (; c < kChunksPerWarp; ++c)
+        cls_acc += stream_chunk_any<VARIANT, GRAD, COHERENT>(p, b, wa0 + 32 * c, lane, s_cls);
+    return warp_sum_f(cls_acc);   // FP32 inside the warp (<= 1024 terms), FP64 from here on
+}
+
+template <int VARIANT, int CS, bool GRAD>
+__global__ void __launch_bounds__(kTile, 5) focal_stream_kernel(const StreamArgs p) {
+    __shared__ StreamSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    if (tid == 0) sm.arrive = 0;
+    __syncthreads();   // the ticket must be zero before the first warp finishes (all warps are still at the start: cheap)
+    const float cs = stream_item<VARIANT, CS, GRAD, false>(p, blockIdx.x, b);
+    // ---- the last warp of the CTA to get here (shared-memory ticket, no block barrier: finished warps retire
+    // immediately) combines the 8 warp partials in warp order; the last CTA of the image (global ticket) reduces it.
     int arrived = 0;
     if (lane == 0) {
         sm.dred[warp] = (double)cs;
@@ -844,6 +862,116 @@ __global__ void __launch_bounds__(kTile, 5) focal_stream_kernel(const StreamArgs
     is_last = __shfl_sync(0xffffffffu, is_last, 0);
     if (is_last) finalize_image<VARIANT>(p, b);
 }
+
+// =====================================================================================================================
+// fused launch (C == 8): assignment and streaming pass in ONE persistent kernel
+// =====================================================================================================================
+// The assignment is issue-bound and leaves HBM almost idle; the streaming pass is HBM / latency bound and leaves issue
+// slots idle.  Run back to back they cost the sum; here persistent CTAs (as many as fit on the GPU) pull work items
+// from two queues - assignment items (tile x image group, group-major) and streaming items (row tile x image,
+// image-major) - so both kinds are resident on every SM at once and the issue-bound work fills the stalls of the
+// memory-bound work.  A streaming item of image b may only start when every assignment item of b's group has finished
+// (its normaliser num_pos and its codes are complete): `group_done` counts them; writers publish with
+// __threadfence + atomicAdd, readers observe the count, fence, and read the codes through L2 (ld.cg).
+// CTAs in odd / even launch slots prefer different queues so that the mix is there from the start; a CTA whose
+// preferred queue is empty (or not ready) takes from the other; only when no assignment item is left does a CTA wait
+// for the streaming queue - the items it waits for are held by running CTAs, so the wait always ends (no co-residency
+// assumption).  Per-item partial sums go to fixed slots; loss_finalize_kernel reduces them in fixed order.
+struct FusedArgs {
+    AssignCodesArgs q;
+    StreamArgs p;
+    int32_t* ctr;             // work counters, zero on entry, one per 128-byte line (kCtrPitch ints apart):
+                              //   [0] next assignment item, [1 + g] next streaming item of image group g,
+                              //   [1 + n_groups + g] finished assignment items of group g
+    int n_tiles_assign;       // ceil(A / kTile)
+    int n_groups;             // ceil(B / kImgPerCta)
+    int n_assign;             // assignment items = n_tiles_assign * n_groups
+    int sms;                  // SM count (consecutive CTA indices land on different SMs)
+    int mix;                  // 0: every CTA prefers assignment items; k > 0: launch slots with (slot % k) == k-1 prefer streaming
+};
+
+__device__ __forceinline__ int ld_volatile(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+
+constexpr int kCtrPitch = 32;
+__device__ __forceinline__ int32_t* ctr_assign_next(const FusedArgs& f) { return f.ctr; }
+__device__ __forceinline__ int32_t* ctr_stream_next(const FusedArgs& f, int g) { return f.ctr + kCtrPitch * (1 + g); }
+__device__ __forceinline__ int32_t* ctr_group_done(const FusedArgs& f, int g) { return f.ctr + kCtrPitch * (1 + f.n_groups + g); }
+
+// thread 0 of a CTA: try to take a streaming item of the first image group that is completely assigned and still has
+// items (g_lo: first group not known to be exhausted).  Tickets are taken with atomicAdd per group - an over-claim on
+// an exhausted group is harmless, nobody ever holds an item that is not ready, nothing retries under contention.
+// Returns 0 with `item` set, 1 if the next group with items is still being assigned, 2 if every group is exhausted.
+__device__ __forceinline__ int claim_stream_item(const FusedArgs& f, int& g_lo, int& item) {
+    for (int g = g_lo; g < f.n_groups; ++g) {
+        if (ld_volatile(ctr_group_done(f, g)) < f.n_tiles_assign) return 1;
+        const int n_items = min(kImgPerCta, f.p.B - g * kImgPerCta) * f.p.T;
+        if (ld_volatile(ctr_stream_next(f, g)) < n_items) {
+            const int idx = atomicAdd(ctr_stream_next(f, g), 1);
+            if (idx < n_items) { item = (1 << 30) | (g * kImgPerCta * f.p.T + idx); return 0; }
+        }
+        g_lo = g + 1;
+    }
+    return 2;
+}
+
+template <int VARIANT, bool GRAD>
+__global__ void __launch_bounds__(kTile, 5) focal_fused_kernel(const FusedArgs f) {
+    __shared__ StageSmem sm;
+    __shared__ double s_dred[kWarps];
+    __shared__ int s_item[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool prefer_stream = f.mix > 0 && ((int)(blockIdx.x / f.sms) % f.mix) == f.mix - 1;
+    int g_lo = 0;
+    for (int it = 0;; ++it) {
+        if (tid == 0) {
+            int item = -2;                       // -2: nothing yet, -1: all work done, >= 0: (kind << 30) | index
+            while (item == -2) {
+                int st = 0;                      // streaming queue: 0 not looked at, 1 blocked (not ready), 2 exhausted
+                if (prefer_stream) st = claim_stream_item(f, g_lo, item);
+                if (item != -2) break;
+                if (ld_volatile(ctr_assign_next(f)) < f.n_assign) {
+                    const int a = atomicAdd(ctr_assign_next(f), 1);
+                    if (a < f.n_assign) { item = a; break; }
+                }
+                // no assignment item left: everybody streams
+                if (st == 0) st = claim_stream_item(f, g_lo, item);
+                if (item != -2) break;
+                if (st == 2) { item = -1; break; }
+                __nanosleep(500);                // streaming items exist but their image group is still being assigned
+            }
+            if (item >= (1 << 30)) __threadfence();   // acquire: the group's codes / num_pos were published before the count
+            s_item[it & 1] = item;
+        }
+        __syncthreads();
+        const int item = s_item[it & 1];
+        if (item == -1) break;
+        if (item >> 30) {
+            const int s = item & ((1 << 30) - 1);
+            const int b = s / f.p.T, tile = s - b * f.p.T;
+            const float cs = stream_item<VARIANT, 8, GRAD, true>(f.p, tile, b);   // codes / num_pos through L2 (ld.cg)
+            if (lane == 0) s_dred[warp] = (double)cs;
+            __syncthreads();
+            if (tid == 0) {
+                double tc = 0.0;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) tc += s_dred[w];
+                __stcg(f.p.partials + (int64_t)b * f.p.T + tile, tc);
+            }
+        } else {
+            const int group = item / f.n_tiles_assign, tile = item - group * f.n_tiles_assign;
+            assign_item(f.q, sm, tile, group);
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                atomicAdd(ctr_group_done(f, group), 1);
+            }
+        }
+    }
+}
+
+// one warp per image: per-image losses from the partial sums, then (last image) the batch means
+template <int VARIANT>
+__global__ void __launch_bounds__(32) loss_finalize_kernel(const StreamArgs p) { finalize_image<VARIANT>(p, blockIdx.x); }
 
 // =====================================================================================================================
 // backward, part 1: the classification gradient for upstream gradients other than the one launch 3 was told to expect
@@ -921,7 +1049,7 @@ struct FocalWorkspace {
     double* partials;    // [B][T]
     int32_t* pos_list;   // [B][A]
     int32_t* counters;   // zeroed per call: [B] image tickets, [1] batch ticket, [B] npos, [B] nonfinite flags, then
-                         // (8-byte aligned) [B][4] int64 fixed-point sums
+                         // (8-byte aligned) [B][4] int64 fixed-point sums, then the fused kernel's work counters
     int64_t n_counters;  // number of int32 words to zero
     int64_t bytes;
 };
@@ -938,7 +1066,7 @@ static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
     w.pos_list = (int32_t*)(p + off); off += align_up(B * A * 4, 256);
     w.counters = (int32_t*)(p + off);
     const int64_t head = align_up(3 * B + 1, 2);          // int32 words before the int64 sums
-    w.n_counters = head + 8 * B;
+    w.n_counters = head + 8 * B + 32 * (2 * ceil_div(B, 4) + 1);   // ... then the fused kernel's counters (kCtrPitch apart)
     off += align_up(w.n_counters * 4, 256);
     w.bytes = off;
     return w;
@@ -946,6 +1074,7 @@ static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
 static inline int32_t* ws_npos(const FocalWorkspace& w, int64_t B) { return w.counters + B + 1; }
 static inline int32_t* ws_nonfinite(const FocalWorkspace& w, int64_t B) { return w.counters + 2 * B + 1; }
 static inline long long* ws_acc(const FocalWorkspace& w, int64_t B) { return (long long*)(w.counters + align_up(3 * B + 1, 2)); }
+static inline int32_t* ws_fused(const FocalWorkspace& w, int64_t B) { return w.counters + align_up(3 * B + 1, 2) + 8 * B; }
 
 // multi-GPU: the [world][5] shard statistics (all-gathered) -> global batch means and this rank's gradient scales.
 // Fixed (rank) summation order: the same bits on every rank and from run to run.
@@ -1005,6 +1134,12 @@ static void launch_stream(const StreamArgs& p, bool grad, dim3 grid, cudaStream_
 
 static dim3 positives_grid(int64_t B) { return dim3(64, (unsigned)B); }
 
+// G3D_LOSS_FUSED=0 in the environment selects the separate assignment / streaming launches (read per call: no state)
+static bool fused_path_enabled() {
+    const char* e = getenv("G3D_LOSS_FUSED");
+    return !(e && e[0] == '0');
+}
+
 extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                                       int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                                       float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
@@ -1029,25 +1164,15 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     if (rc != G3D_OK) return rc;
     int32_t* npos = ws_npos(w, B);
 
-    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[0], st));
     AssignCodesArgs q;
     q.anchors = (const float4*)anchors; q.gt_box = w.gt_box; q.gt_row = w.gt_row; q.gt_count = w.gt_count;
     q.assign = assign; q.npos = npos; q.pos_list = w.pos_list; q.dreg = dreg; q.B = (int)B; q.A = (int)A; q.Gmax = (int)Gmax;
     q.R = (int)R;
-    assign_codes_kernel<<<dim3((unsigned)ceil_div(A, kTile), (unsigned)ceil_div(B, kImgPerCta)), kTile, 0, st>>>(q);
-    G3D_LAUNCH_CHECK();
-    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));
-
     PosArgs pp;
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.ann = ann; pp.assign = assign; pp.pos_list = w.pos_list;
     pp.npos = npos; pp.acc = ws_acc(w, B); pp.nonfinite = ws_nonfinite(w, B); pp.grad_out = nullptr; pp.grad_scale = nullptr;
     pp.losses = nullptr;
     pp.dreg = nullptr; pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.W = (int)W;
-    if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, false><<<positives_grid(B), 128, 0, st>>>(pp);
-    else                           positives_kernel<G3D_VARIANT_2D, false><<<positives_grid(B), 128, 0, st>>>(pp);
-    G3D_LAUNCH_CHECK();
-    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
-
     StreamArgs p;
     p.cls = cls; p.ann = ann; p.assign = assign; p.npos = npos; p.gt_count = w.gt_count;
     p.acc = ws_acc(w, B); p.nonfinite = ws_nonfinite(w, B); p.gt_count_out = gt_count_out;
@@ -1056,8 +1181,50 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     p.dcls = dcls; p.dreg = dreg; p.g0 = grad_cls_expected;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
     p.T = (int)ceil_div(A, kRowsPerCta);
-    const dim3 grid((unsigned)p.T, (unsigned)B);
     const bool grad = dcls != nullptr;
+    const dim3 agrid((unsigned)ceil_div(A, kTile), (unsigned)ceil_div(B, kImgPerCta));
+
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[0], st));
+    if (C == 8 && fused_path_enabled()) {
+        // ---- one persistent kernel for assignment + streaming pass, then the positives, then the reduction
+        FusedArgs f;
+        f.q = q; f.p = p;
+        f.ctr = ws_fused(w, B);
+        f.n_tiles_assign = (int)agrid.x;
+        f.n_groups = (int)agrid.y;
+        f.n_assign = (int)(agrid.x * agrid.y);
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        f.sms = sms;
+        { const char* e = getenv("G3D_FUSED_MIX"); f.mix = e ? atoi(e) : 2; }
+        const void* kern = nullptr;
+        if (variant == G3D_VARIANT_3D) kern = grad ? (const void*)focal_fused_kernel<G3D_VARIANT_3D, true> : (const void*)focal_fused_kernel<G3D_VARIANT_3D, false>;
+        else                           kern = grad ? (const void*)focal_fused_kernel<G3D_VARIANT_2D, true> : (const void*)focal_fused_kernel<G3D_VARIANT_2D, false>;
+        G3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, 0));
+        int64_t nctas = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+        if (nctas > (int64_t)f.n_assign + p.T * B) nctas = (int64_t)f.n_assign + p.T * B;
+        void* kargs[] = {(void*)&f};
+        G3D_CUDA(cudaLaunchKernel(kern, dim3((unsigned)nctas), dim3(kTile), kargs, 0, st));
+        if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));
+        if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+        else                           positives_kernel<G3D_VARIANT_2D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+        G3D_LAUNCH_CHECK();
+        if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
+        if (variant == G3D_VARIANT_3D) loss_finalize_kernel<G3D_VARIANT_3D><<<(unsigned)B, 32, 0, st>>>(p);
+        else                           loss_finalize_kernel<G3D_VARIANT_2D><<<(unsigned)B, 32, 0, st>>>(p);
+        G3D_LAUNCH_CHECK();
+        if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[3], st));
+        return G3D_OK;
+    }
+    // ---- separate launches (any class count; G3D_LOSS_FUSED=0)
+    assign_codes_kernel<<<agrid, kTile, 0, st>>>(q);
+    G3D_LAUNCH_CHECK();
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));
+    if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+    else                           positives_kernel<G3D_VARIANT_2D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+    G3D_LAUNCH_CHECK();
+    if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
+    const dim3 grid((unsigned)p.T, (unsigned)B);
     if (variant == G3D_VARIANT_3D) {
         if (C == 8) launch_stream<G3D_VARIANT_3D, 8>(p, grad, grid, st);
         else        launch_stream<G3D_VARIANT_3D, 0>(p, grad, grid, st);

@@ -422,14 +422,21 @@ def run_ours(args):
     del cls_h, reg_h, cls_in, reg_in
 
     if rank == 0:
-        # algorithmic bytes.  forward = assign_codes_kernel (issue-bound; anchors + GT in, codes and the
-        # zero-filled dreg out), the positives launch (negligible) and the HBM-bound focal_stream_kernel: cls + codes in,
-        # dcls out.  backward (dcls already written): the positive rows only.
+        # algorithmic bytes of the forward launches.  Fused path (default, C == 8): ONE persistent kernel
+        # does the assignment (anchors + GT in, codes + zero-filled dreg out; issue-bound) and the streaming pass (cls +
+        # codes in, dcls out; HBM-bound) with both kinds of work item resident on every SM.  G3D_LOSS_FUSED=0: the two
+        # as separate launches.  backward (dcls already written): the positive rows only.
+        fused = os.environ.get("G3D_LOSS_FUSED", "1") != "0"
         stream_bytes = B * A * (C_CLS * 4 + 4 + C_CLS * 4)          # cls + codes in, dcls out
         assign_bytes = B * A * (4 + R_REG * 4) + A * 16             # codes + the zero-filled dreg out, anchors in
         fwd_bytes = stream_bytes + assign_bytes + ann_h.numel() * 4
         bwd_bytes = int(sum(p[3] for p in per_image_vals)) * (R_REG * 4 * 2 + 4 + 21 * 4)
-        dom, dom_bytes, dom_ms = "focal_stream_kernel", stream_bytes, ms_stream
+        if fused:
+            knames = ("focal_fused_kernel", "positives_kernel", "loss_finalize_kernel")
+            dom, dom_bytes, dom_ms = "focal_fused_kernel", stream_bytes + assign_bytes, ms_assign
+        else:
+            knames = ("assign_codes_kernel", "positives_kernel", "focal_stream_kernel")
+            dom, dom_bytes, dom_ms = "focal_stream_kernel", stream_bytes, ms_stream
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -447,8 +454,8 @@ def run_ours(args):
             "gpu_launches": 6 * args.steps,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": _traffic(dom), "peak_source": peak_src,
-                         "ms": {"forward": ms_fwd, "backward": ms_bwd, "focal_stream_kernel": ms_stream,
-                                "assign_codes_kernel": ms_assign, "positives_kernel": ms_pos},
+                         "ms": {"forward": ms_fwd, "backward": ms_bwd, knames[0]: ms_assign, knames[1]: ms_pos,
+                                knames[2]: ms_stream},
                          "forward": {"bytes": fwd_bytes, "GBps": fwd_bytes / (ms_fwd * 1e-3) / 1e9,
                                      "frac": fwd_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak},
                          "backward": {"bytes": bwd_bytes, "GBps": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
