@@ -631,6 +631,7 @@ struct StreamArgs {
     float* dreg;               // [B][A][R]  (GRAD only; zero-filled by launch 1)
     float g0;                  // upstream gradient of the classification loss that dcls is formed for
     int B, A, C, R, Gmax, W, T;
+    int cpw;                   // 32-row chunks per warp and work item (rows per item = kWarps * 32 * cpw; T = items per image)
 };
 
 // Executed by ONE warp - the last CTA of image b: reduce the image's T partials in a fixed order (lane-strided
@@ -798,19 +799,19 @@ struct StreamSmem {
     int arrive;
 };
 
-// One work item of the streaming pass: rows [tile * kRowsPerCta, +kRowsPerCta) of image b, 4 chunks of 32 rows per warp.
+// One work item of the streaming pass: kWarps * 32 * cpw consecutive rows of image b, cpw chunks of 32 rows per warp.
 // Returns this warp's share of the focal sum (valid in every lane).
 template <int VARIANT, int CS, bool GRAD, bool COHERENT>
 __device__ __forceinline__ float stream_item(const StreamArgs& p, int tile, int b) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float npos = (float)(COHERENT ? __ldcg(p.npos + b) : __ldg(p.npos + b));
     const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
-    const int wa0 = tile * kRowsPerCta + warp * (32 * kChunksPerWarp);   // first anchor of this warp
+    const int wa0 = (tile * kWarps + warp) * (32 * p.cpw);   // first anchor of this warp
     float cls_acc = 0.0f;
     int c = 0;
     if (CS == 8) {
         // full 32-row chunks: software pipeline, the loads of chunk c + 1 are in flight while chunk c is evaluated
-        const int nfull = max(0, min(kChunksPerWarp, (p.A - wa0) >> 5));
+        const int nfull = max(0, min(p.cpw, (p.A - wa0) >> 5));
         if (nfull > 0) {
             int64_t row0 = (int64_t)b * p.A + wa0;
             Chunk8 cur = load_chunk8<COHERENT>(p, row0, lane);
@@ -825,7 +826,7 @@ __device__ __forceinline__ float stream_item(const StreamArgs& p, int tile, int 
     }
     // generic class count, and the ragged last chunk of an image: one thread per row
 #pragma unroll 1
-    for (; c < kChunksPerWarp; ++c)
+    for (; c < p.cpw; ++c)
         cls_acc += stream_chunk_any<VARIANT, GRAD, COHERENT>(p, b, wa0 + 32 * c, lane, s_cls);
     return warp_sum_f(cls_acc);   // FP32 inside the warp (<= 1024 terms), FP64 from here on
 }
@@ -905,13 +906,31 @@ __device__ __forceinline__ int claim_stream_item(const FusedArgs& f, int& g_lo, 
     for (int g = g_lo; g < f.n_groups; ++g) {
         if (ld_volatile(ctr_group_done(f, g)) < f.n_tiles_assign) return 1;
         const int n_items = min(kImgPerCta, f.p.B - g * kImgPerCta) * f.p.T;
-        if (ld_volatile(ctr_stream_next(f, g)) < n_items) {
-            const int idx = atomicAdd(ctr_stream_next(f, g), 1);
-            if (idx < n_items) { item = (1 << 30) | (g * kImgPerCta * f.p.T + idx); return 0; }
-        }
+        const int idx = atomicAdd(ctr_stream_next(f, g), 1);
+        if (idx < n_items) { item = (1 << 30) | (g * kImgPerCta * f.p.T + idx); return 0; }
         g_lo = g + 1;
     }
     return 2;
+}
+
+// thread 0 of a CTA, non-blocking: the next work item as (kind << 30) | index, -1 when all work is done, -2 when the only
+// work left is streaming items whose image group is still being assigned (try again later).
+__device__ __forceinline__ int claim_item(const FusedArgs& f, bool prefer_stream, int& g_lo, bool& assign_left) {
+    int item = -2, st = 0;      // st: streaming queue 0 not looked at, 1 blocked, 2 exhausted
+    if (prefer_stream || !assign_left) {
+        st = claim_stream_item(f, g_lo, item);
+        if (item != -2) return item;
+    }
+    if (assign_left) {
+        const int a = atomicAdd(ctr_assign_next(f), 1);
+        if (a < f.n_assign) return a;
+        assign_left = false;
+    }
+    if (st == 0) {
+        st = claim_stream_item(f, g_lo, item);
+        if (item != -2) return item;
+    }
+    return st == 2 ? -1 : -2;
 }
 
 template <int VARIANT, bool GRAD>
@@ -921,23 +940,17 @@ __global__ void __launch_bounds__(kTile, 5) focal_fused_kernel(const FusedArgs f
     __shared__ int s_item[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool prefer_stream = f.mix > 0 && ((int)(blockIdx.x / f.sms) % f.mix) == f.mix - 1;
-    int g_lo = 0;
+    // thread 0 keeps the scheduling state and always holds the NEXT item (claimed while the current one is processed,
+    // so the L2 round trips of the work queue are off the critical path)
+    int g_lo = 0, next = -2;
+    bool assign_left = true;
+    if (tid == 0) next = claim_item(f, prefer_stream, g_lo, assign_left);
     for (int it = 0;; ++it) {
         if (tid == 0) {
-            int item = -2;                       // -2: nothing yet, -1: all work done, >= 0: (kind << 30) | index
-            while (item == -2) {
-                int st = 0;                      // streaming queue: 0 not looked at, 1 blocked (not ready), 2 exhausted
-                if (prefer_stream) st = claim_stream_item(f, g_lo, item);
-                if (item != -2) break;
-                if (ld_volatile(ctr_assign_next(f)) < f.n_assign) {
-                    const int a = atomicAdd(ctr_assign_next(f), 1);
-                    if (a < f.n_assign) { item = a; break; }
-                }
-                // no assignment item left: everybody streams
-                if (st == 0) st = claim_stream_item(f, g_lo, item);
-                if (item != -2) break;
-                if (st == 2) { item = -1; break; }
-                __nanosleep(500);                // streaming items exist but their image group is still being assigned
+            int item = next;
+            while (item == -2) {                 // streaming items exist but their image group is still being assigned
+                __nanosleep(500);
+                item = claim_item(f, prefer_stream, g_lo, assign_left);
             }
             if (item >= (1 << 30)) __threadfence();   // acquire: the group's codes / num_pos were published before the count
             s_item[it & 1] = item;
@@ -945,6 +958,7 @@ __global__ void __launch_bounds__(kTile, 5) focal_fused_kernel(const FusedArgs f
         __syncthreads();
         const int item = s_item[it & 1];
         if (item == -1) break;
+        if (tid == 0) next = claim_item(f, prefer_stream, g_lo, assign_left);
         if (item >> 30) {
             const int s = item & ((1 << 30) - 1);
             const int b = s / f.p.T, tile = s - b * f.p.T;
@@ -1180,6 +1194,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     p.shard_stats = shard_stats;
     p.dcls = dcls; p.dreg = dreg; p.g0 = grad_cls_expected;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.Gmax = (int)Gmax; p.W = (int)W;
+    p.cpw = kChunksPerWarp;
     p.T = (int)ceil_div(A, kRowsPerCta);
     const bool grad = dcls != nullptr;
     const dim3 agrid((unsigned)ceil_div(A, kTile), (unsigned)ceil_div(B, kImgPerCta));
@@ -1188,6 +1203,8 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     if (C == 8 && fused_path_enabled()) {
         // ---- one persistent kernel for assignment + streaming pass, then the positives, then the reduction
         FusedArgs f;
+        p.cpw = 2 * kChunksPerWarp;                     // larger streaming items: half as many trips to the work queue
+        p.T = (int)ceil_div(A, 2 * kRowsPerCta);
         f.q = q; f.p = p;
         f.ctr = ws_fused(w, B);
         f.n_tiles_assign = (int)agrid.x;
@@ -1196,7 +1213,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
         int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         f.sms = sms;
-        { const char* e = getenv("G3D_FUSED_MIX"); f.mix = e ? atoi(e) : 2; }
+        { const char* e = getenv("G3D_FUSED_MIX"); f.mix = e ? atoi(e) : 3; }
         const void* kern = nullptr;
         if (variant == G3D_VARIANT_3D) kern = grad ? (const void*)focal_fused_kernel<G3D_VARIANT_3D, true> : (const void*)focal_fused_kernel<G3D_VARIANT_3D, false>;
         else                           kern = grad ? (const void*)focal_fused_kernel<G3D_VARIANT_2D, true> : (const void*)focal_fused_kernel<G3D_VARIANT_2D, false>;
