@@ -240,6 +240,11 @@ __device__ __forceinline__ void im_to_state_one(const T* __restrict__ p /*object
     state_from_bottom(bx, by, fabs(height), o);
 }
 
+__device__ __forceinline__ double2 ld_half_line(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -262,7 +267,9 @@ __global__ void __launch_bounds__(256) im_to_state_kernel(const T* __restrict__ 
         if (in) {
             c = cam ? (int)__ldg(cam + i) : cam_const;
             if (sizeof(T) == 8) {
-                const double2 uv = __ldg(reinterpret_cast<const double2*>(pts + i * 16) + q);
+                // only the bottom face (first 64 of the object's 128 bytes) is needed: ask L2 for 64-byte fills so the
+                // unused top-face half of every line is not fetched from HBM
+                const double2 uv = ld_half_line(reinterpret_cast<const double2*>(pts + i * 16) + q);
                 u = uv.x; v = uv.y;
             } else {
                 const float2 uv = __ldg(reinterpret_cast<const float2*>(pts + i * 16) + q);
