@@ -1,5 +1,5 @@
 // decode.cu — a7 3D BBoxTransform (12 -> 20), a8 2D BBoxTransform (+ fused a9 clip), a9 ClipBoxes.
-#include "common.cuh"
+#include "decode_row.cuh"
 
 namespace g3d {
 
@@ -20,14 +20,9 @@ __global__ void __launch_bounds__(kDecTile) decode3d_kernel(const float4* __rest
     const int a0 = blockIdx.x * kDecTile;
     const int nvalid = min(kDecTile, A - a0);
     const int a = a0 + tid;
-    float w = 0.f, h = 0.f, cx = 0.f, cy = 0.f;
-    if (tid < nvalid) {
-        const float4 an = __ldg(anchors + a);
-        w = __fsub_rn(an.z, an.x);
-        h = __fsub_rn(an.w, an.y);
-        cx = __fadd_rn(an.x, __fmul_rn(0.5f, w));
-        cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
-    }
+    AnchorGeom ag;
+    ag.w = ag.h = ag.cx = ag.cy = 0.f;
+    if (tid < nvalid) ag = anchor_geom(__ldg(anchors + a));
     for (int b = blockIdx.y; b < B; b += gridDim.y) {
         const float4* src = reg + ((int64_t)b * A + a0) * 3;
         float4* dst = out + ((int64_t)b * A + a0) * 5;
@@ -41,24 +36,7 @@ __global__ void __launch_bounds__(kDecTile) decode3d_kernel(const float4* __rest
             const float4 q0 = s_in[3 * tid], q1 = s_in[3 * tid + 1], q2 = s_in[3 * tid + 2];
             const float r[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
             float p[20];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                // corner k = c -/+ L -/+ W +/- H  (utils.py:114-130)
-                const bool lp = k & 2, wp = k & 1, hp = !(k & 4);
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    float v = lp ? __fadd_rn(r[c], r[2 + c]) : __fsub_rn(r[c], r[2 + c]);
-                    v = wp ? __fadd_rn(v, r[4 + c]) : __fsub_rn(v, r[4 + c]);
-                    v = hp ? __fadd_rn(v, r[6 + c]) : __fsub_rn(v, r[6 + c]);
-                    p[2 * k + c] = v;
-                }
-            }
-            p[16] = r[8]; p[17] = r[9]; p[18] = r[10]; p[19] = r[11];
-#pragma unroll
-            for (int i = 0; i < 20; i += 2) {  // utils.py:134-135
-                p[i] = __fadd_rn(__fmul_rn(p[i], w), cx);
-                p[i + 1] = __fadd_rn(__fmul_rn(p[i + 1], h), cy);
-            }
+            decode3d_row(r, ag, p);
 #pragma unroll
             for (int j = 0; j < 5; ++j)
                 s_out[5 * tid + j] = make_float4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
@@ -80,21 +58,7 @@ __global__ void __launch_bounds__(256) decode2d_kernel(const float4* __restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < BA; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 an = __ldg(anchors + (per_image_anchors ? i : (i % A)));
         const float4 d = ld_stream(deltas + i);
-        const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
-        const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
-        const float dx = __fadd_rn(__fmul_rn(d.x, stdv.x), mean.x), dy = __fadd_rn(__fmul_rn(d.y, stdv.y), mean.y);
-        const float dw = __fadd_rn(__fmul_rn(d.z, stdv.z), mean.z), dh = __fadd_rn(__fmul_rn(d.w, stdv.w), mean.w);
-        const float pcx = __fadd_rn(cx, __fmul_rn(dx, w)), pcy = __fadd_rn(cy, __fmul_rn(dy, h));
-        const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
-        float4 o;
-        o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
-        o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-        o.z = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
-        o.w = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
-        if (clip) {
-            o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f);
-            o.z = fminf(o.z, cw);   o.w = fminf(o.w, ch);
-        }
+        const float4 o = decode2d_row(an, d, mean, stdv, clip, cw, ch);
         st_stream(out + i, o);
     }
 }

@@ -5,7 +5,7 @@
 // which covers classification[B, A, C] taken per (image, class) (outer = B, inner = C, N = A, outer_pitch = A*C;
 // retinanet/model.py:287-289, 3D model.py:365-374) and flat vectors (inner = 1; the MULTI_FRAME max-score vector of
 // 3D model.py:320-328).
-#include "common.cuh"
+#include "decode_row.cuh"
 
 namespace g3d {
 
@@ -173,6 +173,28 @@ __global__ void __launch_bounds__(1024) seg_scan_kernel(const int32_t* __restric
     for (int i = lo; i < hi; ++i) { seg_offsets[i] = run; run += min(count[i], cap); }
 }
 
+// Where a candidate's NMS box comes from: a decoded-box tensor (boxes != null), or decoded on the fly from the
+// regression output and the anchors (reg != null) - bit-identical to the corresponding BBoxTransform row - so that the
+// detection tail never has to materialise the [B, A, 20] decoded tensor (80 bytes per anchor) for the ~1 % of rows
+// that survive the score filter.
+struct BoxDecode {
+    const float4* anchors;   // [A] (or [B][A] if per_image_anchors)
+    const float* reg;        // [B][A][12] (variant 3D) or [B][A][4] (variant 2D); null = not used
+    int variant, per_image_anchors, clip;
+    float cw, ch;
+    float4 mean, stdv;
+};
+
+__device__ __forceinline__ float4 decoded_nms_box(const BoxDecode& d, int64_t o, int64_t N, int64_t e) {
+    const float4 an = __ldg(d.anchors + (d.per_image_anchors ? o * N + e : e));
+    if (d.variant == G3D_VARIANT_3D) {
+        const float4 r8 = __ldg(reinterpret_cast<const float4*>(d.reg + (o * N + e) * 12) + 2);
+        return decode3d_box(r8, anchor_geom(an));
+    }
+    const float4 dl = __ldg(reinterpret_cast<const float4*>(d.reg + (o * N + e) * 4));
+    return decode2d_row(an, dl, d.mean, d.stdv, d.clip, d.cw, d.ch);
+}
+
 // One CTA per segment: sort the (arrival-ordered) candidate indices ascending - the order of the reference's
 // boolean-mask gather (3D model.py:380-382) - and pack score / box / source index contiguously.
 __global__ void __launch_bounds__(1024) gather_candidates_kernel(const float* __restrict__ scores, int inner, int64_t N,
@@ -183,7 +205,7 @@ __global__ void __launch_bounds__(1024) gather_candidates_kernel(const float* __
                                                                  const int32_t* __restrict__ seg_offsets,
                                                                  float* __restrict__ cand_scores,
                                                                  float4* __restrict__ cand_boxes,
-                                                                 int32_t* __restrict__ cand_src) {
+                                                                 int32_t* __restrict__ cand_src, const BoxDecode dec) {
     extern __shared__ unsigned int s_idx[];
     const int s = blockIdx.x;
     const int n = min(count[s], cap);
@@ -213,6 +235,8 @@ __global__ void __launch_bounds__(1024) gather_candidates_kernel(const float* __
         if (boxes) {
             const float* bp = boxes + ((int64_t)o * N + e) * box_stride + box_col;
             cand_boxes[off + i] = make_float4(__ldg(bp), __ldg(bp + 1), __ldg(bp + 2), __ldg(bp + 3));
+        } else if (dec.reg) {
+            cand_boxes[off + i] = decoded_nms_box(dec, o, N, e);
         }
     }
 }
@@ -312,15 +336,15 @@ extern "C" int g3d_filter_compact(const float* scores, int64_t outer, int64_t in
     return G3D_OK;
 }
 
-extern "C" int g3d_gather_candidates(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
-                                     const float* boxes, int64_t box_stride, int64_t box_col, const int32_t* idx,
-                                     const int32_t* count, int64_t cap, int32_t* seg_offsets, float* cand_scores,
-                                     float* cand_boxes, int32_t* cand_src, int device, void* stream) {
+static int gather_candidates_launch(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                                    const float* boxes, int64_t box_stride, int64_t box_col, const BoxDecode& dec,
+                                    const int32_t* idx, const int32_t* count, int64_t cap, int32_t* seg_offsets,
+                                    float* cand_scores, float* cand_boxes, int32_t* cand_src, int device, void* stream) {
     G3D_REQUIRE(outer >= 1 && inner >= 1 && N >= 0 && cap >= 1 && cap <= 16384, "bad size (1 <= cap <= 16384)");
     G3D_REQUIRE(outer * inner < ((int64_t)1 << 24), "too many segments");
     G3D_REQUIRE(scores && idx && count && seg_offsets && cand_scores && cand_src, "null pointer");
     G3D_REQUIRE(!boxes || (cand_boxes && box_stride >= 4 && box_col >= 0 && box_col + 4 <= box_stride), "bad box layout");
-    G3D_REQUIRE(!boxes || ((uintptr_t)cand_boxes % 16) == 0, "cand_boxes must be 16-byte aligned");
+    G3D_REQUIRE(!(boxes || dec.reg) || ((uintptr_t)cand_boxes % 16) == 0, "cand_boxes must be 16-byte aligned");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int S = (int)(outer * inner);
@@ -332,7 +356,123 @@ extern "C" int g3d_gather_candidates(const float* scores, int64_t outer, int64_t
     G3D_CUDA(cudaFuncSetAttribute(gather_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gather_candidates_kernel<<<S, 1024, smem, st>>>(scores, (int)inner, N, outer_pitch, boxes, box_stride, box_col, idx,
                                                     count, (int)cap, seg_offsets, cand_scores, (float4*)cand_boxes,
-                                                    cand_src);
+                                                    cand_src, dec);
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}
+
+static int make_box_decode(BoxDecode& d, const float* anchors, int64_t Ba, int64_t B, const float* reg, int variant,
+                           const float* mean_host, const float* std_host, int clip, float clip_w, float clip_h) {
+    G3D_REQUIRE(variant == G3D_VARIANT_2D || variant == G3D_VARIANT_3D, "unknown variant");
+    G3D_REQUIRE(anchors && reg, "null pointer");
+    G3D_REQUIRE(Ba == 1 || Ba == B, "anchors batch must be 1 or B");
+    G3D_REQUIRE(((uintptr_t)anchors % 16) == 0 && ((uintptr_t)reg % 16) == 0, "anchors / regression must be 16-byte aligned");
+    G3D_REQUIRE(variant == G3D_VARIANT_3D || (mean_host && std_host), "2D decode needs mean / std");
+    d.anchors = (const float4*)anchors; d.reg = reg; d.variant = variant;
+    d.per_image_anchors = (Ba == B && B > 1) ? 1 : 0;
+    d.clip = clip; d.cw = clip_w; d.ch = clip_h;
+    d.mean = mean_host ? make_float4(mean_host[0], mean_host[1], mean_host[2], mean_host[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    d.stdv = std_host ? make_float4(std_host[0], std_host[1], std_host[2], std_host[3]) : make_float4(1.f, 1.f, 1.f, 1.f);
+    return G3D_OK;
+}
+
+extern "C" int g3d_gather_candidates(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                                     const float* boxes, int64_t box_stride, int64_t box_col, const int32_t* idx,
+                                     const int32_t* count, int64_t cap, int32_t* seg_offsets, float* cand_scores,
+                                     float* cand_boxes, int32_t* cand_src, int device, void* stream) {
+    BoxDecode none;
+    none.anchors = nullptr; none.reg = nullptr; none.variant = -1; none.per_image_anchors = 0; none.clip = 0;
+    none.cw = none.ch = 0.f; none.mean = none.stdv = make_float4(0.f, 0.f, 0.f, 0.f);
+    return gather_candidates_launch(scores, outer, inner, N, outer_pitch, boxes, box_stride, box_col, none, idx, count, cap,
+                                    seg_offsets, cand_scores, cand_boxes, cand_src, device, stream);
+}
+
+extern "C" int g3d_gather_candidates_decoded(const float* scores, int64_t outer, int64_t inner, int64_t N,
+                                             int64_t outer_pitch, const float* anchors, int64_t Ba, const float* reg,
+                                             int variant, const float* mean_host, const float* std_host, int clip,
+                                             float clip_w, float clip_h, const int32_t* idx, const int32_t* count,
+                                             int64_t cap, int32_t* seg_offsets, float* cand_scores, float* cand_boxes,
+                                             int32_t* cand_src, int device, void* stream) {
+    BoxDecode d;
+    int rc = make_box_decode(d, anchors, Ba, outer, reg, variant, mean_host, std_host, clip, clip_w, clip_h);
+    if (rc != G3D_OK) return rc;
+    G3D_REQUIRE(cand_boxes, "null pointer");
+    return gather_candidates_launch(scores, outer, inner, N, outer_pitch, nullptr, 4, 0, d, idx, count, cap, seg_offsets,
+                                    cand_scores, cand_boxes, cand_src, device, stream);
+}
+
+// ------------------------------------------------------------------------------------------- detection assembly
+namespace g3d {
+
+// One CTA per segment s = (image o, class c): its kept candidates (NMS order = descending score) become rows
+// out_offsets[s] ... of the final tensors: score, class, image index and the box row decoded from the regression
+// output (3D: 20 columns; 2D: 4 columns) - the reference's scores[keep] / boxes[keep] gathers and torch.cat
+// (3D model.py:384-395, retinanet/model.py:298-309) in one launch.
+__global__ void __launch_bounds__(128) assemble_detections_kernel(const int64_t* __restrict__ keep,
+                                                                  const int32_t* __restrict__ keep_count,
+                                                                  const int32_t* __restrict__ seg_offsets,
+                                                                  const int32_t* __restrict__ out_offsets,
+                                                                  const float* __restrict__ cand_scores,
+                                                                  const int32_t* __restrict__ cand_src, int inner, int64_t N,
+                                                                  const BoxDecode dec, float* __restrict__ out_scores,
+                                                                  int64_t* __restrict__ out_classes,
+                                                                  float* __restrict__ out_boxes,
+                                                                  int64_t* __restrict__ out_image) {
+    const int s = blockIdx.x;
+    const int n = keep_count[s];
+    const int64_t in0 = seg_offsets[s], out0 = out_offsets[s];
+    const int64_t o = s / inner, c = s - o * inner;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int64_t pos = keep[in0 + k];
+        const int64_t e = cand_src[pos];
+        const int64_t row = out0 + k;
+        out_scores[row] = cand_scores[pos];
+        out_classes[row] = c;
+        out_image[row] = o;
+        const float4 an = __ldg(dec.anchors + (dec.per_image_anchors ? o * N + e : e));
+        if (dec.variant == G3D_VARIANT_3D) {
+            const float4* rp = reinterpret_cast<const float4*>(dec.reg + (o * N + e) * 12);
+            const float4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2);
+            const float r[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            float p[20];
+            decode3d_row(r, anchor_geom(an), p);
+            float4* op = reinterpret_cast<float4*>(out_boxes + row * 20);
+#pragma unroll
+            for (int j = 0; j < 5; ++j) op[j] = make_float4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+        } else {
+            const float4 dl = __ldg(reinterpret_cast<const float4*>(dec.reg + (o * N + e) * 4));
+            reinterpret_cast<float4*>(out_boxes)[row] = decode2d_row(an, dl, dec.mean, dec.stdv, dec.clip, dec.cw, dec.ch);
+        }
+    }
+}
+
+}  // namespace g3d
+
+extern "C" int g3d_exclusive_scan_i32(const int32_t* count, int64_t S, int32_t* offsets, int device, void* stream) {
+    G3D_REQUIRE(S >= 0 && S < ((int64_t)1 << 24), "bad size");
+    G3D_REQUIRE(offsets && (count || S == 0), "null pointer");
+    G3D_GUARD(device);
+    seg_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(count, (int)S, 0x7fffffff, offsets);
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}
+
+extern "C" int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_count, const int32_t* seg_offsets,
+                                       const int32_t* out_offsets, const float* cand_scores, const int32_t* cand_src,
+                                       int64_t outer, int64_t inner, int64_t N, const float* anchors, int64_t Ba,
+                                       const float* reg, int variant, const float* mean_host, const float* std_host,
+                                       int clip, float clip_w, float clip_h, float* out_scores, int64_t* out_classes,
+                                       float* out_boxes, int64_t* out_image, int device, void* stream) {
+    G3D_REQUIRE(outer >= 1 && inner >= 1 && N >= 0 && outer * inner < ((int64_t)1 << 24), "bad size");
+    G3D_REQUIRE(keep_count && seg_offsets && out_offsets, "null pointer");
+    BoxDecode d;
+    int rc = make_box_decode(d, anchors, Ba, outer, reg, variant, mean_host, std_host, clip, clip_w, clip_h);
+    if (rc != G3D_OK) return rc;
+    G3D_REQUIRE(((uintptr_t)out_boxes % 16) == 0, "out_boxes must be 16-byte aligned");
+    G3D_GUARD(device);
+    assemble_detections_kernel<<<(unsigned)(outer * inner), 128, 0, (cudaStream_t)stream>>>(
+        keep, keep_count, seg_offsets, out_offsets, cand_scores, cand_src, (int)inner, N, d, out_scores, out_classes,
+        out_boxes, out_image);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

@@ -352,6 +352,67 @@ def gather_candidates(scores, outer, inner, N, outer_pitch, idx, count, cap, box
     return seg_offsets, cand_scores, cand_boxes, cand_src
 
 
+def _decode_args(anchors, regression, mean, std, clip_wh):
+    """common argument block of the decode-on-the-fly entry points"""
+    anc = _prep(anchors, torch.float32)
+    if anc.dim() == 2:
+        anc = anc.unsqueeze(0)
+    reg = _prep(regression, torch.float32)
+    if reg.dim() != 3 or reg.shape[2] not in (4, 12) or anc.dim() != 3 or anc.shape[1] != reg.shape[1] or anc.shape[2] != 4:
+        raise ValueError(f"expected anchors[1|B,A,4] and regression[B,A,12|4], got {tuple(anc.shape)} and {tuple(reg.shape)}")
+    variant = VARIANT_3D if reg.shape[2] == 12 else VARIANT_2D
+    mean_h = (ctypes.c_float * 4)(*[float(x) for x in mean]) if mean is not None else None
+    std_h = (ctypes.c_float * 4)(*[float(x) for x in std]) if std is not None else None
+    if variant == VARIANT_2D and (mean_h is None or std_h is None):
+        raise ValueError("the 2D decode needs mean and std")
+    clip = 0 if clip_wh is None else 1
+    cw, ch = (0.0, 0.0) if clip_wh is None else (float(clip_wh[0]), float(clip_wh[1]))
+    return anc, reg, variant, mean_h, std_h, clip, cw, ch
+
+
+def gather_candidates_decoded(scores, outer, inner, N, outer_pitch, idx, count, cap, anchors, regression, mean=None,
+                              std=None, clip_wh=None):
+    """gather_candidates whose NMS boxes are decoded on the fly from (anchors, regression) - no decoded tensor needed.
+    Returns (seg_offsets i32[S+1], cand_scores f32[T], cand_boxes f32[T,4], cand_src i32[T])."""
+    dev = _need_cuda(scores, idx, count, anchors, regression)
+    anc, reg, variant, mean_h, std_h, clip, cw, ch = _decode_args(anchors, regression, mean, std, clip_wh)
+    S = outer * inner
+    T = S * cap
+    seg_offsets = torch.empty((S + 1,), dtype=torch.int32, device=dev)
+    cand_scores = torch.empty((T,), dtype=torch.float32, device=dev)
+    cand_src = torch.empty((T,), dtype=torch.int32, device=dev)
+    cand_boxes = torch.empty((T, 4), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_gather_candidates_decoded(_p(scores), outer, inner, N, outer_pitch, _p(anc), anc.shape[0], _p(reg),
+                                                   variant, mean_h, std_h, clip, cw, ch, _p(idx), _p(count), cap,
+                                                   _p(seg_offsets), _p(cand_scores), _p(cand_boxes), _p(cand_src),
+                                                   _idx(dev), _stream(dev)), "g3d_gather_candidates_decoded")
+    return seg_offsets, cand_scores, cand_boxes, cand_src
+
+
+def assemble_detections(keep, keep_count, seg_offsets, cand_scores, cand_src, outer, inner, N, anchors, regression,
+                        mean=None, std=None, clip_wh=None):
+    """Final (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K]) from the per-segment keep lists of
+    nms_segmented(relative=False): one scan, ONE 4-byte device->host read (K), one assembly launch."""
+    dev = _need_cuda(keep, keep_count, seg_offsets, cand_scores, cand_src, anchors, regression)
+    anc, reg, variant, mean_h, std_h, clip, cw, ch = _decode_args(anchors, regression, mean, std, clip_wh)
+    S = outer * inner
+    L = _lib.lib()
+    out_offsets = torch.empty((S + 1,), dtype=torch.int32, device=dev)
+    check(L.g3d_exclusive_scan_i32(_p(keep_count), S, _p(out_offsets), _idx(dev), _stream(dev)), "g3d_exclusive_scan_i32")
+    K = int(out_offsets[S].item())
+    cols = 20 if variant == VARIANT_3D else 4
+    scores = torch.empty((K,), dtype=torch.float32, device=dev)
+    classes = torch.empty((K,), dtype=torch.int64, device=dev)
+    image = torch.empty((K,), dtype=torch.int64, device=dev)
+    boxes = torch.empty((K, cols), dtype=torch.float32, device=dev)
+    if K:
+        check(L.g3d_assemble_detections(_p(keep), _p(keep_count), _p(seg_offsets), _p(out_offsets), _p(cand_scores),
+                                        _p(cand_src), outer, inner, N, _p(anc), anc.shape[0], _p(reg), variant, mean_h,
+                                        std_h, clip, cw, ch, _p(scores), _p(classes), _p(boxes), _p(image), _idx(dev),
+                                        _stream(dev)), "g3d_assemble_detections")
+    return scores, classes, boxes, image
+
+
 # ------------------------------------------------------------------------------------------------ a11: NMS
 def nms_segmented(boxes, scores, seg_offsets, max_seg_len, iou_threshold, box_col=0, relative=True):
     """Greedy NMS on S independent segments.  boxes[N,K] (box columns box_col..box_col+3), scores[N],

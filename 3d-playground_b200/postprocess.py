@@ -145,6 +145,38 @@ def detect_per_class(classification, boxes, box_col=0, score_threshold=None, lad
     return scores, classes, out_boxes, image_index
 
 
+def detect_per_class_fused(classification, regression, anchors, score_threshold=None, ladder_start=None, keep_max=KEEP_MAX,
+                           iou_threshold=NMS_IOU, cap=None, mean=None, std=None, clip_wh=None):
+    """detect_per_class without the decoded tensor: the score filter runs first, only the candidates' NMS
+    boxes and the kept rows are decoded - from regression[B,A,12] (3D directional model: NMS on columns 16..19, 20-column
+    rows out) or regression[B,A,4] (2D model: mean / std / optional clip as BBoxTransform + ClipBoxes).
+    Same result, bit for bit, as decode -> detect_per_class; 7 launches and one 4-byte device->host read per batch.
+    Returns (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K])."""
+    if (score_threshold is None) == (ladder_start is None):
+        raise ValueError("give exactly one of score_threshold / ladder_start")
+    dev = classification.device
+    cls = ops._prep(classification, torch.float32)
+    B, A, C = cls.shape
+    if ladder_start is not None:
+        _, _, thr = ops.threshold_ladder(cls, B, C, A, A * C, ladder_start, keep_max)
+        cap = min(keep_max, 16384) if cap is None else cap
+    else:
+        thr = torch.full((B * C,), float(np.float32(score_threshold)), dtype=torch.float32, device=dev)
+        cap = 16384 if cap is None else cap
+    cap = int(min(cap, max(A, 1)))
+    idx, count = ops.filter_compact(cls, B, C, A, A * C, thr, cap)
+    seg_offsets, cand_scores, cand_boxes, cand_src = ops.gather_candidates_decoded(
+        cls, B, C, A, A * C, idx, count, cap, anchors, regression, mean, std, clip_wh)
+    keep, keep_count = ops.nms_segmented(cand_boxes, cand_scores, seg_offsets, cap, iou_threshold, 0, relative=False)
+    out = ops.assemble_detections(keep, keep_count, seg_offsets, cand_scores, cand_src, B, C, A, anchors, regression,
+                                  mean, std, clip_wh)
+    # candidate overflow is checked after the fact, on the same synchronisation point the result needs anyway
+    if int(count.max().item()) > cap:
+        raise Geom3dError(f"a (image, class) segment has {int(count.max().item())} candidates above the score threshold but "
+                          f"the candidate capacity is {cap}; pass a larger `cap` (<= 16384) or raise the threshold")
+    return out
+
+
 def detect_multi_frame(classification, boxes, box_col=16, ladder_start=LADDER_START_MULTI, keep_max=KEEP_MAX,
                        iou_threshold=NMS_IOU):
     """MULTI_FRAME branch of the 3D model (model.py:311-344): max over classes, one ladder over the whole batch,
@@ -178,13 +210,13 @@ class PostProcess3D(nn.Module):
         self.regressBoxes = BBoxTransform3D()
 
     def forward(self, classification, regression, anchors, LOCALIZE=False, MULTI_FRAME=False):
-        transformed_anchors = self.regressBoxes(anchors, regression)
         if MULTI_FRAME:
-            return detect_multi_frame(classification, transformed_anchors)
+            return detect_multi_frame(classification, self.regressBoxes(anchors, regression))
         if LOCALIZE:
-            return transformed_anchors, classification
-        scores, classes, boxes, _ = detect_per_class(classification[:1], transformed_anchors[:1], box_col=16,
-                                                     ladder_start=LADDER_START_SINGLE)
+            return self.regressBoxes(anchors, regression), classification
+        # default branch: filter first, decode only what survives (no [B,A,20] tensor)
+        scores, classes, boxes, _ = detect_per_class_fused(classification[:1], regression[:1], anchors,
+                                                           ladder_start=LADDER_START_SINGLE)
         return [scores, classes, boxes]
 
 
@@ -198,9 +230,11 @@ class PostProcess2D(nn.Module):
 
     def forward(self, classification, regression, anchors, img_batch, LOCALIZE=False):
         _, _, height, width = img_batch.shape
-        transformed_anchors = self.regressBoxes(anchors, regression, clip_wh=(width, height))  # decode + clip fused
         if LOCALIZE:
-            return transformed_anchors, classification
-        scores, classes, boxes, _ = detect_per_class(classification[:1], transformed_anchors[:1], box_col=0,
-                                                     score_threshold=SCORE_THRESHOLD_2D)
+            return self.regressBoxes(anchors, regression, clip_wh=(width, height)), classification  # decode + clip fused
+        mean, std = self.regressBoxes._host_params()
+        anc = anchors if anchors.shape[0] == 1 else anchors[:1]
+        scores, classes, boxes, _ = detect_per_class_fused(classification[:1], regression[:1], anc,
+                                                           score_threshold=SCORE_THRESHOLD_2D, mean=mean, std=std,
+                                                           clip_wh=(width, height))
         return [scores, classes, boxes]

@@ -196,6 +196,36 @@ int g3d_gather_candidates(const float* scores, int64_t outer, int64_t inner, int
                           float* cand_boxes, int32_t* cand_src, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * the detection tail without the decoded tensor.  Thresholding happens BEFORE decoding, so only the
+ * candidates' NMS boxes and the kept rows are ever decoded - bit-identical to the rows g3d_decode3d / g3d_decode2d
+ * (with the same clip) would produce.  Replaces, together with g3d_filter_compact / g3d_nms_segmented, everything
+ * ResNet.forward does after the heads: 3D model.py:346-397 (regressBoxes, ladder, per-class nms, cat), 2D
+ * retinanet/model.py:270-311 (regressBoxes, clipBoxes, scores > 0.05, nms, cat).
+ *
+ * g3d_gather_candidates_decoded: as g3d_gather_candidates, but cand_boxes[.,4] is decoded from reg[B,A,12] (variant 3D:
+ *   columns 16..19 of the BBoxTransform row) or reg[B,A,4] (variant 2D: the BBoxTransform row, clipped if clip != 0),
+ *   anchors[Ba,A,4] with Ba == 1 or B.  mean_host / std_host: 2D only (may be NULL for 3D).
+ * g3d_exclusive_scan_i32: offsets[S+1] = exclusive scan of count[S] (offsets[S] = total; one 4-byte read tells the host
+ *   how many detections to allocate).
+ * g3d_assemble_detections: rows out_offsets[s] ... of out_scores[K], out_classes[K] (int64), out_image[K] (int64) and
+ *   out_boxes[K,20|4] from the keep lists of g3d_nms_segmented(relative = 0): segment s = o*inner + c contributes its
+ *   keep_count[s] kept candidates in NMS order (descending score) - image-major, then class, as the reference
+ *   concatenates them.
+ */
+int g3d_gather_candidates_decoded(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                                  const float* anchors, int64_t Ba, const float* reg, int variant,
+                                  const float* mean_host, const float* std_host, int clip, float clip_w, float clip_h,
+                                  const int32_t* idx, const int32_t* count, int64_t cap, int32_t* seg_offsets,
+                                  float* cand_scores, float* cand_boxes, int32_t* cand_src, int device, void* stream);
+int g3d_exclusive_scan_i32(const int32_t* count, int64_t S, int32_t* offsets, int device, void* stream);
+int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_count, const int32_t* seg_offsets,
+                            const int32_t* out_offsets, const float* cand_scores, const int32_t* cand_src,
+                            int64_t outer, int64_t inner, int64_t N, const float* anchors, int64_t Ba,
+                            const float* reg, int variant, const float* mean_host, const float* std_host,
+                            int clip, float clip_w, float clip_h, float* out_scores, int64_t* out_classes,
+                            float* out_boxes, int64_t* out_image, int device, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * a11 NMS       torchvision.ops.nms as called at retinanet/model.py:297, 3D model.py:383 (and :336 through
  *               batched_nms :19-57), perform_3D_detection_on_video_sequences.py:78, MC3D_crop_tracker.py:507,614,634
  * Segmented greedy NMS: S independent segments, segment s = entries seg_offsets[s] .. seg_offsets[s+1]-1 of

@@ -209,3 +209,34 @@ def test_full_size_decode_nms_properties():
         m = key == grp
         k2 = ops.nms(b[m][:, 16:20].contiguous(), s[m].contiguous(), 0.5)
         assert torch.equal(k2, torch.arange(int(m.sum()), device="cuda"))
+
+
+@pytest.mark.parametrize("three_d", [True, False])
+def test_fused_detection_tail_equals_decode_then_detect(three_d):
+    """filter-before-decode must give, bit for bit, what decode -> detect_per_class gives - batch of
+    images, fixed threshold and adaptive ladder, and an image without any detection"""
+    _, pp = _mods()
+    g = synth.gen(21)
+    H, W, B = 128, 160, 4
+    anc = synth.anchors(H, W).cuda()
+    A = anc.shape[1]
+    cls = synth.detection_scores(B, A, 8, g, objects=12, per_object=9).cuda()
+    cls[2] = 0.01                                                     # nothing above the fixed threshold in image 2
+    if three_d:
+        reg = torch.randn(B, A, 12, generator=g).cuda() * 0.1
+        reg[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5]).cuda() + torch.randn(B, A, 4, generator=g).cuda() * 0.05
+        boxes, col, extra = pp.BBoxTransform3D()(anc, reg), 16, {}
+    else:
+        reg = torch.randn(B, A, 4, generator=g).cuda() * 0.5
+        t = pp.BBoxTransform2D()
+        boxes, col = t(anc, reg, clip_wh=(W, H)), 0
+        mean, std = t._host_params()
+        extra = dict(mean=mean, std=std, clip_wh=(W, H))
+    for kw in (dict(score_threshold=0.05), dict(ladder_start=1e-25, keep_max=300, cap=512)):
+        want = pp.detect_per_class(cls, boxes, box_col=col, **kw)
+        got = pp.detect_per_class_fused(cls, reg, anc, **kw, **extra)
+        assert want[0].numel() > 0
+        for w_, g_ in zip(want, got):
+            assert w_.dtype == g_.dtype and torch.equal(w_, g_)
+    none = pp.detect_per_class_fused(cls[2:3], reg[2:3], anc, score_threshold=0.05, **extra)
+    assert none[0].numel() == 0 and none[2].shape == (0, 20 if three_d else 4)
