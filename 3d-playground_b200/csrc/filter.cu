@@ -152,6 +152,51 @@ __global__ void __launch_bounds__(256) compact_kernel(const float* __restrict__ 
     }
 }
 
+// 8 scores per row (classification[B,A,8]): one warp per 32 consecutive rows, lane l holding float4 l and l + 32 of the
+// chunk's 64 - every global access of the warp is one contiguous 512-byte run - i.e. classes (l & 1) * 4 .. + 3 of rows
+// l >> 1 and 16 + (l >> 1).  A chunk without a single passing score (the usual case: ~99 % of the rows are background)
+// costs two loads, eight compares and one vote.
+__global__ void __launch_bounds__(256) compact8_kernel(const float* __restrict__ scores, int64_t N, int64_t outer_pitch,
+                                                       const float* __restrict__ thr, int cap,
+                                                       int32_t* __restrict__ idx_out, int32_t* __restrict__ count) {
+    const int o = blockIdx.y, lane = threadIdx.x & 31;
+    const float4* base = reinterpret_cast<const float4*>(scores + (int64_t)o * outer_pitch);
+    const int c0 = (lane & 1) * 4;
+    const float4 t = make_float4(__ldg(thr + o * 8 + c0), __ldg(thr + o * 8 + c0 + 1), __ldg(thr + o * 8 + c0 + 2),
+                                 __ldg(thr + o * 8 + c0 + 3));
+    const int64_t nchunks = (N + 31) >> 5;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const unsigned lt = (1u << lane) - 1u;
+    for (int64_t ch = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ch < nchunks; ch += nwarps) {
+        const int64_t n0 = ch << 5;
+        const int nrows = (int)min((int64_t)32, N - n0);
+        const int r0 = lane >> 1, r1 = 16 + (lane >> 1);
+        float4 v0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), v1 = v0;
+        if (r0 < nrows) v0 = ld_stream(base + n0 * 2 + lane);
+        if (r1 < nrows) v1 = ld_stream(base + n0 * 2 + 32 + lane);
+        const bool p[2][4] = {{v0.x > t.x, v0.y > t.y, v0.z > t.z, v0.w > t.w}, {v1.x > t.x, v1.y > t.y, v1.z > t.z, v1.w > t.w}};
+        const bool any = p[0][0] | p[0][1] | p[0][2] | p[0][3] | p[1][0] | p[1][1] | p[1][2] | p[1][3];
+        if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned bal = __ballot_sync(0xffffffffu, p[h][k]);
+                if (bal == 0) continue;
+                // even lanes hold class k, odd lanes class 4 + k
+                const unsigned mine = bal & ((lane & 1) ? 0xaaaaaaaau : 0x55555555u);
+                const int s = o * 8 + c0 + k;
+                int pos = 0;
+                const int leader = __ffs(mine) - 1;
+                if (mine && lane == leader) pos = atomicAdd(count + s, __popc(mine));
+                // both parities shuffle in the same instruction: each lane reads its own group's leader
+                pos = __shfl_sync(0xffffffffu, pos, mine ? leader : lane) + __popc(mine & lt);
+                if (p[h][k] && pos < cap) idx_out[(int64_t)s * cap + pos] = (int32_t)(n0 + (h ? r1 : r0));
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------- candidate packing (a10)
 // exclusive scan of min(count, cap) over the S segments -> seg_offsets[S+1]   (single CTA; S is small)
 __global__ void __launch_bounds__(1024) seg_scan_kernel(const int32_t* __restrict__ count, int S, int cap,
@@ -329,7 +374,7 @@ extern "C" int g3d_filter_compact(const float* scores, int64_t outer, int64_t in
     if (N == 0) return G3D_OK;
     dim3 grid((unsigned)grid_x_for(N, outer), (unsigned)outer);
     if (inner == 8)
-        compact_kernel<8><<<grid, 256, 0, st>>>(scores, N, 8, outer_pitch, thr, (int)cap, idx_out, count_out);
+        compact8_kernel<<<grid, 256, 0, st>>>(scores, N, outer_pitch, thr, (int)cap, idx_out, count_out);
     else
         compact_kernel<0><<<grid, 256, 0, st>>>(scores, N, (int)inner, outer_pitch, thr, (int)cap, idx_out, count_out);
     G3D_LAUNCH_CHECK();

@@ -17,6 +17,7 @@ constexpr int kNmsThreads = 1024;
 constexpr int kSortCap = 16384;        // longest segment the single-CTA shared-memory sort handles
 constexpr int kSmemBoxCap = 4096;      // longest segment whose sorted boxes are cached in shared memory
 constexpr int kLocalSort = 4096;       // tile of the multi-CTA (global) bitonic sort
+constexpr int kShortSeg = 2048;        // two-size scheme (S >= 64): segments up to this length run on 256-thread CTAs
 
 __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
     if (score == 0.0f) score = 0.0f;  // -0.0 and +0.0 compare equal in the reference's sort
@@ -46,16 +47,20 @@ __device__ __forceinline__ void bitonic_smem(uint64_t* sk, int P, int k_from, in
     }
 }
 
-// one CTA per segment, n <= kSortCap
-__global__ void __launch_bounds__(kNmsThreads) seg_sort_kernel(const float* __restrict__ scores,
-                                                               const int32_t* __restrict__ seg_offsets,
-                                                               const float* __restrict__ boxes, int64_t stride, int64_t col,
-                                                               int32_t* __restrict__ sidx, float4* __restrict__ sbox) {
+// one CTA per segment, n <= kSortCap.  Segments whose length is outside (n_lo, n_hi] are left to the other launch of a
+// two-size scheme: many short segments run 256-thread CTAs with little shared memory (several per SM), the rare long
+// ones 1024-thread CTAs with the full buffer.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) seg_sort_kernel(const float* __restrict__ scores,
+                                                           const int32_t* __restrict__ seg_offsets,
+                                                           const float* __restrict__ boxes, int64_t stride, int64_t col,
+                                                           int32_t* __restrict__ sidx, float4* __restrict__ sbox, int n_lo,
+                                                           int n_hi) {
     extern __shared__ uint64_t sk[];
     const int seg = blockIdx.x;
     const int off = seg_offsets[seg];
     const int n = seg_offsets[seg + 1] - off;
-    if (n <= 0) return;
+    if (n <= n_lo || n > n_hi) return;
     int P = 2;
     while (P < n) P <<= 1;
     for (int i = threadIdx.x; i < P; i += blockDim.x)
@@ -148,12 +153,13 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-__global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* __restrict__ sbox,
-                                                                 const int32_t* __restrict__ sidx,
-                                                                 const int32_t* __restrict__ seg_offsets, float thr,
-                                                                 int relative, int removed_words, int box_cap,
-                                                                 int64_t* __restrict__ keep_out,
-                                                                 int32_t* __restrict__ keep_count) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __restrict__ sbox,
+                                                             const int32_t* __restrict__ sidx,
+                                                             const int32_t* __restrict__ seg_offsets, float thr,
+                                                             int relative, int removed_words, int box_cap,
+                                                             int64_t* __restrict__ keep_out,
+                                                             int32_t* __restrict__ keep_count, int n_lo, int n_hi) {
     extern __shared__ __align__(16) unsigned char dyn[];
     float4* cbox = reinterpret_cast<float4*>(dyn);  // [box_cap]: sorted boxes of segments with n <= box_cap
     uint32_t* removed = reinterpret_cast<uint32_t*>(dyn + sizeof(float4) * box_cap);
@@ -169,16 +175,17 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
     const int off = seg_offsets[seg];
     const int n = seg_offsets[seg + 1] - off;
     if (n <= 0) {
-        if (tid == 0) keep_count[seg] = 0;
+        if (tid == 0 && n_lo < 0) keep_count[seg] = 0;
         return;
     }
+    if (n <= n_lo || n > n_hi) return;   // the other launch of the two-size scheme handles this segment
     const float4* gbox = sbox + off;
     const int my_words = 2 * ((n + 63) >> 6);
-    for (int i = tid; i < my_words; i += kNmsThreads) removed[i] = 0u;
+    for (int i = tid; i < my_words; i += THREADS) removed[i] = 0u;
     // short segments keep their boxes in shared memory; long ones stream them from L2 (generic pointer)
     const float4* bsrc = gbox;
     if (n <= box_cap) {
-        for (int i = tid; i < n; i += kNmsThreads) cbox[i] = gbox[i];
+        for (int i = tid; i < n; i += THREADS) cbox[i] = gbox[i];
         bsrc = cbox;
     }
     __syncthreads();
@@ -197,8 +204,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
             darea[tid] = box_area_rn(b.x, b.y, b.z, b.w);
         }
         __syncthreads();
-        {   // 64x64 strictly-upper-triangular suppression bits: thread (row i = tid/16) covers columns l16 + 16q
-            const int i = tid >> 4, l16 = tid & 15;
+        // 64x64 strictly-upper-triangular suppression bits: 16 lanes per row, lane l16 covers columns l16 + 16q
+#pragma unroll 1
+        for (int i = tid >> 4; i < 64; i += THREADS >> 4) {
+            const int l16 = tid & 15;
             const bool row_live = (i < m) && !((remword >> i) & 1ull);
             uint64_t word = 0ull;
 #pragma unroll
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_greedy_kernel(const float4* _
         const int kc = __popcll(s_keep);
         total_kept += kc;
         if (kc > 0) {
-            for (int j = base + 64 + tid; j < n; j += kNmsThreads) {
+            for (int j = base + 64 + tid; j < n; j += THREADS) {
                 if ((removed[j >> 5] >> (j & 31)) & 1u) continue;
                 const float4 bj = bsrc[j];
                 const float aj = box_area_rn(bj.x, bj.y, bj.z, bj.w);
@@ -318,14 +327,27 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
     float thr_f = (float)iou_threshold;
     if ((double)thr_f > iou_threshold) thr_f = nextafterf(thr_f, -INFINITY);
 
+    // many segments: short ones (<= kShortSeg boxes) on small CTAs, several per SM; the rest on 1024-thread CTAs
+    const bool two_size = (S >= 64) && (max_seg_len > kShortSeg);
+    const bool all_short = (S >= 64) && (max_seg_len <= kShortSeg);
     if (max_seg_len <= kSortCap) {
         int P = 2;
         while (P < max_seg_len) P <<= 1;
         const size_t smem = (size_t)P * 8;
-        G3D_CUDA(cudaFuncSetAttribute(seg_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        seg_sort_kernel<<<(unsigned)S, kNmsThreads, smem, st>>>(scores, seg_offsets, boxes, box_stride, box_col, w.sidx,
-                                                                w.sbox);
-        G3D_LAUNCH_CHECK();
+        if (two_size || all_short) {
+            int Ps = 2;
+            while (Ps < (all_short ? max_seg_len : kShortSeg)) Ps <<= 1;
+            seg_sort_kernel<256><<<(unsigned)S, 256, (size_t)Ps * 8, st>>>(scores, seg_offsets, boxes, box_stride, box_col,
+                                                                         w.sidx, w.sbox, 0, kShortSeg);
+            G3D_LAUNCH_CHECK();
+        }
+        if (!all_short) {
+            G3D_CUDA(cudaFuncSetAttribute(seg_sort_kernel<kNmsThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            seg_sort_kernel<kNmsThreads><<<(unsigned)S, kNmsThreads, smem, st>>>(scores, seg_offsets, boxes, box_stride,
+                                                                             box_col, w.sidx, w.sbox,
+                                                                             two_size ? kShortSeg : 0, 0x7fffffff);
+            G3D_LAUNCH_CHECK();
+        }
     } else {
         int64_t P = kLocalSort;
         while (P < max_seg_len) P <<= 1;
@@ -348,12 +370,23 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
         G3D_LAUNCH_CHECK();
     }
     const int removed_words = (int)(2 * ceil_div(max_seg_len, 64));
-    const int box_cap = (int)(max_seg_len < kSmemBoxCap ? max_seg_len : kSmemBoxCap);
-    const size_t smem = sizeof(float4) * box_cap + (size_t)removed_words * 4;
-    G3D_REQUIRE(smem <= 220 * 1024, "segment too long for the shared-memory suppression bitset (max ~1.2M boxes)");
-    G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nms_greedy_kernel<<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative, removed_words,
-                                                              box_cap, keep_out, keep_count);
-    G3D_LAUNCH_CHECK();
+    if (two_size || all_short) {
+        const int cap_s = (int)(all_short ? max_seg_len : kShortSeg);
+        const int words_s = (int)(2 * ceil_div(cap_s, 64));
+        const size_t smem_s = sizeof(float4) * cap_s + (size_t)words_s * 4;
+        nms_greedy_kernel<256><<<(unsigned)S, 256, smem_s, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative, words_s, cap_s,
+                                                               keep_out, keep_count, -1, kShortSeg);
+        G3D_LAUNCH_CHECK();
+    }
+    if (!all_short) {
+        const int box_cap = (int)(max_seg_len < kSmemBoxCap ? max_seg_len : kSmemBoxCap);
+        const size_t smem = sizeof(float4) * box_cap + (size_t)removed_words * 4;
+        G3D_REQUIRE(smem <= 220 * 1024, "segment too long for the shared-memory suppression bitset (max ~1.2M boxes)");
+        G3D_CUDA(cudaFuncSetAttribute(nms_greedy_kernel<kNmsThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        nms_greedy_kernel<kNmsThreads><<<(unsigned)S, kNmsThreads, smem, st>>>(w.sbox, w.sidx, seg_offsets, thr_f, relative,
+                                                                           removed_words, box_cap, keep_out, keep_count,
+                                                                           two_size ? kShortSeg : -1, 0x7fffffff);
+        G3D_LAUNCH_CHECK();
+    }
     return G3D_OK;
 }
