@@ -20,7 +20,6 @@ reg3[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5], device=dev) + torch.randn
 torch.cuda.synchronize()
 for it in range(iters):
     t0 = time.perf_counter()
-    boxes = ops.decode3d(anc, reg3)
-    out = postprocess.detect_per_class(cls, boxes, box_col=16, score_threshold=0.05)
+    out = postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05)
     torch.cuda.synchronize()
     print("iter", it, "wall ms", (time.perf_counter() - t0) * 1e3, "detections", out[0].numel(), flush=True)
