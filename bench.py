@@ -348,7 +348,8 @@ def run_ours(args):
     # ---- the same K steps as ONE CUDA graph launch per step (forward + backward, all kernels and the small torch ops):
     # removes the host-side launch gaps between the six short kernels.  Falls back to the eager figure if capture fails.
     ms_step, mode = ms_step_eager, "eager (one Python call per step)"
-    if not args.no_graph and world == 1:   # NCCL inside a capture: a failure on one rank only would deadlock the others
+    if not args.no_graph:
+        graph, ok = None, 1
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -358,8 +359,19 @@ def run_ours(args):
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: the NCCL watchdog thread's CUDA calls must not invalidate the capture (world > 1)
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 g_losses = step_device().detach()
+            torch.cuda.synchronize(dev)
+        except Exception as e:   # noqa: BLE001 - any capture problem: keep the eager number
+            ok, mode = 0, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:200]})"
+        if world > 1:   # every rank must take the same branch (the replays contain a collective)
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            if ok and int(flag.item()) == 0:
+                mode = "eager (graph capture failed on another rank)"
+            ok = int(flag.item())
+        if ok:
             for _ in range(args.warmup):
                 graph.replay()
             torch.cuda.synchronize(dev)
@@ -374,11 +386,14 @@ def run_ours(args):
             if world > 1:
                 torch.distributed.barrier()
             ms_graph = _max_over_ranks(g0.elapsed_time(g1), world, dev) / args.steps
-            same = torch.equal(g_losses, losses)
-            if same and ms_graph < ms_step:
+            same = torch.tensor([1 if torch.equal(g_losses, losses) else 0], dtype=torch.int32, device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(same, op=torch.distributed.ReduceOp.MIN)
+            if int(same.item()) and ms_graph < ms_step:
                 ms_step, mode = ms_graph, "CUDA graph replay (one launch per step)"
-        except Exception as e:   # noqa: BLE001 - any capture problem: keep the eager number
-            mode = f"eager (graph capture failed: {type(e).__name__}: {str(e)[:300]})"
+        if graph is not None:
+            graph.reset()
+            del graph
     clocks = sampler.stop() if rank == 0 else None
     ms_fwd = _event_ms([(e[0], e[1]) for e in evs]) / args.steps
     ms_bwd = _event_ms([(e[1], e[2]) for e in evs]) / args.steps
@@ -482,10 +497,15 @@ def run_ours(args):
                     line["other_workloads"] = other_workloads(dev, hbm_peak)
                 except Exception as e:  # the headline line must still be printed
                     line["other_workloads"] = {"error": f"{type(e).__name__}: {e}"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # A captured graph holds NCCL work; tearing the process group down with it alive can block.  Everything is
+        # measured and printed: synchronise, meet the other ranks once more, and leave without the teardown.
+        torch.cuda.synchronize(dev)
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
