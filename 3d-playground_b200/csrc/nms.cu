@@ -266,12 +266,121 @@ __global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __res
     if (tid == 0) keep_count[seg] = total_kept;
 }
 
+// ---- single long segment (the trackers' NMS calls: one set of 10^2..10^4 boxes): the serial chain of the one-CTA
+// greedy pass (n / 64 blocks x ~5 us) dominates, so the pair tests are spread over the whole GPU instead -
+// a 64x64-block suppression bit-matrix in L2 (upper triangle only) - and ONE warp then walks the blocks: a 64-step
+// shuffle scan on the diagonal words, then the kept rows' words are OR-ed into the running "removed" set (coalesced,
+// independent loads).  Same pair test, same order, same keep list as the greedy kernel.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox, int n, int nb, float thr,
+                                                      uint64_t* __restrict__ mask) {
+    const int rb = blockIdx.y, cb = blockIdx.x, tid = threadIdx.x;
+    if (cb < rb) return;
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    const bool thr_nonneg = thr >= 0.0f;
+    const int col = cb * 64 + tid;
+    if (col < n) {
+        const float4 b = sbox[col];
+        cbox[tid] = b;
+        carea[tid] = box_area_rn(b.x, b.y, b.z, b.w);
+    }
+    __syncthreads();
+    const int row = rb * 64 + tid;
+    if (row >= n) return;
+    const float4 me = sbox[row];
+    const float area = box_area_rn(me.x, me.y, me.z, me.w);
+    const int m = min(64, n - cb * 64);
+    uint64_t word = 0ull;
+    for (int j = 0; j < m; ++j)
+        if (cb * 64 + j > row && suppresses(me, area, cbox[j], carea[j], thr, thr_nonneg)) word |= 1ull << j;
+    mask[(int64_t)row * nb + cb] = word;
+}
+
+// WPL = 64-bit words of the "removed" set per lane (nb <= 32 * WPL)
+template <int WPL>
+__global__ void __launch_bounds__(32) nms_mask_scan_kernel(const uint64_t* __restrict__ mask,
+                                                           const int32_t* __restrict__ sidx, int n, int nb,
+                                                           int64_t* __restrict__ keep_out,
+                                                           int32_t* __restrict__ keep_count) {
+    const int lane = threadIdx.x;
+    uint64_t remv[WPL];
+#pragma unroll
+    for (int k = 0; k < WPL; ++k) remv[k] = 0ull;
+    int total = 0;
+    // diagonal words of block 0 (each later block's are requested one block ahead: they depend on nothing)
+    uint64_t dA = (lane < n) ? mask[(int64_t)lane * nb] : 0ull;
+    uint64_t dB = (lane + 32 < n) ? mask[(int64_t)(lane + 32) * nb] : 0ull;
+    int sA = (lane < n) ? sidx[lane] : 0, sB = (lane + 32 < n) ? sidx[lane + 32] : 0;   // original indices, same prefetch
+    for (int blk = 0; blk < nb; ++blk) {
+        const int base = blk << 6;
+        const int m = min(64, n - base);
+        const uint64_t mmask = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
+        const uint64_t cA = dA, cB = dB;
+        const int tA = sA, tB = sB;
+        if (blk + 1 < nb) {
+            const int ra = base + 64 + lane, rb2 = ra + 32;
+            dA = (ra < n) ? mask[(int64_t)ra * nb + blk + 1] : 0ull;
+            dB = (rb2 < n) ? mask[(int64_t)rb2 * nb + blk + 1] : 0ull;
+            sA = (ra < n) ? sidx[ra] : 0;
+            sB = (rb2 < n) ? sidx[rb2] : 0;
+        }
+        uint64_t mine = 0ull;
+#pragma unroll
+        for (int k = 0; k < WPL; ++k)
+            if (k == (blk >> 5)) mine = remv[k];
+        uint64_t rem = shfl64(mine, blk & 31);
+        if ((rem & mmask) == mmask) continue;          // whole block already suppressed
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const uint64_t d = shfl64(i < 32 ? cA : cB, i & 31);
+            if (!((rem >> i) & 1ull)) rem |= d;
+        }
+        const uint64_t keep = ~rem & mmask;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = lane + 32 * half;
+            if ((keep >> i) & 1ull) keep_out[total + __popcll(keep & ((1ull << i) - 1ull))] = half ? tB : tA;
+        }
+        total += __popcll(keep);
+        // the kept rows suppress later blocks: their words are independent loads - keep kBatch rows in flight
+        constexpr int kBatch = (WPL == 1) ? 16 : (WPL == 2 ? 8 : 4);
+        uint64_t bits = keep;
+        while (bits) {
+            uint64_t v[kBatch][WPL];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const bool have = bits != 0ull;
+                const int i = have ? __ffsll((long long)bits) - 1 : 0;
+                bits &= bits - 1;      // 0 stays 0
+                const uint64_t* rowp = mask + (int64_t)(base + i) * nb;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) {
+                    const int w = lane + 32 * k;
+                    v[u][k] = (have && w > blk && w < nb) ? __ldg(rowp + w) : 0ull;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u)
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) remv[k] |= v[u][k];
+        }
+    }
+    if (lane == 0) keep_count[0] = total;
+}
+
 struct NmsWorkspace {
     int32_t* sidx;
     float4* sbox;
     uint64_t* keys;
+    uint64_t* mask;      // [n][ceil(n/64)] suppression bit-matrix (single-segment path only)
+    int32_t* single;
     int64_t bytes;
 };
+// one segment of a few hundred to kSortCap boxes: bit-matrix + one-warp scan instead of the one-CTA greedy pass
+static bool use_mask_path(int64_t S, int64_t max_seg_len, int64_t N) {
+    return S == 1 && max_seg_len == N && N >= 256 && N <= kSortCap;
+}
+__global__ void single_segment_kernel(int32_t* seg, int n) { seg[0] = 0; seg[1] = n; }
 static NmsWorkspace carve_nms(void* base, int64_t N, int64_t S, int64_t max_seg_len) {
     NmsWorkspace w;
     char* p = (char*)base;
@@ -284,7 +393,13 @@ static NmsWorkspace carve_nms(void* base, int64_t N, int64_t S, int64_t max_seg_
         while (P < max_seg_len) P <<= 1;
         off += align_up(P * 8, 256);
     }
-    (void)S;
+    w.mask = nullptr;
+    if (use_mask_path(S, max_seg_len, N)) {
+        w.mask = (uint64_t*)(p + off);
+        off += align_up(max_seg_len * ceil_div(max_seg_len, 64) * 8, 256);
+    }
+    w.single = (int32_t*)(p + off);   // {0, N} for callers that pass seg_offsets == NULL with S == 1
+    off += 256;
     w.bytes = off;
     return w;
 }
@@ -306,7 +421,7 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
                 "bad size");
     G3D_REQUIRE(N < ((int64_t)1 << 31) && S < ((int64_t)1 << 31), "size out of range");
     if (S == 0) return G3D_OK;
-    G3D_REQUIRE(seg_offsets && keep_count, "null pointer");
+    G3D_REQUIRE(keep_count && (seg_offsets || S == 1), "null pointer (seg_offsets may be NULL only for S == 1: one segment [0, N))");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
     if (N == 0 || max_seg_len == 0) {
@@ -318,6 +433,11 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
     G3D_REQUIRE(((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
     NmsWorkspace w = carve_nms(workspace, N, S, max_seg_len);
     G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (see g3d_nms_workspace_bytes)");
+    if (!seg_offsets) {
+        single_segment_kernel<<<1, 1, 0, st>>>(w.single, (int)N);
+        G3D_LAUNCH_CHECK();
+        seg_offsets = w.single;
+    }
     if (max_seg_len > kSortCap && S != 1) {
         set_error("g3d_nms_segmented: segments longer than %d boxes are only supported for S == 1", kSortCap);
         return G3D_ERR_UNSUPPORTED;
@@ -368,6 +488,18 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
         }
         keys_gather_kernel<<<g256, 256, 0, st>>>(w.keys, n, boxes, box_stride, box_col, w.sidx, w.sbox);
         G3D_LAUNCH_CHECK();
+    }
+    if (use_mask_path(S, max_seg_len, N)) {
+        const int n = (int)N, nb = (int)ceil_div(N, 64);
+        nms_mask_kernel<<<dim3((unsigned)nb, (unsigned)nb), 64, 0, st>>>(w.sbox, n, nb, thr_f, w.mask);
+        G3D_LAUNCH_CHECK();
+        if (nb <= 32)       nms_mask_scan_kernel<1><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
+        else if (nb <= 64)  nms_mask_scan_kernel<2><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
+        else if (nb <= 128) nms_mask_scan_kernel<4><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
+        else                nms_mask_scan_kernel<8><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
+        G3D_LAUNCH_CHECK();
+        (void)relative;   // one segment starting at 0: relative and absolute indices coincide
+        return G3D_OK;
     }
     const int removed_words = (int)(2 * ceil_div(max_seg_len, 64));
     if (two_size || all_short) {

@@ -421,11 +421,11 @@ def nms_segmented(boxes, scores, seg_offsets, max_seg_len, iou_threshold, box_co
     dev = _need_cuda(boxes, scores, seg_offsets)
     bx = _prep(boxes, torch.float32)
     sc = _prep(scores, torch.float32)
-    so = _prep(seg_offsets, torch.int32)
+    so = _prep(seg_offsets, torch.int32) if seg_offsets is not None else None
     if bx.dim() != 2 or bx.shape[1] < box_col + 4 or sc.dim() != 1 or sc.shape[0] != bx.shape[0]:
         raise ValueError(f"expected boxes[N,>=4] and scores[N], got {tuple(bx.shape)} and {tuple(sc.shape)}")
     N, K = bx.shape
-    S = so.numel() - 1
+    S = so.numel() - 1 if so is not None else 1
     keep = torch.empty((N,), dtype=torch.int64, device=dev)
     keep_count = torch.empty((max(S, 0),), dtype=torch.int32, device=dev)
     L = _lib.lib()
@@ -447,8 +447,7 @@ def nms(boxes, scores, iou_threshold):
     N = boxes.shape[0]
     if N == 0:
         return torch.empty((0,), dtype=torch.int64, device=dev)
-    so = torch.tensor([0, N], dtype=torch.int32, device=dev)
-    keep, cnt = nms_segmented(boxes, scores, so, N, iou_threshold, 0, True)
+    keep, cnt = nms_segmented(boxes, scores, None, N, iou_threshold, 0, True)   # one segment [0, N)
     return keep[: int(cnt.item())]
 
 

@@ -234,7 +234,11 @@ int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_count, cons
  * IoU(i,j) > iou_threshold, IoU in FP32 as torchvision computes it, the comparison against the double threshold.
  * keep_out[N] int64: for segment s the kept indices (relative to the segment start when relative != 0, else global)
  * in descending score order, stored from position seg_offsets[s]; keep_count[S] int32.
- * seg_offsets is a DEVICE int32 array of S+1 entries; max_seg_len is a host upper bound of the longest segment.
+ * seg_offsets is a DEVICE int32 array of S+1 entries (NULL is allowed for S == 1: one segment [0, N)); max_seg_len is a
+ * host upper bound of the longest segment.
+ * Three execution shapes, one result: many short segments (S >= 64) run one 256-thread CTA per segment; a single
+ * segment of 256..16384 boxes (the trackers' calls) builds a 64x64-block suppression bit-matrix with the whole GPU and
+ * scans it with one warp; everything else runs the one-CTA-per-segment greedy pass.
  */
 int64_t g3d_nms_workspace_bytes(int64_t N, int64_t S, int64_t max_seg_len);
 int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t box_col, const float* scores, int64_t N,
