@@ -253,3 +253,27 @@ def test_sharded_loss_single_rank_equals_plain_loss_and_gradients():
     assert_close_rel(got.cpu(), want.detach().cpu(), 1e-6, "losses")
     assert_close_rel(c1.grad.cpu(), c0.grad.cpu(), 1e-6, "dcls")
     assert_close_rel(r1.grad.cpu(), r0.grad.cpu(), 1e-6, "dreg")
+
+
+def test_baseline_config_1_vs_oracle():
+    """BASELINE.json configs[0], the reference's own CPU-runnable case: B = 2 at 540x960 (A = 97 965), 20 GT boxes per
+    image - losses, assignment codes and gradients against the oracle at full size"""
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    g = synth.gen(0)
+    anc = synth.anchors(540, 960)
+    A = anc.shape[1]
+    assert A == 97965
+    ann = synth.gt_annotations_3d(2, 20, 540, 960, g)
+    cls, reg = synth.head_outputs(2, A, 8, 12, g)
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref = lo.focal_loss(c0, r0, anc, ann)
+    sum(l.sum() for l in ref[:-1]).backward()
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    out = li.FocalLoss()(c1, r1, anc.cuda(), ann.cuda())
+    sum(o.sum() for o in out).backward()
+    assert_close_rel(torch.cat(out).detach().cpu(), torch.cat(ref[:-1]).detach(), TOL, "losses")
+    assert_close_rel(c1.grad.cpu(), c0.grad, TOL, "dcls")
+    assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg")
+    fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc.cuda(), ann.cuda())
+    assert torch.equal(fwd["assign"].cpu(), _codes_from_oracle(ref[-1], ann, True)), "assignment codes must be exact"
