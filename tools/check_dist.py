@@ -11,7 +11,7 @@ from geom3d_b200 import dist as gdist, losses_impl
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
-B = 7                                   # uneven shards on purpose
+B = 2 * world + 3                       # uneven shards on purpose (every rank gets at least 2 images)
 g = synth.gen(5)
 anc = synth.anchors(200, 168).to(dev); A = anc.shape[1]
 ann = synth.gt_annotations_3d(B, 9, 200, 168, g, n_pad=1, empty_images=(1,), **synth.TINY).to(dev)
