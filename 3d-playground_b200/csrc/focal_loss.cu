@@ -560,7 +560,7 @@ __device__ __forceinline__ void fixed_split(float t, long long& hi, long long& l
 }
 
 template <int VARIANT, bool BWD>
-__global__ void __launch_bounds__(128) positives_kernel(const PosArgs p) {
+__device__ __forceinline__ void positives_body(const PosArgs& p) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int n = min(__ldg(p.npos + b), p.A);
     const float npos = (float)n;
@@ -607,6 +607,9 @@ __global__ void __launch_bounds__(128) positives_kernel(const PosArgs p) {
     }
 }
 
+template <int VARIANT, bool BWD>
+__global__ void __launch_bounds__(128) positives_kernel(const PosArgs p) { positives_body<VARIANT, BWD>(p); }
+
 // =====================================================================================================================
 // launch 3: the streaming classification pass (loss terms + gradient) - the dominant, HBM-bound kernel
 // =====================================================================================================================
@@ -647,13 +650,13 @@ __device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
     tc = warp_sum(tc);
     int last = 0;
     if (lane == 0) {
-        const double tn = (double)__ldg(p.npos + b);
+        const double tn = (double)__ldcg(p.npos + b);
         const double per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0 : 4.0;
         const long long* acc = p.acc + 4 * b;
         const double lo_unit = 1.0 / 4503599627370496.0, hi_unit = 1.0 / 1048576.0;
-        double tr = (double)acc[0] * hi_unit + (double)acc[1] * lo_unit;
-        double tv = (double)acc[2] * hi_unit + (double)acc[3] * lo_unit;
-        if (__ldg(p.nonfinite + b)) tr = tv = __longlong_as_double(0x7ff8000000000000LL);   // NaN
+        double tr = (double)__ldcg(acc + 0) * hi_unit + (double)__ldcg(acc + 1) * lo_unit;
+        double tv = (double)__ldcg(acc + 2) * hi_unit + (double)__ldcg(acc + 3) * lo_unit;
+        if (__ldcg(p.nonfinite + b)) tr = tv = __longlong_as_double(0x7ff8000000000000LL);   // NaN
         float4 o;
         o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
         o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
@@ -987,6 +990,21 @@ __global__ void __launch_bounds__(kTile, 5) focal_fused_kernel(const FusedArgs f
 template <int VARIANT>
 __global__ void __launch_bounds__(32) loss_finalize_kernel(const StreamArgs p) { finalize_image<VARIANT>(p, blockIdx.x); }
 
+// Fused path: the positives launch also does the reduction - the last CTA of an image (per-image ticket) finalises that
+// image, the last image the batch - so the forward is gt_prepare, focal_fused_kernel and this.
+template <int VARIANT>
+__global__ void __launch_bounds__(128) positives_finalize_kernel(const PosArgs q, const StreamArgs p) {
+    positives_body<VARIANT, false>(q);
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(p.counters + blockIdx.y, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) finalize_image<VARIANT>(p, blockIdx.y);
+}
+
 // =====================================================================================================================
 // backward, part 1: the classification gradient for upstream gradients other than the one launch 3 was told to expect
 // =====================================================================================================================
@@ -1223,14 +1241,13 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
         void* kargs[] = {(void*)&f};
         G3D_CUDA(cudaLaunchKernel(kern, dim3((unsigned)nctas), dim3(kTile), kargs, 0, st));
         if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));
-        if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D, false><<<positives_grid(B), 128, 0, st>>>(pp);
-        else                           positives_kernel<G3D_VARIANT_2D, false><<<positives_grid(B), 128, 0, st>>>(pp);
+        if (variant == G3D_VARIANT_3D) positives_finalize_kernel<G3D_VARIANT_3D><<<positives_grid(B), 128, 0, st>>>(pp, p);
+        else                           positives_finalize_kernel<G3D_VARIANT_2D><<<positives_grid(B), 128, 0, st>>>(pp, p);
         G3D_LAUNCH_CHECK();
-        if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
-        if (variant == G3D_VARIANT_3D) loss_finalize_kernel<G3D_VARIANT_3D><<<(unsigned)B, 32, 0, st>>>(p);
-        else                           loss_finalize_kernel<G3D_VARIANT_2D><<<(unsigned)B, 32, 0, st>>>(p);
-        G3D_LAUNCH_CHECK();
-        if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[3], st));
+        if (trace_events) {
+            G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[2], st));
+            G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[3], st));
+        }
         return G3D_OK;
     }
     // ---- separate launches (any class count; G3D_LOSS_FUSED=0)

@@ -455,7 +455,7 @@ def run_ours(args):
         fwd_bytes = stream_bytes + assign_bytes + ann_h.numel() * 4
         bwd_bytes = int(sum(p[3] for p in per_image_vals)) * (R_REG * 4 * 2 + 4 + 21 * 4)
         if fused:
-            knames = ("focal_fused_kernel", "positives_kernel", "loss_finalize_kernel")
+            knames = ("focal_fused_kernel", "positives_finalize_kernel", "-")
             dom, dom_bytes, dom_ms = "focal_fused_kernel", stream_bytes + assign_bytes, ms_assign
         else:
             knames = ("assign_codes_kernel", "positives_kernel", "focal_stream_kernel")
@@ -473,8 +473,8 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                     "ms_per_step": t_e2e * 1e3, "steps": e2e_steps},
-            # gt_prepare, assign_codes, positives (fwd), focal_stream, focal_cls_grad, positives (bwd) per step
-            "gpu_launches": 6 * args.steps,
+            # gt_prepare, focal_fused, positives_finalize, focal_cls_grad, positives (bwd) per step
+            "gpu_launches": (5 if fused else 6) * args.steps,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": _traffic(dom), "peak_source": peak_src,
                          "ms": {"forward": ms_fwd, "backward": ms_bwd, knames[0]: ms_assign, knames[1]: ms_pos,
