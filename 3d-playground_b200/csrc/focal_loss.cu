@@ -305,6 +305,9 @@ struct AssignCodesArgs {
 struct StageSmem {
     float4 box[kImgPerCta][kTile];
     int idx[kImgPerCta][kTile];
+    float4 an[kTile];          // the tile's anchors: any warp can process any 32-anchor slice
+    float4 wbb[kWarps];        // bounding box of each slice
+    int next_unit;             // dynamic (slice, image) work units of the item
     float red[8][kWarps];
     float tile[8];
     int tile_wf;
@@ -378,8 +381,11 @@ __device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem&
 #pragma unroll
             for (int k = 0; k < 8; ++k) sm.red[k][warp] = v[k];
             sm.wcount[0][warp] = wf ? 1 : 0;
+            sm.wbb[warp] = ws.bb;
         }
+        sm.an[tid] = an;
         if (tid < kImgPerCta) sm.total[tid] = 0;
+        if (tid == 0) sm.next_unit = 0;
         __syncthreads();
         if (warp == 0) {     // tile statistics: lane k < 8 reduces statistic k over the warps
             if (lane < 8) {
@@ -442,16 +448,30 @@ __device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem&
     }
     __syncthreads();
 
-    // ---- per image: IoU max / first argmax over the staged survivors that can still matter.  No barriers.
+    // ---- (slice of 32 anchors) x (image) work units, handed out dynamically: the candidate loops of the slices differ a
+    // lot in length, and a warp that is done early takes the next unit instead of waiting at the end of the item.
+    // No barriers; units are image-major so that the warps walk the same staged image together.
+    const int nunits = nimg * kWarps;
 #pragma unroll 1
-    for (int i = 0; i < nimg; ++i) {
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= nunits) break;
+        const int i = u / kWarps, slice = u - i * kWarps;
         const int b = b0 + i;
+        const int a = tile * kTile + slice * 32 + lane;
+        const bool valid = a < p.A;
+        const float4 an = sm.an[slice * 32 + lane];
+        const float area_a = box_area_rn(an.x, an.y, an.z, an.w);
+        GroupStats ws;
+        ws.bb = sm.wbb[slice];
         const int Gi = __ldg(p.gt_count + b);
         // The regression gradient is zero except on the few positive rows.  This kernel is issue-bound and leaves HBM
         // idle, so the 48 bytes / row of zeros are written from here (3 coalesced 16-byte stores per lane, drained in
         // the background) instead of costing the HBM-bound streaming kernel 41 % more traffic.
         if (p.dreg) {
-            const int wa0 = tile * kTile + warp * 32, nrows = min(32, p.A - wa0);
+            const int wa0 = tile * kTile + slice * 32, nrows = min(32, p.A - wa0);
             if (nrows > 0) {
                 if (p.R == 12) zero_rows<12>(p.dreg + ((int64_t)b * p.A + wa0) * 12, nrows, lane);
                 else           zero_rows<4>(p.dreg + ((int64_t)b * p.A + wa0) * 4, nrows, lane);
@@ -1166,10 +1186,12 @@ static void launch_stream(const StreamArgs& p, bool grad, dim3 grid, cudaStream_
 
 static dim3 positives_grid(int64_t B) { return dim3(64, (unsigned)B); }
 
-// G3D_LOSS_FUSED=0 in the environment selects the separate assignment / streaming launches (read per call: no state)
+// G3D_LOSS_FUSED=1 in the environment selects the experimental single persistent kernel for the assignment and the
+// streaming pass (read per call: no state).  Default: two plain launches - measured equal or slightly faster (both
+// kinds of work sit at ~60 % issue-slot utilisation, limited by latency, so sharing an SM buys nothing) and simpler.
 static bool fused_path_enabled() {
     const char* e = getenv("G3D_LOSS_FUSED");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
 }
 
 extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
@@ -1250,7 +1272,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
         }
         return G3D_OK;
     }
-    // ---- separate launches (any class count; G3D_LOSS_FUSED=0)
+    // ---- separate launches (the default)
     assign_codes_kernel<<<agrid, kTile, 0, st>>>(q);
     G3D_LAUNCH_CHECK();
     if (trace_events) G3D_CUDA(cudaEventRecord((cudaEvent_t)trace_events[1], st));

@@ -445,11 +445,11 @@ def run_ours(args):
     del cls_h, reg_h, cls_in, reg_in
 
     if rank == 0:
-        # algorithmic bytes of the forward launches.  Fused path (default, C == 8): ONE persistent kernel
-        # does the assignment (anchors + GT in, codes + zero-filled dreg out; issue-bound) and the streaming pass (cls +
-        # codes in, dcls out; HBM-bound) with both kinds of work item resident on every SM.  G3D_LOSS_FUSED=0: the two
-        # as separate launches.  backward (dcls already written): the positive rows only.
-        fused = os.environ.get("G3D_LOSS_FUSED", "1") != "0"
+        # algorithmic bytes of the forward launches: assign_codes_kernel (anchors + GT in, codes + the
+        # zero-filled dreg out; issue-bound), positives_kernel (negligible) and the HBM-bound focal_stream_kernel (cls +
+        # codes in, dcls out; the dominant kernel).  G3D_LOSS_FUSED=1: the experimental single persistent kernel for
+        # both.  backward (dcls already written): the positive rows only.
+        fused = os.environ.get("G3D_LOSS_FUSED", "0") == "1"
         stream_bytes = B * A * (C_CLS * 4 + 4 + C_CLS * 4)          # cls + codes in, dcls out
         assign_bytes = B * A * (4 + R_REG * 4) + A * 16             # codes + the zero-filled dreg out, anchors in
         fwd_bytes = stream_bytes + assign_bytes + ann_h.numel() * 4
