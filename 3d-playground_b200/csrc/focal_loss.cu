@@ -711,27 +711,24 @@ __device__ __forceinline__ void finalize_image(const StreamArgs& p, int b) {
     }
 }
 
-// Fix-up of one float4 (4 classes of row r) that belongs to a positive or ignored anchor.  Rare and divergent: compact
-// generic code (a real loop, full logf) instead of the straight-line negative path; arguments and result by value so
-// that nothing of the hot path is forced into local memory.
+// Fix-up of one float4 (4 classes of row r) of a POSITIVE anchor whose assigned class is element e of this float4: the
+// other three elements keep their negative-anchor terms, element e trades its target-0 term for the target-1 term.
+// Rare and divergent: out of line, full logf; arguments and result by value so that nothing of the hot path is forced
+// into local memory.
 struct QuadOut {
     float4 g;
     float acc;
 };
 template <bool GRAD>
-__device__ __noinline__ QuadOut special_quad(float4 v, int code_r, int pc_r, int c0, float s_cls) {
+__device__ __noinline__ QuadOut positive_fix(float4 v, int e, float s_cls, float acc, float4 g) {
+    const float pe = (e == 0) ? v.x : (e == 1) ? v.y : (e == 2) ? v.z : v.w;
     QuadOut o;
-    o.acc = 0.0f;
-    o.g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (code_r == G3D_ASSIGN_IGNORE) return o;
-    float gv[4];
-    const float pv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        o.acc += focal_term(pv[e], c0 + e == pc_r);
-        gv[e] = GRAD ? s_cls * focal_term_grad(pv[e], c0 + e == pc_r) : 0.0f;
+    o.acc = acc + (focal_term(pe, true) - focal_term(pe, false));
+    o.g = g;
+    if (GRAD) {
+        const float ge = s_cls * focal_term_grad(pe, true);
+        if (e == 0) o.g.x = ge; else if (e == 1) o.g.y = ge; else if (e == 2) o.g.z = ge; else o.g.w = ge;
     }
-    o.g = make_float4(gv[0], gv[1], gv[2], gv[3]);
     return o;
 }
 
@@ -774,12 +771,15 @@ __device__ __forceinline__ float process_chunk8(const StreamArgs& p, int b, int6
         const int r0 = lane >> 1, r1 = 16 + (lane >> 1), c0 = (lane & 1) * 4;
         const int code0 = __shfl_sync(0xffffffffu, c.code, r0), pc0 = __shfl_sync(0xffffffffu, pos_cls, r0);
         const int code1 = __shfl_sync(0xffffffffu, c.code, r1), pc1 = __shfl_sync(0xffffffffu, pos_cls, r1);
-        if (code0 != G3D_ASSIGN_NEGATIVE) {
-            const QuadOut o = special_quad<GRAD>(c.v0, code0, pc0, c0, s_cls);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (code0 == G3D_ASSIGN_IGNORE) { acc0 = 0.0f; g0 = zero4; }          // ignored anchor: no loss, no gradient
+        else if (code0 >= 0 && pc0 >= c0 && pc0 < c0 + 4) {
+            const QuadOut o = positive_fix<GRAD>(c.v0, pc0 - c0, s_cls, acc0, g0);
             acc0 = o.acc; g0 = o.g;
         }
-        if (code1 != G3D_ASSIGN_NEGATIVE) {
-            const QuadOut o = special_quad<GRAD>(c.v1, code1, pc1, c0, s_cls);
+        if (code1 == G3D_ASSIGN_IGNORE) { acc1 = 0.0f; g1 = zero4; }
+        else if (code1 >= 0 && pc1 >= c0 && pc1 < c0 + 4) {
+            const QuadOut o = positive_fix<GRAD>(c.v1, pc1 - c0, s_cls, acc1, g1);
             acc1 = o.acc; g1 = o.g;
         }
     }
