@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(128) positives_kernel(const PosArgs p) { posit
 // =====================================================================================================================
 // launch 3: the streaming classification pass (loss terms + gradient) - the dominant, HBM-bound kernel
 // =====================================================================================================================
-constexpr int kChunksPerWarp = 4;                            // 32-row chunks handled by one warp
+constexpr int kChunksPerWarp = 8;                            // 32-row chunks handled by one warp
 constexpr int kRowsPerCta = kWarps * 32 * kChunksPerWarp;    // 1024 (image, anchor) rows per CTA
 
 struct StreamArgs {
@@ -1243,8 +1243,8 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     if (C == 8 && fused_path_enabled()) {
         // ---- one persistent kernel for assignment + streaming pass, then the positives, then the reduction
         FusedArgs f;
-        p.cpw = 2 * kChunksPerWarp;                     // larger streaming items: half as many trips to the work queue
-        p.T = (int)ceil_div(A, 2 * kRowsPerCta);
+        p.cpw = kChunksPerWarp;
+        p.T = (int)ceil_div(A, kRowsPerCta);
         f.q = q; f.p = p;
         f.ctr = ws_fused(w, B);
         f.n_tiles_assign = (int)agrid.x;
