@@ -231,7 +231,26 @@ def other_workloads(dev, hbm_peak):
                         "the NMS chain is latency-bound (SURVEY.md §8d)",
                 "roofline": {"kernel": "decode3d_kernel", "bound": "hbm", "achieved": dec_bytes / (t_dec * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": dec_bytes / (t_dec * 1e-3) / 1e9 / hbm_peak}})
-    del cls, reg3
+    # CPU port of the reference on ONE of the 64 images (decode + scores > 0.05 + per-class nms + cat)
+    from oracle import decode_oracle, homography_oracle, nms_oracle, tracker_oracle
+    cls1, reg1, anc_h = cls[:1].cpu(), reg3[:1].cpu(), anc.cpu()
+    try:    # the reference calls torchvision.ops.nms (C++ CPU kernel); fall back to the oracle's restatement of it
+        from torchvision.ops import nms as cpu_nms
+        nms_name = "torchvision.ops.nms"
+    except Exception:   # noqa: BLE001
+        cpu_nms, nms_name = nms_oracle.nms, "oracle nms"
+    t0 = time.perf_counter()
+    dec1 = decode_oracle.decode3d(anc_h, reg1)[0]
+    for c in range(C_CLS):
+        m = cls1[0, :, c] > 0.05
+        if int(m.sum()):
+            kept = cpu_nms(dec1[m][:, 16:20].contiguous(), cls1[0, m, c], 0.5)
+            _ = dec1[m][kept]
+    t_cpu3 = time.perf_counter() - t0
+    out[-1]["cpu_baseline"] = {"value": 1.0 / t_cpu3, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"1 of the 64 images (oracle decode3d + scores>0.05 + per-class {nms_name} + gather, "
+                                         f"{t_cpu3:.2f} s)"}
+    del cls, reg3, cls1, reg1
     torch.cuda.empty_cache()
     # ---- config 4: homography, 10 M states x 18 cameras
     P, Hm = synth.camera_matrices(18)
@@ -258,7 +277,16 @@ def other_workloads(dev, hbm_peak):
                              "peak": hbm_peak, "unit": "GB/s", "frac": s2i_bytes / (t_s2i * 1e-3) / 1e9 / hbm_peak,
                              "im_to_state_frac": i2s_bytes / (t_i2s * 1e-3) / 1e9 / hbm_peak,
                              "all_cameras_frac": all_bytes / (t_all * 1e-3) / 1e9 / hbm_peak}})
-    del st, cam
+    # CPU port: 1 M of the 10 M states through the wrapper's state_to_im (per-object camera matrices)
+    n_cpu = 1_000_000
+    st_h, cam_h = st[:n_cpu].cpu(), cam[:n_cpu].cpu().long()
+    P_h = torch.from_numpy(P)[cam_h]
+    t0 = time.perf_counter()
+    homography_oracle.wrapper_state_to_im(st_h, P_h[:, 0], P_h[:, 1])
+    t_cpu4 = time.perf_counter() - t0
+    out[-1]["cpu_baseline"] = {"value": n_cpu / t_cpu4 / 1e6, "unit": "M states/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"1 M of the 10 M states (oracle wrapper_state_to_im, {t_cpu4:.2f} s)"}
+    del st, cam, st_h, cam_h, P_h
     torch.cuda.empty_cache()
     # ---- config 5: tracking frame, 2000 objects: association matrix + space NMS + image NMS
     s5, c5 = synth.vehicle_states(2000, g)
@@ -274,9 +302,18 @@ def other_workloads(dev, hbm_peak):
         k2 = tracker_geometry.im_nms(corners, sc5, 0.3)
         return cost, k1, k2
     t_frame = timed(frame, 10)
+    s5h, j5h, sc5h = s5.cpu(), j5.cpu(), sc5.cpu()
+    P5 = torch.from_numpy(P)[c5.cpu().long()]
+    t0 = time.perf_counter()
+    tracker_oracle.association_cost(s5h, j5h)
+    tracker_oracle.space_nms(s5h, sc5h, 0.1)
+    tracker_oracle.im_nms(homography_oracle.wrapper_state_to_im(s5h, P5[:, 0], P5[:, 1]), sc5h, 0.3)
+    t_cpu5 = time.perf_counter() - t0
     out.append({"workload": "config 5: 2000 objects: footprint association matrix (f64) + space NMS 0.1 + image NMS 0.3",
                 "metric": "tracking-frame geometry frames/s", "value": 1e3 / t_frame, "unit": "frames/s",
-                "ms": {"frame": t_frame}, "note": "launch/latency bound (SURVEY.md §8d); includes 2 host syncs for the NMS lengths"})
+                "ms": {"frame": t_frame}, "note": "launch/latency bound (SURVEY.md §8d); includes 2 host syncs for the NMS lengths",
+                "cpu_baseline": {"value": 1.0 / t_cpu5, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"one frame (oracle association_cost + space_nms + state_to_im + im_nms, {t_cpu5:.2f} s)"}})
     return out
 
 
