@@ -520,6 +520,12 @@ def run_ours(args):
                          "frac": achieved / hbm_peak, "traffic": _traffic(dom), "peak_source": peak_src,
                          "ms": {"forward": ms_fwd, "backward": ms_bwd, knames[0]: ms_assign, knames[1]: ms_pos,
                                 knames[2]: ms_stream},
+                         # SURVEY.md §8(d) "fused fwd+bwd": 160 B per (image, anchor) - cls + reg in, dcls + dreg out - plus
+                         # the anchors once: the whole step against the HBM roofline (this design never reads reg except
+                         # for the positives, so its own traffic is lower: see forward / backward below)
+                         "step_on_survey_bytes": {"bytes": B * A * 160 + A * 16,
+                                                  "GBps": (B * A * 160 + A * 16) / (ms_step * 1e-3) / 1e9,
+                                                  "frac": (B * A * 160 + A * 16) / (ms_step * 1e-3) / 1e9 / hbm_peak},
                          "forward": {"bytes": fwd_bytes, "GBps": fwd_bytes / (ms_fwd * 1e-3) / 1e9,
                                      "frac": fwd_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak},
                          "backward": {"bytes": bwd_bytes, "GBps": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
