@@ -1,0 +1,277 @@
+// kf.cu — SURVEY §8(f)-4: Torch_KF.predict / Torch_KF.update of util_track/kf.py (:292-336, :339-403), the batched
+// Kalman filter the trackers run between the geometry kernels.  The reference builds per-object copies of F / H / Q / R
+// with .repeat() and pushes them through bmm and a batched inverse on the CPU; here one thread owns one object and its
+// S x S covariance lives in registers (S = 6 states, M = 5 measurements in the trackers; up to 8 x 8 supported).
+// Arithmetic is FP32 like the reference's (FP64 where torch promotes: the innovation z + mu_R - H x, and the Q scaling
+// when dt is a per-object float64 tensor); sums run in index order with separately rounded products.
+#include "common.cuh"
+
+namespace g3d {
+
+constexpr int kKfMax = 8;
+
+struct KfModel {
+    float F[kKfMax * kKfMax];
+    float Q[kKfMax * kKfMax];
+    float H[kKfMax * kKfMax];
+    float R[kKfMax * kKfMax];
+    float mu_R[kKfMax];
+};
+
+// predict (kf.py:292-336): F_rep = F with F_rep[0,5] = D * dt;  X = F_rep X;  P = F_rep P F_rep^T + Q * dt / dt_default
+template <int S>
+__global__ void __launch_bounds__(128) kf_predict_kernel(float* __restrict__ X, float* __restrict__ P,
+                                                         const float* __restrict__ D, const double* __restrict__ dt_arr,
+                                                         double dt_scalar, double dt_default, double* __restrict__ T,
+                                                         int64_t n, int s_rt, const KfModel m) {
+    const int SS = (S > 0) ? S : s_rt;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double dt = dt_arr ? dt_arr[i] : dt_scalar;
+        float F[kKfMax][kKfMax], Pm[kKfMax][kKfMax], A[kKfMax][kKfMax], x[kKfMax], xn[kKfMax];
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) {
+                if (r < SS && c < SS) {
+                    F[r][c] = m.F[r * SS + c];
+                    Pm[r][c] = P[(i * SS + r) * SS + c];
+                }
+            }
+        if (SS > 5) F[0][5] = (float)((double)D[i] * dt);            // kf.py:315 (hard-wired position / speed slots)
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) if (r < SS) x[r] = X[i * SS + r];
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) {
+            if (r >= SS) continue;
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(F[r][k], x[k]));
+            xn[r] = acc;
+        }
+        // A = F P
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) {
+                if (r >= SS || c >= SS) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(F[r][k], Pm[k][c]));
+                A[r][c] = acc;
+            }
+        // P = A F^T + Q * dt / dt_default
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) {
+                if (r >= SS || c >= SS) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(A[r][k], F[c][k]));
+                float out;
+                if (dt_arr) {   // float * double tensor / python float: the scaling and the sum in double, then .float()
+                    const double q = (double)m.Q[r * SS + c] * dt / dt_default;
+                    out = (float)((double)acc + q);
+                } else {        // float tensor * python scalar: FP32 with the scalar rounded to FP32
+                    const float q = __fdiv_rn(__fmul_rn(m.Q[r * SS + c], (float)dt), (float)dt_default);
+                    out = __fadd_rn(acc, q);
+                }
+                P[(i * SS + r) * SS + c] = out;
+            }
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) if (r < SS) X[i * SS + r] = xn[r];
+        if (T) T[i] += dt;
+    }
+}
+
+// update (kf.py:339-403) of the objects rows[j]:  y = z + mu_R - H x;  S = H P H^T + R;  K = P H^T S^-1;
+// x += K y;  P = (I - K H) P
+template <int S, int M>
+__global__ void __launch_bounds__(128) kf_update_kernel(float* __restrict__ X, float* __restrict__ P,
+                                                        const int64_t* __restrict__ rows, const double* __restrict__ z,
+                                                        int64_t mcount, int s_rt, int m_rt, const KfModel mdl) {
+    const int SS = (S > 0) ? S : s_rt, MM = (M > 0) ? M : m_rt;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < mcount; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = rows[j];
+        float Pm[kKfMax][kKfMax], x[kKfMax], HP[kKfMax][kKfMax], Sm[kKfMax][kKfMax], Si[kKfMax][kKfMax];
+        float PHt[kKfMax][kKfMax], K[kKfMax][kKfMax], y[kKfMax];
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) {
+            if (r < SS) x[r] = X[i * SS + r];
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c)
+                if (r < SS && c < SS) Pm[r][c] = P[(i * SS + r) * SS + c];
+        }
+        // innovation: double(z) + mu_R - float(x H^T), then .float()
+#pragma unroll
+        for (int a = 0; a < kKfMax; ++a) {
+            if (a >= MM) continue;
+            float hx = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kKfMax; ++k) if (k < SS) hx = __fadd_rn(hx, __fmul_rn(x[k], mdl.H[a * SS + k]));
+            y[a] = (float)(z[j * MM + a] + (double)mdl.mu_R[a] - (double)hx);
+        }
+        // HP = H P  [M,S];  S = HP H^T + R  [M,M]
+#pragma unroll
+        for (int a = 0; a < kKfMax; ++a)
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) {
+                if (a >= MM || c >= SS) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(mdl.H[a * SS + k], Pm[k][c]));
+                HP[a][c] = acc;
+            }
+#pragma unroll
+        for (int a = 0; a < kKfMax; ++a)
+#pragma unroll
+            for (int b = 0; b < kKfMax; ++b) {
+                if (a >= MM || b >= MM) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(HP[a][k], mdl.H[b * SS + k]));
+                Sm[a][b] = __fadd_rn(acc, mdl.R[a * MM + b]);
+            }
+        // S^-1: Gauss-Jordan with partial pivoting (torch: LU with partial pivoting; both backward stable)
+#pragma unroll
+        for (int a = 0; a < kKfMax; ++a)
+#pragma unroll
+            for (int b = 0; b < kKfMax; ++b) Si[a][b] = (a == b) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int col = 0; col < kKfMax; ++col) {
+            if (col >= MM) continue;
+            int piv = col;
+            float best = fabsf(Sm[col][col]);
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r)
+                if (r > col && r < MM && fabsf(Sm[r][col]) > best) { best = fabsf(Sm[r][col]); piv = r; }
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r) {
+                if (r != piv || r == col) continue;
+#pragma unroll
+                for (int c = 0; c < kKfMax; ++c) {
+                    const float t = Sm[col][c]; Sm[col][c] = Sm[r][c]; Sm[r][c] = t;
+                    const float u = Si[col][c]; Si[col][c] = Si[r][c]; Si[r][c] = u;
+                }
+            }
+            const float inv = 1.0f / Sm[col][col];
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) { Sm[col][c] *= inv; Si[col][c] *= inv; }
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r) {
+                if (r == col || r >= MM) continue;
+                const float f = Sm[r][col];
+#pragma unroll
+                for (int c = 0; c < kKfMax; ++c) {
+                    Sm[r][c] = fmaf(-f, Sm[col][c], Sm[r][c]);
+                    Si[r][c] = fmaf(-f, Si[col][c], Si[r][c]);
+                }
+            }
+        }
+        // PHt = P H^T [S,M];  K = PHt S^-1 [S,M]
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+            for (int a = 0; a < kKfMax; ++a) {
+                if (r >= SS || a >= MM) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(Pm[r][k], mdl.H[a * SS + k]));
+                PHt[r][a] = acc;
+            }
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+            for (int a = 0; a < kKfMax; ++a) {
+                if (r >= SS || a >= MM) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(PHt[r][k], Si[k][a]));
+                K[r][a] = acc;
+            }
+        // x += K y
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) {
+            if (r >= SS) continue;
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[r][k], y[k]));
+            X[i * SS + r] = __fadd_rn(x[r], acc);
+        }
+        // P = (I - K H) P
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) {
+            if (r >= SS) continue;
+            float IKH[kKfMax];
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) {
+                if (c >= SS) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[r][k], mdl.H[k * SS + c]));
+                IKH[c] = __fsub_rn((r == c) ? 1.0f : 0.0f, acc);
+            }
+#pragma unroll
+            for (int c = 0; c < kKfMax; ++c) {
+                if (c >= SS) continue;
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(IKH[k], Pm[k][c]));
+                P[(i * SS + r) * SS + c] = acc;
+            }
+        }
+    }
+}
+
+static int fill_model(KfModel& m, const float* F, const float* Q, const float* H, const float* R, const float* mu_R, int S,
+                      int M) {
+    for (int i = 0; i < kKfMax * kKfMax; ++i) m.F[i] = m.Q[i] = m.H[i] = m.R[i] = 0.0f;
+    for (int i = 0; i < kKfMax; ++i) m.mu_R[i] = 0.0f;
+    if (F) for (int i = 0; i < S * S; ++i) m.F[i] = F[i];
+    if (Q) for (int i = 0; i < S * S; ++i) m.Q[i] = Q[i];
+    if (H) for (int i = 0; i < M * S; ++i) m.H[i] = H[i];
+    if (R) for (int i = 0; i < M * M; ++i) m.R[i] = R[i];
+    if (mu_R) for (int i = 0; i < M; ++i) m.mu_R[i] = mu_R[i];
+    return 0;
+}
+
+}  // namespace g3d
+
+using namespace g3d;
+
+extern "C" int g3d_kf_predict(float* X, float* P, const float* D, const double* dt_per_object, double dt_scalar,
+                              double dt_default, double* T, int64_t n, int64_t S, const float* F_host,
+                              const float* Q_host, int device, void* stream) {
+    G3D_REQUIRE(n >= 0 && S >= 1 && S <= kKfMax, "state size must be 1..8");
+    if (n == 0) return G3D_OK;
+    G3D_REQUIRE(X && P && F_host && Q_host, "null pointer");
+    G3D_REQUIRE(S <= 5 || D, "direction vector needed (F[0,5] = D * dt)");
+    G3D_GUARD(device);
+    KfModel m;
+    fill_model(m, F_host, Q_host, nullptr, nullptr, nullptr, (int)S, 0);
+    const int grid = (int)(ceil_div(n, 128) < 148 * 8 ? ceil_div(n, 128) : 148 * 8);
+    if (S == 6)
+        kf_predict_kernel<6><<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, D, dt_per_object, dt_scalar, dt_default, T, n, 6, m);
+    else
+        kf_predict_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, D, dt_per_object, dt_scalar, dt_default, T, n,
+                                                                   (int)S, m);
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}
+
+extern "C" int g3d_kf_update(float* X, float* P, const int64_t* rows, const double* z, int64_t m_count, int64_t S, int64_t M,
+                             const float* H_host, const float* R_host, const float* mu_R_host, int device, void* stream) {
+    G3D_REQUIRE(m_count >= 0 && S >= 1 && S <= kKfMax && M >= 1 && M <= kKfMax, "state / measurement size must be 1..8");
+    if (m_count == 0) return G3D_OK;
+    G3D_REQUIRE(X && P && rows && z && H_host && R_host, "null pointer");
+    G3D_GUARD(device);
+    KfModel m;
+    fill_model(m, nullptr, nullptr, H_host, R_host, mu_R_host, (int)S, (int)M);
+    const int grid = (int)(ceil_div(m_count, 128) < 148 * 8 ? ceil_div(m_count, 128) : 148 * 8);
+    if (S == 6 && M == 5)
+        kf_update_kernel<6, 5><<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, rows, z, m_count, 6, 5, m);
+    else
+        kf_update_kernel<0, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, rows, z, m_count, (int)S, (int)M, m);
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}

@@ -636,3 +636,55 @@ def md_iou(a, b):
     out = torch.empty(a.shape[:-1], dtype=torch.float64, device=dev)
     check(_lib.lib().g3d_md_iou(_p(a64), _p(b64), out.numel(), _p(out), _idx(dev), _stream(dev)), "g3d_md_iou")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ §8(f)-4: Kalman filter
+def _host_f32(t, n):
+    a = np.ascontiguousarray(np.asarray(t.detach().cpu() if isinstance(t, torch.Tensor) else t, dtype=np.float32).reshape(-1))
+    if a.size != n:
+        raise ValueError(f"expected {n} coefficients, got {a.size}")
+    return a
+
+
+def kf_predict_(X, P, D, dt, F, Q, dt_default, T=None):
+    """Torch_KF.predict in place (util_track/kf.py:292-336).  X f32[n,S], P f32[n,S,S], D f32[n] (direction), T f64[n]|None
+    (device, contiguous); dt: python float or a float64 device tensor [n]; F, Q: [S,S] (any tensor / array, read on the host)."""
+    dev = _need_cuda(X, P, D, T)
+    if X.dtype != torch.float32 or P.dtype != torch.float32 or not X.is_contiguous() or not P.is_contiguous():
+        raise Geom3dError("kf_predict_ works in place: X and P must be contiguous float32")
+    n, S = X.shape
+    Fh, Qh = _host_f32(F, S * S), _host_f32(Q, S * S)
+    Dd = _prep(D, torch.float32) if D is not None else None
+    if isinstance(dt, torch.Tensor):
+        dtd, dts = _prep(dt.to(dev), torch.float64), 0.0
+        if dtd.numel() != n:
+            raise ValueError("dt tensor must have one entry per object")
+    else:
+        dtd, dts = None, float(dt)
+    if T is not None and (T.dtype != torch.float64 or not T.is_contiguous()):
+        raise Geom3dError("T must be a contiguous float64 tensor")
+    check(_lib.lib().g3d_kf_predict(_p(X), _p(P), _p(Dd), _p(dtd), dts, float(dt_default), _p(T), n, S,
+                                    Fh.ctypes.data_as(ctypes.c_void_p), Qh.ctypes.data_as(ctypes.c_void_p), _idx(dev),
+                                    _stream(dev)), "g3d_kf_predict")
+    return X, P
+
+
+def kf_update_(X, P, rows, z, H, R, mu_R=None):
+    """Torch_KF.update in place (util_track/kf.py:339-403) for the objects `rows` (int64 device tensor, distinct) with
+    measurements z[m,M] (promoted to float64 like the reference)."""
+    dev = _need_cuda(X, P, rows, z)
+    if X.dtype != torch.float32 or P.dtype != torch.float32 or not X.is_contiguous() or not P.is_contiguous():
+        raise Geom3dError("kf_update_ works in place: X and P must be contiguous float32")
+    n, S = X.shape
+    zz = _prep(z, torch.float64)
+    m, M = zz.shape
+    rr = _prep(rows, torch.int64)
+    if rr.numel() != m:
+        raise ValueError("one row index per measurement")
+    Hh, Rh = _host_f32(H, M * S), _host_f32(R, M * M)
+    muh = _host_f32(mu_R, M) if mu_R is not None else None
+    check(_lib.lib().g3d_kf_update(_p(X), _p(P), _p(rr), _p(zz), m, S, M, Hh.ctypes.data_as(ctypes.c_void_p),
+                                   Rh.ctypes.data_as(ctypes.c_void_p),
+                                   muh.ctypes.data_as(ctypes.c_void_p) if muh is not None else None, _idx(dev),
+                                   _stream(dev)), "g3d_kf_update")
+    return X, P

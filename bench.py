@@ -318,6 +318,39 @@ def other_workloads(dev, hbm_peak):
                 "ms": {"frame": t_frame}, "note": "launch/latency bound (SURVEY.md §8d); includes 2 host syncs for the NMS lengths",
                 "cpu_baseline": {"value": 1.0 / t_cpu5, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                  "sample": f"one frame (oracle association_cost + space_nms + state_to_im + im_nms, {t_cpu5:.2f} s)"}})
+    # ---- batched Kalman filter (Torch_KF.predict with per-object dt + update of every object)
+    nk, Sk, Mk = 1_000_000, 6, 5
+    Fk = torch.eye(Sk)
+    Hk = torch.zeros(Mk, Sk); Hk[:Mk, :Mk] = torch.eye(Mk)
+    Qk, Rk = torch.eye(Sk) * 0.5, torch.eye(Mk) * 0.8
+    Xk = torch.randn(nk, Sk, device=dev) * 20
+    Ck = torch.randn(nk, Sk, Sk, device=dev)
+    Pk = (Ck @ Ck.transpose(1, 2) + torch.eye(Sk, device=dev) * 3.0).contiguous()
+    del Ck
+    Dk = torch.ones(nk, device=dev)
+    Tk = torch.zeros(nk, dtype=torch.float64, device=dev)
+    dtk = torch.full((nk,), 1 / 30.0, dtype=torch.float64, device=dev)
+    rowsk = torch.arange(nk, device=dev)
+    zk = torch.randn(nk, Mk, dtype=torch.float64, device=dev) * 20
+    t_pred = timed(lambda: ops.kf_predict_(Xk, Pk, Dk, dtk, Fk, Qk, 1 / 30.0, Tk), 5)
+    t_upd = timed(lambda: ops.kf_update_(Xk, Pk, rowsk, zk, Hk, Rk, None), 5)
+    pred_bytes = nk * (2 * (Sk + Sk * Sk) * 4 + 4 + 8 + 16)         # X, P in and out, D, dt, T in and out
+    upd_bytes = nk * (2 * (Sk + Sk * Sk) * 4 + 8 + Mk * 8)          # X, P in and out, row index, measurement
+    from oracle import kf_oracle
+    n_cpu = 100_000
+    Xc, Pc, Dc, dtc = Xk[:n_cpu].cpu(), Pk[:n_cpu].cpu(), Dk[:n_cpu].cpu(), dtk[:n_cpu].cpu()
+    t0 = time.perf_counter()
+    Xc, Pc = kf_oracle.predict(Xc, Pc, Dc, dtc, Fk, Qk)
+    kf_oracle.update(Xc, Pc, torch.arange(n_cpu), zk[:n_cpu].cpu(), Hk, Rk, torch.zeros(Mk))
+    t_cpuk = time.perf_counter() - t0
+    out.append({"workload": "SURVEY 8(f)-4: Torch_KF predict (per-object dt) + update, 1M objects, 6 states / 5 measurements",
+                "metric": "Kalman predict+update M objects/s", "value": nk / ((t_pred + t_upd) * 1e-3) / 1e6,
+                "unit": "M objects/s", "ms": {"predict": t_pred, "update": t_upd},
+                "roofline": {"kernel": "kf_predict_kernel", "bound": "hbm", "achieved": pred_bytes / (t_pred * 1e-3) / 1e9,
+                             "peak": hbm_peak, "unit": "GB/s", "frac": pred_bytes / (t_pred * 1e-3) / 1e9 / hbm_peak,
+                             "update_frac": upd_bytes / (t_upd * 1e-3) / 1e9 / hbm_peak},
+                "cpu_baseline": {"value": n_cpu / t_cpuk / 1e6, "unit": "M objects/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"100 k of the 1 M objects (oracle predict + update, torch CPU bmm / inverse, {t_cpuk:.2f} s)"}})
     return out
 
 

@@ -322,6 +322,24 @@ int g3d_pairwise_iou_f64(const float* first, int64_t n, const float* second, int
 /* a20 literal form: a[n,4], b[n,4] float64 element-wise -> out[n] (the reference signature with pre-broadcast inputs) */
 int g3d_md_iou(const double* a, const double* b, int64_t n, double* out, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SURVEY §8(f)-4  Torch_KF.predict / Torch_KF.update        util_track/kf.py:292-336, :339-403
+ * The batched Kalman filter of the trackers: X[n,S] float32 states, P[n,S,S] float32 covariances (S <= 8; the trackers
+ * use S = 6, M = 5).  One thread per object, everything in registers, same FP32 / FP64 split as the reference.
+ *
+ * g3d_kf_predict: F_rep = F with F_rep[0,5] = D[i] * dt (S > 5);  X = F_rep X;  P = F_rep P F_rep^T + Q * dt / dt_default.
+ *   dt: one host scalar (dt_per_object == NULL; FP32 scaling of Q as torch does for a python float) or a device
+ *   float64 array [n] (the `dts = filter.get_dt(...)` form; the scaling and the sum in FP64, then rounded to FP32).
+ *   T[n] (nullable, float64) += dt.   F_host[S*S], Q_host[S*S]: host arrays.
+ * g3d_kf_update: for the objects rows[j] (int64 indices into X / P, distinct) with measurements z[m,M] float64:
+ *   y = z + mu_R - H x;  S = H P H^T + R;  K = P H^T S^-1;  x += K y;  P = (I - K H) P.
+ *   H_host[M*S], R_host[M*M], mu_R_host[M] (nullable = 0): host arrays.
+ */
+int g3d_kf_predict(float* X, float* P, const float* D, const double* dt_per_object, double dt_scalar, double dt_default,
+                   double* T, int64_t n, int64_t S, const float* F_host, const float* Q_host, int device, void* stream);
+int g3d_kf_update(float* X, float* P, const int64_t* rows, const double* z, int64_t m_count, int64_t S, int64_t M,
+                  const float* H_host, const float* R_host, const float* mu_R_host, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,53 @@ def golden_tracker():
          im_nms_groups=T.im_nms(me, corners, scores, threshold=0.3, groups=torch.zeros(120)))
 
 
+def kf_inputs(seed=71, n=40, m=25):
+    """seeded Kalman-filter scenario shared with the tests (the model matrices mimic a fitted kf_params INIT dict)"""
+    g = synth.gen(seed)
+    S, M = 6, 5
+    F = torch.eye(S)
+    H = torch.zeros(M, S); H[:M, :M] = torch.eye(M)
+    A = torch.randn(S, S, generator=g) * 0.3
+    Q = A @ A.t() + torch.eye(S) * 0.5
+    Bm = torch.randn(M, M, generator=g) * 0.2
+    R = Bm @ Bm.t() + torch.eye(M) * 0.8
+    Cm = torch.randn(S, S, generator=g)
+    P0 = Cm @ Cm.t() + torch.eye(S) * 5.0
+    init = {"P": P0, "F": F, "H": H, "Q": Q, "R": R, "mu_Q": torch.zeros(S), "mu_R": torch.randn(M, generator=g) * 0.1,
+            "mu_v": torch.tensor([75.0])}
+    st, _ = synth.vehicle_states(n, g)
+    det = st[:, :5].clone()
+    directions = st[:, 5].clone()
+    times = torch.rand(n, generator=g).double() * 0.2
+    dts = (torch.rand(n, generator=g).double() * 0.1 + 0.01)
+    rows = torch.randperm(n, generator=g)[:m]
+    z = det[rows] + torch.randn(m, M, generator=g) * 0.5
+    return init, det, directions, times, dts, rows, z
+
+
+def golden_kf():
+    sys.path.insert(0, REF)
+    from util_track.kf import Torch_KF
+    sys.path.pop(0)
+    init, det, directions, times, dts, rows, z = kf_inputs()
+    kf = Torch_KF(torch.device("cpu"), INIT=init, ADD_MEAN_R=True)
+    ids = list(range(100, 100 + len(det)))
+    kf.add(det, ids, directions, times, init_speed=True)
+    out = {"X0": kf.X.clone(), "P0": kf.P.clone(), "T0": kf.T.clone()}
+    kf.predict()                                   # default dt, python float
+    out.update(X1=kf.X.clone(), P1=kf.P.clone(), T1=kf.T.clone())
+    kf.predict(dt=dts)                             # per-object float64 dt
+    out.update(X2=kf.X.clone(), P2=kf.P.clone(), T2=kf.T.clone())
+    kf.update(z, [ids[int(r)] for r in rows])
+    out.update(X3=kf.X.clone(), P3=kf.P.clone())
+    _, view = kf.view(dt=dts, with_direction=True)
+    out.update(view=view)
+    kf.remove([ids[3], ids[17]])
+    kf.predict(dt=0.05)
+    out.update(X4=kf.X.clone(), P4=kf.P.clone())
+    save("kf", **out)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs the reference checkout at /root/reference")
@@ -335,3 +382,4 @@ if __name__ == "__main__":
     golden_postprocess()
     golden_homography()
     golden_tracker()
+    golden_kf()

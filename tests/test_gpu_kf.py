@@ -1,0 +1,91 @@
+"""GPU parity of the Kalman-filter drop-in: Torch_KF on the CUDA kernels against the unmodified
+reference's golden vectors and against the oracle on larger seeded inputs.  Bar: 1e-5 relative (FP32 matrices; entries
+far below a matrix's typical magnitude are judged against that magnitude)."""
+import importlib.util
+import os
+
+import pytest
+import torch
+
+import synth
+from conftest import GOLDEN, assert_close_rel, load_golden
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _kf_inputs():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg.kf_inputs()
+
+
+def test_torch_kf_dropin_golden_scenario():
+    from geom3d_b200.kf_impl import Torch_KF
+    init, det, directions, times, dts, rows, z = _kf_inputs()
+    gd = load_golden("kf")
+    kf = Torch_KF(torch.device("cuda"), INIT=init, ADD_MEAN_R=True)
+    ids = list(range(100, 100 + len(det)))
+    kf.add(det, ids, directions, times, init_speed=True)
+    assert torch.equal(kf.X.cpu(), gd["X0"]) and torch.equal(kf.P.cpu(), gd["P0"]) and torch.equal(kf.T.cpu(), gd["T0"])
+    kf.predict()
+    assert_close_rel(kf.X.cpu(), gd["X1"], TOL, "X after predict()")
+    assert_close_rel(kf.P.cpu(), gd["P1"], TOL, "P after predict()")
+    assert torch.allclose(kf.T.cpu(), gd["T1"], rtol=1e-12)
+    kf.predict(dt=dts)
+    assert_close_rel(kf.X.cpu(), gd["X2"], TOL, "X after predict(dts)")
+    assert_close_rel(kf.P.cpu(), gd["P2"], TOL, "P after predict(dts)")
+    assert torch.allclose(kf.T.cpu(), gd["T2"], rtol=1e-12)
+    kf.update(z, [ids[int(r)] for r in rows])
+    assert_close_rel(kf.X.cpu(), gd["X3"], TOL, "X after update")
+    assert_close_rel(kf.P.cpu(), gd["P3"], 5 * TOL, "P after update")      # (I - KH)P cancels: a few ulp of the 1e1 entries
+    id_list, view = kf.view(dt=dts, with_direction=True)
+    assert id_list == ids and view.shape == (len(det), 7)
+    assert_close_rel(view.cpu(), gd["view"], TOL, "view")
+    kf.remove([ids[3], ids[17]])
+    kf.predict(dt=0.05)
+    assert len(kf.obj_idxs) == len(det) - 2 and kf.obj_idxs[ids[4]] == 3
+    assert_close_rel(kf.X.cpu(), gd["X4"], TOL, "X after remove + predict")
+    assert_close_rel(kf.P.cpu(), gd["P4"], 5 * TOL, "P after remove + predict")
+
+
+@pytest.mark.parametrize("S,M", [(6, 5), (4, 2), (7, 7)])
+def test_kf_kernels_vs_oracle(S, M):
+    """5000 objects, both dt forms; the generic-size path for (4,2) and (7,7)"""
+    from geom3d_b200 import ops
+    from oracle import kf_oracle as ko
+    g = synth.gen(100 + S)
+    n, m = 5000, 3000
+    F = torch.eye(S) + torch.randn(S, S, generator=g) * 0.01
+    A = torch.randn(S, S, generator=g) * 0.3
+    Q = A @ A.t() + torch.eye(S) * 0.5
+    H = torch.zeros(M, S); H[:M, :M] = torch.eye(M)
+    Bm = torch.randn(M, M, generator=g) * 0.2
+    R = Bm @ Bm.t() + torch.eye(M) * 0.8
+    mu_R = torch.randn(M, generator=g) * 0.1
+    Cm = torch.randn(n, S, S, generator=g)
+    P = (Cm @ Cm.transpose(1, 2) + torch.eye(S) * 3.0).float()
+    X = torch.randn(n, S, generator=g) * 20
+    D = torch.where(torch.rand(n, generator=g) < 0.5, -torch.ones(n), torch.ones(n))
+    dts = torch.rand(n, generator=g).double() * 0.1
+    rows = torch.randperm(n, generator=g)[:m]
+    z = torch.randn(m, M, generator=g) * 20
+
+    def ref_predict(X, P, dt):
+        if S > 5:
+            return ko.predict(X, P, D, dt, F, Q)
+        Frep = F.unsqueeze(0).repeat(n, 1, 1)
+        sc = (dt.unsqueeze(1).unsqueeze(2) if isinstance(dt, torch.Tensor) else dt)
+        return torch.bmm(Frep, X.unsqueeze(2)).squeeze(2), (torch.bmm(torch.bmm(Frep, P), Frep.transpose(1, 2)) + Q * sc / (1 / 30.0)).float()
+    Xd, Pd = X.cuda(), P.cuda()
+    Xr, Pr = X, P
+    for dt in (1 / 30.0, dts):
+        ops.kf_predict_(Xd, Pd, D.cuda(), dt if not isinstance(dt, torch.Tensor) else dt.cuda(), F, Q, 1 / 30.0)
+        Xr, Pr = ref_predict(Xr, Pr, dt)
+        assert_close_rel(Xd.cpu(), Xr, TOL, "X predict")
+        assert_close_rel(Pd.cpu(), Pr, TOL, "P predict")
+    ops.kf_update_(Xd, Pd, rows.cuda(), z.cuda(), H, R, mu_R)
+    Xr, Pr = ko.update(Xr, Pr, rows, z, H, R, mu_R)
+    assert_close_rel(Xd.cpu(), Xr, TOL, "X update")
+    assert_close_rel(Pd.cpu(), Pr, 5 * TOL, "P update")

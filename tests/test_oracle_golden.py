@@ -6,7 +6,9 @@ import pytest
 import torch
 
 import synth
-from conftest import assert_close_rel
+import os
+
+from conftest import GOLDEN, assert_close_rel, load_golden
 from oracle import decode_oracle, homography_oracle as ho, losses_oracle as lo, nms_oracle, tracker_oracle
 
 
@@ -164,3 +166,26 @@ def test_tracker(golden):
     assert torch.equal(tracker_oracle.space_nms(st, sc, 0.4), gd["space_nms_0_4"])
     assert torch.equal(tracker_oracle.im_nms(gd["corners"], sc, 0.3), gd["im_nms_0_3"])
     assert torch.equal(tracker_oracle.im_nms(gd["corners"], sc, 0.3, groups=torch.zeros(120)), gd["im_nms_groups"])
+
+
+def test_kf_oracle_matches_reference_golden():
+    """oracle/kf_oracle.py against the UNMODIFIED Torch_KF (tests/golden/kf.npz): default-dt predict, per-object float64 dt
+    predict, update, view"""
+    import importlib.util
+    from oracle import kf_oracle as ko
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    init, det, directions, times, dts, rows, z = mg.kf_inputs()
+    gd = load_golden("kf")
+    F, Q, H, R, mu_R = init["F"].float(), init["Q"].float(), init["H"].float(), init["R"].float(), init["mu_R"].float()
+    X, P = gd["X0"], gd["P0"]
+    X, P = ko.predict(X, P, directions, 1 / 30.0, F, Q)
+    assert torch.allclose(X, gd["X1"], rtol=1e-6, atol=0) and torch.allclose(P, gd["P1"], rtol=1e-6, atol=1e-6)
+    X, P = ko.predict(X, P, directions, dts, F, Q)
+    assert torch.allclose(X, gd["X2"], rtol=1e-6, atol=0) and torch.allclose(P, gd["P2"], rtol=1e-6, atol=1e-6)
+    X3, P3 = ko.update(X, P, rows, z, H, R, mu_R)
+    assert torch.allclose(X3, gd["X3"], rtol=1e-6, atol=1e-6) and torch.allclose(P3, gd["P3"], rtol=1e-5, atol=1e-5)
+    Xv, _ = ko.predict(X3, P3, directions, dts, F, Q)
+    view = torch.cat((Xv[:, :-1], directions.float().unsqueeze(1), Xv[:, -1:]), dim=1)
+    assert torch.allclose(view, gd["view"], rtol=1e-6, atol=1e-6)
