@@ -26,20 +26,35 @@ __global__ void __launch_bounds__(128) kf_predict_kernel(float* __restrict__ X, 
                                                          int64_t n, int s_rt, const KfModel m) {
     const int SS = (S > 0) ? S : s_rt;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ii = i;
+        const bool live = true;
         const double dt = dt_arr ? dt_arr[i] : dt_scalar;
-        float F[kKfMax][kKfMax], Pm[kKfMax][kKfMax], A[kKfMax][kKfMax], x[kKfMax], xn[kKfMax];
+        const double dt_over_default = dt / dt_default;
+        float F[kKfMax][kKfMax], Pm[kKfMax][kKfMax], A[kKfMax][kKfMax], x[kKfMax], xn[kKfMax], Pn[kKfMax][kKfMax];
 #pragma unroll
         for (int r = 0; r < kKfMax; ++r)
 #pragma unroll
-            for (int c = 0; c < kKfMax; ++c) {
-                if (r < SS && c < SS) {
-                    F[r][c] = m.F[r * SS + c];
-                    Pm[r][c] = P[(i * SS + r) * SS + c];
-                }
-            }
-        if (SS > 5) F[0][5] = (float)((double)D[i] * dt);            // kf.py:315 (hard-wired position / speed slots)
+            for (int c = 0; c < kKfMax; ++c)
+                if (r < SS && c < SS) F[r][c] = m.F[r * SS + c];
+        if (S == 6) {   // 144-byte rows: nine 16-byte loads per object instead of 36 scalar ones
+            const float4* prow = reinterpret_cast<const float4*>(P + i * 36);
 #pragma unroll
-        for (int r = 0; r < kKfMax; ++r) if (r < SS) x[r] = X[i * SS + r];
+            for (int q = 0; q < 9; ++q) {
+                const float4 v = prow[q];
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) Pm[(4 * q + k) / 6][(4 * q + k) % 6] = e[k];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+                for (int c = 0; c < kKfMax; ++c)
+                    if (r < SS && c < SS) Pm[r][c] = P[(i * SS + r) * SS + c];
+        }
+        if (SS > 5) F[0][5] = (float)((double)D[ii] * dt);           // kf.py:315 (hard-wired position / speed slots)
+#pragma unroll
+        for (int r = 0; r < kKfMax; ++r) if (r < SS) x[r] = X[ii * SS + r];
 #pragma unroll
         for (int r = 0; r < kKfMax; ++r) {
             if (r >= SS) continue;
@@ -70,17 +85,32 @@ __global__ void __launch_bounds__(128) kf_predict_kernel(float* __restrict__ X, 
                 for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(A[r][k], F[c][k]));
                 float out;
                 if (dt_arr) {   // float * double tensor / python float: the scaling and the sum in double, then .float()
-                    const double q = (double)m.Q[r * SS + c] * dt / dt_default;
+                    const double q = (double)m.Q[r * SS + c] * dt_over_default;   // = Q * dt / dt_default to 1 ulp of FP64
                     out = (float)((double)acc + q);
                 } else {        // float tensor * python scalar: FP32 with the scalar rounded to FP32
                     const float q = __fdiv_rn(__fmul_rn(m.Q[r * SS + c], (float)dt), (float)dt_default);
                     out = __fadd_rn(acc, q);
                 }
-                P[(i * SS + r) * SS + c] = out;
+                Pn[r][c] = out;
             }
+        if (S == 6) {
+            float4* prow = reinterpret_cast<float4*>(P + i * 36);
 #pragma unroll
-        for (int r = 0; r < kKfMax; ++r) if (r < SS) X[i * SS + r] = xn[r];
-        if (T) T[i] += dt;
+            for (int q = 0; q < 9; ++q)
+                prow[q] = make_float4(Pn[(4 * q) / 6][(4 * q) % 6], Pn[(4 * q + 1) / 6][(4 * q + 1) % 6],
+                                      Pn[(4 * q + 2) / 6][(4 * q + 2) % 6], Pn[(4 * q + 3) / 6][(4 * q + 3) % 6]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+                for (int c = 0; c < kKfMax; ++c)
+                    if (r < SS && c < SS) P[(i * SS + r) * SS + c] = Pn[r][c];
+        }
+        if (live) {
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r) if (r < SS) X[i * SS + r] = xn[r];
+            if (T) T[i] += dt;
+        }
     }
 }
 
@@ -95,12 +125,26 @@ __global__ void __launch_bounds__(128) kf_update_kernel(float* __restrict__ X, f
         const int64_t i = rows[j];
         float Pm[kKfMax][kKfMax], x[kKfMax], HP[kKfMax][kKfMax], Sm[kKfMax][kKfMax], Si[kKfMax][kKfMax];
         float PHt[kKfMax][kKfMax], K[kKfMax][kKfMax], y[kKfMax];
+        if (S == 6) {   // 144-byte rows: nine 16-byte loads per object instead of 36 scalar ones
+            const float4* prow = reinterpret_cast<const float4*>(P + i * 36);
 #pragma unroll
-        for (int r = 0; r < kKfMax; ++r) {
-            if (r < SS) x[r] = X[i * SS + r];
+            for (int q = 0; q < 9; ++q) {
+                const float4 v = __ldg(prow + q);
+                const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int c = 0; c < kKfMax; ++c)
-                if (r < SS && c < SS) Pm[r][c] = P[(i * SS + r) * SS + c];
+                for (int k = 0; k < 4; ++k) Pm[(4 * q + k) / 6][(4 * q + k) % 6] = e[k];
+            }
+            const float2* xrow = reinterpret_cast<const float2*>(X + i * 6);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { const float2 v = xrow[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r) {
+                if (r < SS) x[r] = X[i * SS + r];
+#pragma unroll
+                for (int c = 0; c < kKfMax; ++c)
+                    if (r < SS && c < SS) Pm[r][c] = P[(i * SS + r) * SS + c];
+            }
         }
         // innovation: double(z) + mu_R - float(x H^T), then .float()
 #pragma unroll
@@ -199,6 +243,7 @@ __global__ void __launch_bounds__(128) kf_update_kernel(float* __restrict__ X, f
             X[i * SS + r] = __fadd_rn(x[r], acc);
         }
         // P = (I - K H) P
+        float Pn[kKfMax][kKfMax];
 #pragma unroll
         for (int r = 0; r < kKfMax; ++r) {
             if (r >= SS) continue;
@@ -217,8 +262,21 @@ __global__ void __launch_bounds__(128) kf_update_kernel(float* __restrict__ X, f
                 float acc = 0.0f;
 #pragma unroll
                 for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(IKH[k], Pm[k][c]));
-                P[(i * SS + r) * SS + c] = acc;
+                Pn[r][c] = acc;
             }
+        }
+        if (S == 6) {
+            float4* prow = reinterpret_cast<float4*>(P + i * 36);
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+                prow[q] = make_float4(Pn[(4 * q) / 6][(4 * q) % 6], Pn[(4 * q + 1) / 6][(4 * q + 1) % 6],
+                                      Pn[(4 * q + 2) / 6][(4 * q + 2) % 6], Pn[(4 * q + 3) / 6][(4 * q + 3) % 6]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kKfMax; ++r)
+#pragma unroll
+                for (int c = 0; c < kKfMax; ++c)
+                    if (r < SS && c < SS) P[(i * SS + r) * SS + c] = Pn[r][c];
         }
     }
 }
@@ -246,6 +304,7 @@ extern "C" int g3d_kf_predict(float* X, float* P, const float* D, const double* 
     if (n == 0) return G3D_OK;
     G3D_REQUIRE(X && P && F_host && Q_host, "null pointer");
     G3D_REQUIRE(S <= 5 || D, "direction vector needed (F[0,5] = D * dt)");
+    G3D_REQUIRE(((uintptr_t)P % 16) == 0, "P must be 16-byte aligned");
     G3D_GUARD(device);
     KfModel m;
     fill_model(m, F_host, Q_host, nullptr, nullptr, nullptr, (int)S, 0);
@@ -264,6 +323,7 @@ extern "C" int g3d_kf_update(float* X, float* P, const int64_t* rows, const doub
     G3D_REQUIRE(m_count >= 0 && S >= 1 && S <= kKfMax && M >= 1 && M <= kKfMax, "state / measurement size must be 1..8");
     if (m_count == 0) return G3D_OK;
     G3D_REQUIRE(X && P && rows && z && H_host && R_host, "null pointer");
+    G3D_REQUIRE(((uintptr_t)P % 16) == 0 && ((uintptr_t)X % 8) == 0, "P must be 16-byte and X 8-byte aligned");
     G3D_GUARD(device);
     KfModel m;
     fill_model(m, nullptr, nullptr, H_host, R_host, mu_R_host, (int)S, (int)M);
