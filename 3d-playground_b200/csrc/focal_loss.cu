@@ -147,12 +147,17 @@ __device__ __forceinline__ float cos_loss(float rx, float ry, float tx, float ty
 }
 // gradient of cos_loss w.r.t. (rx, ry)
 __device__ __forceinline__ void cos_loss_grad(float rx, float ry, float tx, float ty, float& gx, float& gy) {
-    const float rn = sqrtf(rx * rx + ry * ry), tn = sqrtf(tx * tx + ty * ty);
-    const float dot = rx * tx + ry * ty, den = rn * tn;
-    // d(-dot/den)/dr = -(t/den) + dot * (r/rn) * tn / den^2
-    const float k = dot / (den * den) * tn / rn;
-    gx = -tx / den + k * rx;
-    gy = -ty / den + k * ry;
+    // d(1 - r.t/(|r||t|))/dr = -(t^ - cos * r^)/|r|.  In the plane t^ - cos*r^ = (r_perp^ . t^) r_perp^, which gives the
+    // cancellation-free form  g = cross * (ry, -rx) / (|r|^3 |t|),  cross = rx*ty - ry*tx  (evaluated with an exact
+    // product residual).  The textbook form subtracts two terms of size 1/|r| and loses digits when r is nearly
+    // parallel to t or very short; this one stays within a few ulp of the exact gradient.
+    const float r2 = rx * rx + ry * ry;
+    const float rn = sqrtf(r2), tn = sqrtf(tx * tx + ty * ty);
+    const float p = ry * tx, e = fmaf(ry, tx, -p);
+    const float cross = fmaf(rx, ty, -p) - e;
+    const float k = cross / ((r2 * rn) * tn);
+    gx = k * ry;
+    gy = -k * rx;
 }
 
 // corner sign table of losses.py:311-327 / utils.py:114-130: corner k = c + sl*L + sw*W + sh*H

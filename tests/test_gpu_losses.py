@@ -277,3 +277,50 @@ def test_baseline_config_1_vs_oracle():
     assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg")
     fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc.cuda(), ann.cuda())
     assert torch.equal(fwd["assign"].cpu(), _codes_from_oracle(ref[-1], ann, True)), "assignment codes must be exact"
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_loss_random_small_configurations(seed):
+    """seeded sweep over odd shapes: anchors not a multiple of the 32-row chunks / 256-anchor tiles, batch not a multiple
+    of the 4-image groups, 0..N padded rows, an empty image, annotation widths 21 / 27 (3D) and 5 (2D), C == 8 and != 8;
+    losses, exact codes and gradients (unit and non-unit upstream) against the oracle"""
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    g = synth.gen(5000 + seed)
+    r = lambda lo_, hi_: int(torch.randint(lo_, hi_ + 1, (1,), generator=g))   # noqa: E731
+    three_d = seed % 3 != 2
+    H, W = 32 * r(2, 5) + 8 * r(0, 3), 32 * r(2, 6) + 8 * r(0, 3)
+    B, G, n_pad, C = r(1, 9), r(1, 40), r(0, 3), (8 if seed % 4 else 5)
+    anc = synth.anchors(H, W)
+    A = anc.shape[1]
+    empty = (r(0, B - 1),) if (B > 1 and seed % 2) else ()
+    maker = synth.gt_annotations_3d if three_d else synth.gt_annotations_2d
+    ann = maker(B, G, H, W, g, n_pad=n_pad, empty_images=empty, num_classes=C, **synth.TINY)
+    if three_d and seed % 5 == 0:
+        ann = ann[..., :21].contiguous()                      # the narrowest legal 3D annotation row
+    cls, reg = synth.head_outputs(B, A, C, 12 if three_d else 4, g)
+    up = (1.0, 1.0, 1.0) if seed % 2 == 0 else (0.5, 2.0, 1.5)
+    n = 3 if three_d else 2
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref = lo.focal_loss(c0, r0, anc, ann)
+    sum(up[i] * ref[i].sum() for i in range(n)).backward()
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    out = li.FocalLoss(check_empty=False)(c1, r1, anc.cuda(), ann.cuda())
+    sum(up[i] * out[i].sum() for i in range(n)).backward()
+    assert_close_rel(torch.cat(out).detach().cpu(), torch.cat(ref[:-1]).detach(), TOL, f"losses (B={B} A={A} G={G} C={C})")
+    assert_close_rel(c1.grad.cpu(), c0.grad, TOL, "dcls")
+    # dreg per anchor row (1e-5 of the row's largest component): the synthetic heads produce direction vectors as short
+    # as 1e-3, where the cosine gradient is a difference of terms ~1/|r| and the FP32 autograd of the reference is itself
+    # 1.2e-5 of an element away from the FP64 value of the same formula (the kernel's cross-product form is closer)
+    assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg", row_scale=True)
+    fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc.cuda(), ann.cuda())
+    codes = _codes_from_oracle(ref[-1], ann, three_d)
+    assert torch.equal(fwd["assign"].cpu(), codes), "assignment codes must be exact"
+    # ... and element-wise against the same formula evaluated in FP64 (images whose FP64 assignment is the FP32 one) at
+    # 3e-5: FP32 rounding of the regression targets alone puts the reference's own FP32 autograd up to 1.7e-5 from it
+    c2, r2 = cls.double().requires_grad_(True), reg.double().requires_grad_(True)
+    ref64 = lo.focal_loss(c2, r2, anc.double(), ann.double())
+    sum(up[i] * ref64[i].sum() for i in range(n)).backward()
+    same = (_codes_from_oracle(ref64[-1], ann, three_d) == codes).all(dim=1)
+    assert same.any()
+    assert_close_rel(r1.grad.cpu()[same], r2.grad[same], 3 * TOL, "dreg vs FP64 formula")
