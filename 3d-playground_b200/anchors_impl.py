@@ -1,9 +1,12 @@
 """Anchor generation with the layout the hot path consumes (anchors.py:6-129, identical in both retinanet copies).
 
 Order: pyramid level 3..7 -> cell row-major (y outer, x inner) -> 9 shapes (ratio-major: ratios {0.5,1,2} x scales
-{2^0, 2^(1/3), 2^(2/3)}).  Values are formed in float64 and cast to float32 exactly as the reference's numpy code does,
-but once per (image shape, device) instead of on every forward (the reference rebuilds them in numpy and copies
-6.2 MB host->device per call at 1080p).
+{2^0, 2^(1/3), 2^(2/3)}).  Values are formed in float64 and cast to float32 exactly as the reference's numpy code does.
+
+For an image on a CUDA device the table is written by one kernel (`g3d_generate_anchors`, csrc/anchors.cu, SURVEY
+§8f-2) from the 45 base-shape doubles, once per (image shape, device), and stays resident; the reference rebuilds it in
+numpy and copies 6.2 MB host->device on every forward at 1080p.  `anchors_for_image` is the host-side generator (numpy,
+what the reference itself runs) used for CPU tensors and by the synthetic-input builders.
 """
 import numpy as np
 import torch
@@ -23,12 +26,14 @@ def _level_shapes(size, ratios, scales):
     return np.stack((0.0 - w * 0.5, 0.0 - h * 0.5, w - w * 0.5, h - h * 0.5), axis=1)
 
 
-def anchors_for_image(height, width, pyramid_levels=_PYRAMID_LEVELS, ratios=_RATIOS, scales=_SCALES):
+def anchors_for_image(height, width, pyramid_levels=_PYRAMID_LEVELS, ratios=_RATIOS, scales=_SCALES, strides=None,
+                      sizes=None):
     """float32 [A,4] anchors for an image of height x width."""
     out = []
-    for lvl in pyramid_levels:
-        stride, size = 2 ** lvl, 2 ** (lvl + 2)
-        rows, cols = (height + stride - 1) // stride, (width + stride - 1) // stride
+    for k, lvl in enumerate(pyramid_levels):
+        stride = 2 ** lvl if strides is None else strides[k]
+        size = 2 ** (lvl + 2) if sizes is None else sizes[k]
+        rows, cols = (height + 2 ** lvl - 1) // 2 ** lvl, (width + 2 ** lvl - 1) // 2 ** lvl     # anchors.py:25
         cx = (np.arange(cols) + 0.5) * stride
         cy = (np.arange(rows) + 0.5) * stride
         gx, gy = np.meshgrid(cx, cy)                            # [rows, cols], x fastest
@@ -54,6 +59,15 @@ class Anchors(nn.Module):
         h, w = int(image.shape[2]), int(image.shape[3])
         key = (h, w, str(image.device))
         if key not in self._cache:
-            a = anchors_for_image(h, w, tuple(self.pyramid_levels), np.asarray(self.ratios), np.asarray(self.scales))
-            self._cache[key] = torch.from_numpy(a).unsqueeze(0).to(image.device)
+            ratios, scales = np.asarray(self.ratios), np.asarray(self.scales)
+            if image.is_cuda:
+                from . import ops
+                strides = [float(s) for s in self.strides]
+                rows = [(h + 2 ** x - 1) // (2 ** x) for x in self.pyramid_levels]
+                cols = [(w + 2 ** x - 1) // (2 ** x) for x in self.pyramid_levels]
+                shapes = np.stack([_level_shapes(size, ratios, scales) for size in self.sizes])
+                self._cache[key] = ops.generate_anchors(shapes, strides, rows, cols, image.device).unsqueeze(0)
+            else:
+                a = anchors_for_image(h, w, tuple(self.pyramid_levels), ratios, scales, self.strides, self.sizes)
+                self._cache[key] = torch.from_numpy(a).unsqueeze(0)
         return self._cache[key]

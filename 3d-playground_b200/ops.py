@@ -688,3 +688,27 @@ def kf_update_(X, P, rows, z, H, R, mu_R=None):
                                    muh.ctypes.data_as(ctypes.c_void_p) if muh is not None else None, _idx(dev),
                                    _stream(dev)), "g3d_kf_update")
     return X, P
+
+
+def generate_anchors(level_shapes, strides, rows, cols, device):
+    """Anchors.forward on the device (anchors.py:21-40): float32 [A,4].  level_shapes: float64 [L,S,4] base boxes per level
+    (numpy, from generate_anchors); strides [L]; rows/cols [L]: feature-map sizes per level."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise Geom3dError(f"geom3d ops run on CUDA devices only (no CPU fallback): got {dev}")
+    shp = np.ascontiguousarray(np.asarray(level_shapes, dtype=np.float64))
+    if shp.ndim != 3 or shp.shape[2] != 4:
+        raise ValueError("level_shapes must be [L,S,4]")
+    L, S = int(shp.shape[0]), int(shp.shape[1])
+    st = np.ascontiguousarray(np.asarray(strides, dtype=np.float64).reshape(-1))
+    rr = np.ascontiguousarray(np.asarray(rows, dtype=np.int64).reshape(-1))
+    cc = np.ascontiguousarray(np.asarray(cols, dtype=np.int64).reshape(-1))
+    if not (st.size == rr.size == cc.size == L):
+        raise ValueError("strides, rows and cols need one entry per level")
+    A = int((rr * cc).sum()) * S
+    out = torch.empty((A, 4), dtype=torch.float32, device=dev)
+    vp = ctypes.c_void_p
+    check(_lib.lib().g3d_generate_anchors(shp.ctypes.data_as(vp), st.ctypes.data_as(vp), rr.ctypes.data_as(vp),
+                                          cc.ctypes.data_as(vp), L, S, _p(out), A, _idx(dev), _stream(dev)),
+          "g3d_generate_anchors")
+    return out

@@ -340,6 +340,18 @@ int g3d_kf_predict(float* X, float* P, const float* D, const double* dt_per_obje
 int g3d_kf_update(float* X, float* P, const int64_t* rows, const double* z, int64_t m_count, int64_t S, int64_t M,
                   const float* H_host, const float* R_host, const float* mu_R_host, int device, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SURVEY §8(f)-2  Anchors.forward                           retinanet/anchors.py:21-40 (generate_anchors :42-74, shift :109-129)
+ * Writes the float32 [A,4] anchor table on the device instead of building it in numpy and copying it on every forward.
+ * Order: level -> cell row-major (y outer, x inner) -> the S shapes of the level.  anchors[i] =
+ * float32(shapes[level][s] + ((col|row) + 0.5) * stride[level]) with the sum in FP64 (numpy's float64 then astype f32).
+ * shapes_host[L][S][4] (x1,y1,x2,y2 around the origin, from generate_anchors), strides_host[L], rows_host[L], cols_host[L]
+ * (feature-map sizes ceil(H / 2^level), ceil(W / 2^level)): host arrays.  L <= 8, L*S <= 96.  A = sum rows*cols*S.
+ */
+int g3d_generate_anchors(const double* shapes_host, const double* strides_host, const int64_t* rows_host,
+                         const int64_t* cols_host, int64_t L, int64_t S, float* anchors, int64_t A, int device,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -370,7 +370,38 @@ def golden_kf():
     save("kf", **out)
 
 
+# ----------------------------------------------------------------------------------------------------------- anchors
+ANCHOR_SHAPES_FULL = ((112, 112), (75, 133), (64, 80))          # stored completely
+ANCHOR_SHAPES_HASHED = ((540, 960), (1080, 1920), (1001, 777))  # stored as sha256 of the float32 bytes + row count
+
+
+def golden_anchors():
+    """the reference's own Anchors.forward (retinanet/anchors.py:21-40; both copies are identical) on zero images"""
+    import hashlib
+    _, _, _, anchors3 = _import_retinanet(True)
+    _, _, _, anchors2 = _import_retinanet(False)
+    avail = torch.cuda.is_available
+    torch.cuda.is_available = lambda: False                     # anchors.py:37 would call .cuda()
+    try:
+        out = {}
+        for h, w in ANCHOR_SHAPES_FULL + ANCHOR_SHAPES_HASHED:
+            a = anchors3.Anchors()(torch.zeros(1, 3, h, w))
+            assert torch.equal(a, anchors2.Anchors()(torch.zeros(1, 3, h, w)))
+            a = np.ascontiguousarray(_np(a)[0])
+            if (h, w) in ANCHOR_SHAPES_FULL:
+                out[f"anchors_{h}x{w}"] = a
+            out[f"sha256_{h}x{w}"] = np.frombuffer(hashlib.sha256(a.tobytes()).digest(), dtype=np.uint8)
+            out[f"count_{h}x{w}"] = np.int64(a.shape[0])
+    finally:
+        torch.cuda.is_available = avail
+    save("anchors", **out)
+
+
 if __name__ == "__main__":
+    if "--only-anchors" in sys.argv:
+        _shim()
+        golden_anchors()
+        sys.exit(0)
     if not os.path.isdir(REF):
         sys.exit("needs the reference checkout at /root/reference")
     torch.manual_seed(0)
@@ -383,3 +414,4 @@ if __name__ == "__main__":
     golden_homography()
     golden_tracker()
     golden_kf()
+    golden_anchors()

@@ -9,7 +9,7 @@ import synth
 import os
 
 from conftest import GOLDEN, assert_close_rel, load_golden
-from oracle import decode_oracle, homography_oracle as ho, losses_oracle as lo, nms_oracle, tracker_oracle
+from oracle import anchors_oracle, decode_oracle, homography_oracle as ho, losses_oracle as lo, nms_oracle, tracker_oracle
 
 
 @pytest.mark.parametrize("name", ["loss3d", "loss2d"])
@@ -189,3 +189,18 @@ def test_kf_oracle_matches_reference_golden():
     Xv, _ = ko.predict(X3, P3, directions, dts, F, Q)
     view = torch.cat((Xv[:, :-1], directions.float().unsqueeze(1), Xv[:, -1:]), dim=1)
     assert torch.allclose(view, gd["view"], rtol=1e-6, atol=1e-6)
+
+
+def test_anchors_oracle_and_host_generator_equal_reference_tables():
+    """anchors.py:21-40: every stored table and every sha256 of the reference's Anchors.forward, bit for bit"""
+    import hashlib
+    from geom3d_b200.anchors_impl import Anchors, anchors_for_image
+    gd = np.load(os.path.join(GOLDEN, "anchors.npz"))
+    shapes = [tuple(map(int, k[7:].split("x"))) for k in gd.files if k.startswith("sha256_")]
+    assert len(shapes) == 6
+    for h, w in shapes:
+        for table in (anchors_oracle.anchors(h, w), anchors_for_image(h, w), Anchors()(torch.zeros(1, 3, h, w))[0].numpy()):
+            assert table.dtype == np.float32 and table.shape == (int(gd[f"count_{h}x{w}"]), 4)
+            assert hashlib.sha256(np.ascontiguousarray(table).tobytes()).digest() == gd[f"sha256_{h}x{w}"].tobytes(), (h, w)
+            if f"anchors_{h}x{w}" in gd.files:
+                assert np.array_equal(table, gd[f"anchors_{h}x{w}"])
