@@ -271,10 +271,16 @@ __global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __res
 // a 64x64-block suppression bit-matrix in L2 (upper triangle only) - and ONE warp then walks the blocks: a 64-step
 // shuffle scan on the diagonal words, then the kept rows' words are OR-ed into the running "removed" set (coalesced,
 // independent loads).  Same pair test, same order, same keep list as the greedy kernel.
-__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox, int n, int nb, float thr,
+// The segment [seg[0], seg[1]) is read on the device (n <= the capacity the grid and the row stride nb were sized for), so
+// a captured launch sequence serves any length up to its capacity.
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__ sbox_all,
+                                                      const int32_t* __restrict__ seg, int nb, float thr,
                                                       uint64_t* __restrict__ mask) {
     const int rb = blockIdx.y, cb = blockIdx.x, tid = threadIdx.x;
     if (cb < rb) return;
+    const int off = seg[0], n = seg[1] - off;
+    if (cb * 64 >= n || rb * 64 >= n) return;
+    const float4* __restrict__ sbox = sbox_all + off;
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     const bool thr_nonneg = thr >= 0.0f;
@@ -299,17 +305,23 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float4* __restrict__
 // WPL = 64-bit words of the "removed" set per lane (nb <= 32 * WPL)
 template <int WPL>
 __global__ void __launch_bounds__(32) nms_mask_scan_kernel(const uint64_t* __restrict__ mask,
-                                                           const int32_t* __restrict__ sidx, int n, int nb,
-                                                           int64_t* __restrict__ keep_out,
+                                                           const int32_t* __restrict__ sidx_all,
+                                                           const int32_t* __restrict__ seg, int nbs, int relative,
+                                                           int64_t* __restrict__ keep_all,
                                                            int32_t* __restrict__ keep_count) {
     const int lane = threadIdx.x;
+    const int off = seg[0], n = seg[1] - off;
+    const int nb = (n + 63) >> 6;               // blocks in use; nbs = row stride of the matrix (capacity)
+    const int32_t* __restrict__ sidx = sidx_all + off;
+    int64_t* __restrict__ keep_out = keep_all + off;
+    const int add = relative ? 0 : off;
     uint64_t remv[WPL];
 #pragma unroll
     for (int k = 0; k < WPL; ++k) remv[k] = 0ull;
     int total = 0;
     // diagonal words of block 0 (each later block's are requested one block ahead: they depend on nothing)
-    uint64_t dA = (lane < n) ? mask[(int64_t)lane * nb] : 0ull;
-    uint64_t dB = (lane + 32 < n) ? mask[(int64_t)(lane + 32) * nb] : 0ull;
+    uint64_t dA = (lane < n) ? mask[(int64_t)lane * nbs] : 0ull;
+    uint64_t dB = (lane + 32 < n) ? mask[(int64_t)(lane + 32) * nbs] : 0ull;
     int sA = (lane < n) ? sidx[lane] : 0, sB = (lane + 32 < n) ? sidx[lane + 32] : 0;   // original indices, same prefetch
     for (int blk = 0; blk < nb; ++blk) {
         const int base = blk << 6;
@@ -319,8 +331,8 @@ __global__ void __launch_bounds__(32) nms_mask_scan_kernel(const uint64_t* __res
         const int tA = sA, tB = sB;
         if (blk + 1 < nb) {
             const int ra = base + 64 + lane, rb2 = ra + 32;
-            dA = (ra < n) ? mask[(int64_t)ra * nb + blk + 1] : 0ull;
-            dB = (rb2 < n) ? mask[(int64_t)rb2 * nb + blk + 1] : 0ull;
+            dA = (ra < n) ? mask[(int64_t)ra * nbs + blk + 1] : 0ull;
+            dB = (rb2 < n) ? mask[(int64_t)rb2 * nbs + blk + 1] : 0ull;
             sA = (ra < n) ? sidx[ra] : 0;
             sB = (rb2 < n) ? sidx[rb2] : 0;
         }
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(32) nms_mask_scan_kernel(const uint64_t* __res
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int i = lane + 32 * half;
-            if ((keep >> i) & 1ull) keep_out[total + __popcll(keep & ((1ull << i) - 1ull))] = half ? tB : tA;
+            if ((keep >> i) & 1ull) keep_out[total + __popcll(keep & ((1ull << i) - 1ull))] = (half ? tB : tA) + add;
         }
         total += __popcll(keep);
         // the kept rows suppress later blocks: their words are independent loads - keep kBatch rows in flight
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(32) nms_mask_scan_kernel(const uint64_t* __res
                 const bool have = bits != 0ull;
                 const int i = have ? __ffsll((long long)bits) - 1 : 0;
                 bits &= bits - 1;      // 0 stays 0
-                const uint64_t* rowp = mask + (int64_t)(base + i) * nb;
+                const uint64_t* rowp = mask + (int64_t)(base + i) * nbs;
 #pragma unroll
                 for (int k = 0; k < WPL; ++k) {
                     const int w = lane + 32 * k;
@@ -490,15 +502,14 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
         G3D_LAUNCH_CHECK();
     }
     if (use_mask_path(S, max_seg_len, N)) {
-        const int n = (int)N, nb = (int)ceil_div(N, 64);
-        nms_mask_kernel<<<dim3((unsigned)nb, (unsigned)nb), 64, 0, st>>>(w.sbox, n, nb, thr_f, w.mask);
+        const int nb = (int)ceil_div(N, 64);      // capacity: the segment's own length is read from seg_offsets on the device
+        nms_mask_kernel<<<dim3((unsigned)nb, (unsigned)nb), 64, 0, st>>>(w.sbox, seg_offsets, nb, thr_f, w.mask);
         G3D_LAUNCH_CHECK();
-        if (nb <= 32)       nms_mask_scan_kernel<1><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
-        else if (nb <= 64)  nms_mask_scan_kernel<2><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
-        else if (nb <= 128) nms_mask_scan_kernel<4><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
-        else                nms_mask_scan_kernel<8><<<1, 32, 0, st>>>(w.mask, w.sidx, n, nb, keep_out, keep_count);
+        if (nb <= 32)       nms_mask_scan_kernel<1><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
+        else if (nb <= 64)  nms_mask_scan_kernel<2><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
+        else if (nb <= 128) nms_mask_scan_kernel<4><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
+        else                nms_mask_scan_kernel<8><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
         G3D_LAUNCH_CHECK();
-        (void)relative;   // one segment starting at 0: relative and absolute indices coincide
         return G3D_OK;
     }
     const int removed_words = (int)(2 * ceil_div(max_seg_len, 64));

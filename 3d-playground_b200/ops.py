@@ -712,3 +712,29 @@ def generate_anchors(level_shapes, strides, rows, cols, device):
                                           cc.ctypes.data_as(vp), L, S, _p(out), A, _idx(dev), _stream(dev)),
           "g3d_generate_anchors")
     return out
+
+
+def cross_camera_pairs(footprints, cams, threshold):
+    """estimate_ts_bias's pair mining (MC3D_crop_tracker.py:277-289): int64 [K,2] pairs (i, j), i < j, different cameras,
+    float64 IoU of the float32 footprints[d,4] > threshold, in the reference's loop order.  One 4-byte read sizes K."""
+    dev = _need_cuda(footprints, cams)
+    fp = _prep(footprints, torch.float32)
+    cm = _prep(cams, torch.int32).reshape(-1)
+    if fp.dim() != 2 or fp.shape[1] != 4 or cm.numel() != fp.shape[0]:
+        raise ValueError(f"expected footprints[d,4] and cams[d], got {tuple(fp.shape)} and {tuple(cm.shape)}")
+    d = fp.shape[0]
+    if d < 2:
+        return torch.empty((0, 2), dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    count = torch.empty((d,), dtype=torch.int32, device=dev)
+    offsets = torch.empty((d + 1,), dtype=torch.int32, device=dev)
+    null = ctypes.c_void_p(0)
+    check(L.g3d_cross_camera_pairs(_p(fp), _p(cm), d, float(threshold), _p(count), null, null, 0, _idx(dev), _stream(dev)),
+          "g3d_cross_camera_pairs")
+    check(L.g3d_exclusive_scan_i32(_p(count), d, _p(offsets), _idx(dev), _stream(dev)), "g3d_exclusive_scan_i32")
+    K = int(offsets[d].item())
+    pairs = torch.empty((K, 2), dtype=torch.int32, device=dev)
+    if K:
+        check(L.g3d_cross_camera_pairs(_p(fp), _p(cm), d, float(threshold), null, _p(offsets), _p(pairs), K, _idx(dev),
+                                       _stream(dev)), "g3d_cross_camera_pairs")
+    return pairs.long()

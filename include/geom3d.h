@@ -321,6 +321,15 @@ int g3d_pairwise_iou_f64(const float* first, int64_t n, const float* second, int
                          double* out, int device, void* stream);
 /* a20 literal form: a[n,4], b[n,4] float64 element-wise -> out[n] (the reference signature with pre-broadcast inputs) */
 int g3d_md_iou(const double* a, const double* b, int64_t n, double* out, int device, void* stream);
+/*
+ * SURVEY §8(f)-3  estimate_ts_bias pair mining              MC3D_crop_tracker.py:277-289
+ * All pairs (i, j), i < j, cams[i] != cams[j], md_iou(boxes[j], boxes[i]) > threshold (float64 IoU of the float32
+ * footprints boxes[d,4], no epsilon), in the reference's loop order (i outer, j inner).  Two passes around
+ * g3d_exclusive_scan_i32: row_offsets == NULL writes row_count[d]; row_offsets[d+1] != NULL writes pairs[.,2] (int32 i, j)
+ * at the rows' offsets (entries at positions >= capacity are dropped).  The d x d matrix is never materialised.
+ */
+int g3d_cross_camera_pairs(const float* boxes, const int32_t* cams, int64_t d, double threshold, int32_t* row_count,
+                           const int32_t* row_offsets, int32_t* pairs, int64_t capacity, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * SURVEY §8(f)-4  Torch_KF.predict / Torch_KF.update        util_track/kf.py:292-336, :339-403

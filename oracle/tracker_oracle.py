@@ -4,6 +4,11 @@
     footprint     MC3D_crop_tracker.py:625-632 (min/max of the 4 bottom space corners)
     im_box        MC3D_crop_tracker.py:602-607
     association_cost   MC3D_crop_tracker.py:663-689 (1 - md_iou on broadcast footprints)
+    cross_camera_pairs / estimate_ts_bias   MC3D_crop_tracker.py:237-315
+
+Parity pin: tests/test_oracle_golden.py::test_tracker / test_estimate_ts_bias against tests/golden/tracker.npz and
+tests/golden/ts_bias.npz, produced by the UNMODIFIED MC_Crop_Tracker methods (tests/golden/make_golden.py).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import this module.
 """
 import torch
 
@@ -51,3 +56,47 @@ def im_nms(corners, scores, threshold=0.8, groups=None):
     if groups is not None:
         boxes = boxes + 10000
     return nms_oracle.nms(boxes.float(), scores, threshold)
+
+
+def cross_camera_pairs(boxes, camera_idxs, phi):
+    """the double loop of estimate_ts_bias (:277-289): (i, j), i < j, different cameras, iou[i, j] > phi, loop order"""
+    fp = footprint(boxes)
+    d = fp.shape[0]
+    iou = md_iou(fp.unsqueeze(0).repeat(d, 1, 1).double(), fp.unsqueeze(1).repeat(1, d, 1).double()).reshape(d, d)
+    cams = torch.as_tensor(camera_idxs).reshape(-1)
+    hit = (iou > phi) & (cams[:, None] != cams[None, :])
+    return torch.nonzero(torch.triu(hit, diagonal=1))          # row-major == i outer, j inner
+
+
+def estimate_ts_bias(boxes, camera_idxs, objs, timestamps, ts_bias, mu_v, phi, alpha):
+    """returns the updated copy of ts_bias (list of python floats), :251-315 step by step"""
+    ts_bias = list(ts_bias)
+    if len(camera_idxs) == 0 or len(objs) == 0:
+        return ts_bias
+    wb = objs[objs[:, 5] == -1, 6]
+    eb = objs[objs[:, 5] == 1, 6]
+    wb_vel = torch.mean(wb) * -1
+    eb_vel = torch.mean(eb)
+    if torch.isnan(wb_vel):
+        wb_vel = torch.tensor(-float(mu_v))
+    if torch.isnan(eb_vel):
+        eb_vel = torch.tensor(float(mu_v))
+    cams = [int(c) for c in camera_idxs]
+    entries = []
+    for i, j in cross_camera_pairs(boxes, camera_idxs, phi).tolist():
+        entries.append((cams[i], cams[j], boxes[j, 0] - boxes[i, 0], boxes[i, 5]))
+        entries.append((cams[j], cams[i], boxes[i, 0] - boxes[j, 0], boxes[i, 5]))
+    if not entries:
+        return ts_bias
+    dx = torch.tensor([float(e[2]) for e in entries])
+    dt_expected = torch.tensor([timestamps[e[1]] - timestamps[e[0]] for e in entries])
+    vel = torch.ones(len(entries)) * eb_vel
+    for k, e in enumerate(entries):
+        if e[3] == -1:
+            vel[k] = wb_vel
+    time_error = dx / vel - dt_expected
+    for k, te in enumerate(time_error):
+        c1, c2 = entries[k][0], entries[k][1]
+        if c1 != 0:
+            ts_bias[c1] = float((1 - alpha) * ts_bias[c1] + alpha * (-te + ts_bias[c2]))
+    return ts_bias

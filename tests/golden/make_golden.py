@@ -323,6 +323,55 @@ def golden_tracker():
          im_nms_groups=T.im_nms(me, corners, scores, threshold=0.3, groups=torch.zeros(120)))
 
 
+def ts_bias_inputs(seed=81, n_obj=45, n_cams=4):
+    """seeded estimate_ts_bias scenario shared with the tests: objects seen by 1-3 cameras (jittered duplicates), a
+    filter view with both directions, per-camera timestamps"""
+    g = synth.gen(seed)
+    base, _ = synth.vehicle_states(n_obj, g, n_cams=1)
+    base[:, 0] = 200 + torch.rand(n_obj, generator=g) * 1500
+    boxes, cams = [], []
+    for k in range(n_obj):
+        seen = torch.randperm(n_cams, generator=g)[: int(torch.randint(1, 4, (1,), generator=g))]
+        for c in seen.tolist():
+            b = base[k].clone()
+            b[:2] += torch.randn(2, generator=g) * torch.tensor([2.0, 0.3])
+            boxes.append(b)
+            cams.append(c)
+    order = torch.randperm(len(boxes), generator=g)
+    boxes = torch.stack(boxes)[order].contiguous()
+    cams = torch.tensor(cams)[order].contiguous()
+    n_filter = 30
+    objs = torch.zeros(n_filter, 7)
+    objs[:, :5] = synth.vehicle_states(n_filter, g, n_cams=1)[0][:, :5]
+    objs[:, 5] = torch.where(torch.rand(n_filter, generator=g) < 0.5, -1.0, 1.0)
+    objs[:, 6] = 90 + torch.rand(n_filter, generator=g) * 40
+    timestamps = [10.0, 10.013, 9.991, 10.02]
+    return boxes, cams, objs, timestamps
+
+
+def golden_ts_bias():
+    """MC_Crop_Tracker.estimate_ts_bias (MC3D_crop_tracker.py:237-315) called unbound, twice (the bias accumulates), plus
+    the one-direction case (:262-265 falls back to mu_v)"""
+    sys.path.insert(0, REF)
+    import homography as ref_h
+    import MC3D_crop_tracker as mc
+    sys.path.pop(0)
+    T = mc.MC_Crop_Tracker
+    boxes, cams, objs, timestamps = ts_bias_inputs()
+    out = {}
+    for tag, view in (("both", objs), ("eastbound_only", objs[objs[:, 5] == 1])):
+        me = types.SimpleNamespace(hg=ref_h.Homography(), phi_nms_space=0.1, ts_alpha=0.05, timestamps=list(timestamps),
+                                   ts_bias=[0 for _ in timestamps])
+        me.md_iou = lambda a, b: T.md_iou(me, a, b)
+        me.filter = types.SimpleNamespace(view=lambda with_direction=False, v=view: (list(range(len(v))), v.clone()), mu_v=105.0)
+        T.estimate_ts_bias(me, boxes.clone(), cams)
+        out[f"bias1_{tag}"] = np.array(me.ts_bias, dtype=np.float64)
+        me.timestamps = [t + 1 / 30.0 + 0.001 * k for k, t in enumerate(timestamps)]
+        T.estimate_ts_bias(me, boxes.clone(), cams)
+        out[f"bias2_{tag}"] = np.array(me.ts_bias, dtype=np.float64)
+    save("ts_bias", boxes=boxes, cams=cams, objs=objs, timestamps=np.array(timestamps), **out)
+
+
 def kf_inputs(seed=71, n=40, m=25):
     """seeded Kalman-filter scenario shared with the tests (the model matrices mimic a fitted kf_params INIT dict)"""
     g = synth.gen(seed)
@@ -402,6 +451,10 @@ if __name__ == "__main__":
         _shim()
         golden_anchors()
         sys.exit(0)
+    if "--only-ts-bias" in sys.argv:
+        _shim()
+        golden_ts_bias()
+        sys.exit(0)
     if not os.path.isdir(REF):
         sys.exit("needs the reference checkout at /root/reference")
     torch.manual_seed(0)
@@ -415,3 +468,4 @@ if __name__ == "__main__":
     golden_tracker()
     golden_kf()
     golden_anchors()
+    golden_ts_bias()

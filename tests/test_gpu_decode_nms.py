@@ -92,6 +92,24 @@ def test_nms_segmented_matches_per_segment():
         assert torch.equal(keep[o:o + exp.numel()], exp), f"segment {i}"
 
 
+@pytest.mark.parametrize("cap", [100, 2000, 5000])
+def test_nms_single_segment_with_device_side_length(cap):
+    """one segment whose bounds live on the device (capacity = buffer size, length read by the kernels): what a captured
+    launch sequence replays for a varying number of boxes; bit-matrix path (cap >= 256) and greedy path (cap < 256)"""
+    ops, _ = _mods()
+    from oracle import nms_oracle
+    b, s = synth.clustered_boxes(cap, synth.gen(cap + 1))
+    bd, sd = b.cuda(), s.cuda()
+    seg = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for lo, hi in ((0, cap), (0, cap // 2 + 7), (0, 0), (0, 1), (0, min(cap, 257)), (cap // 3, cap - 5), (0, 64)):
+        seg.copy_(torch.tensor([lo, hi], dtype=torch.int32))
+        exp = nms_oracle.nms(b[lo:hi], s[lo:hi], 0.3)
+        for relative in (True, False):
+            keep, cnt = ops.nms_segmented(bd, sd, seg, cap, 0.3, 0, relative)
+            assert int(cnt[0]) == exp.numel(), (lo, hi)
+            assert torch.equal(keep[lo:lo + exp.numel()].cpu(), exp + (0 if relative else lo)), (lo, hi, relative)
+
+
 def test_threshold_ladder_and_compaction_vs_oracle():
     ops, _ = _mods()
     from oracle import nms_oracle

@@ -1,0 +1,89 @@
+"""GPU parity of the tracker-frame widening: estimate_ts_bias's pair mining + bias update against the
+unmodified method's golden vectors and the oracle, and the one-graph frame (`FrameGeometry`) against the separate calls
+and the oracle.  Pair lists, keep lists and bias floats must be identical; the cost matrix is FP64 of the same formula."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from conftest import GOLDEN, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cross_camera_pairs_vs_oracle():
+    from geom3d_b200 import tracker_geometry as tg
+    from oracle import tracker_oracle as to
+    for seed, d, n_cams, spread in ((1, 300, 5, 600.0), (2, 65, 2, 150.0), (3, 1000, 18, 2500.0), (4, 33, 3, 1e6)):
+        g = synth.gen(900 + seed)
+        st, _ = synth.vehicle_states(d, g, n_cams=1)
+        st[:, 0] = 100 + torch.rand(d, generator=g) * spread
+        cams = torch.randint(0, n_cams, (d,), generator=g)
+        exp = to.cross_camera_pairs(st, cams, 0.1)
+        got = tg.cross_camera_pairs(st.cuda(), cams.cuda(), 0.1)
+        assert got.dtype == torch.int64 and torch.equal(got.cpu(), exp), (seed, exp.shape, got.shape)
+        assert torch.equal(tg.cross_camera_pairs(st, cams, 0.1), exp)                      # CPU tensors in, CPU out
+    one = synth.vehicle_states(1, synth.gen(5), n_cams=1)[0]
+    assert tg.cross_camera_pairs(one.cuda(), torch.zeros(1).cuda(), 0.1).shape == (0, 2)
+    assert tg.cross_camera_pairs(torch.zeros(0, 6).cuda(), torch.zeros(0).cuda(), 0.1).shape == (0, 2)
+    same = one.repeat(40, 1)                                                                # one camera: no pair qualifies
+    assert tg.cross_camera_pairs(same.cuda(), torch.zeros(40).cuda(), 0.1).shape == (0, 2)
+    assert tg.cross_camera_pairs(same.cuda(), torch.arange(40).cuda() % 2, 0.1).shape == (400, 2)
+
+
+def test_estimate_ts_bias_golden():
+    """MC3D_crop_tracker.py:237-315: bias lists equal to the unmodified method's floats, two consecutive calls"""
+    from geom3d_b200 import tracker_geometry as tg
+    gd = load_golden("ts_bias")
+    boxes, cams, objs = gd["boxes"], gd["cams"], gd["objs"]
+    ts = [float(t) for t in gd["timestamps"]]
+    for tag, view in (("both", objs), ("eastbound_only", objs[objs[:, 5] == 1])):
+        for put in (lambda t: t.cuda(), lambda t: t):
+            bias = [0, 0, 0, 0]
+            assert tg.estimate_ts_bias(put(boxes), put(cams), put(view), ts, bias, 105.0, 0.1, 0.05) is bias
+            assert bias == gd[f"bias1_{tag}"].tolist(), tag
+            ts2 = [t + 1 / 30.0 + 0.001 * k for k, t in enumerate(ts)]
+            tg.estimate_ts_bias(put(boxes), put(cams), put(view), ts2, bias, 105.0, 0.1, 0.05)
+            assert bias == gd[f"bias2_{tag}"].tolist(), tag
+    bias = [0.5, 0.25]
+    assert tg.estimate_ts_bias(boxes[:0], cams[:0], objs, ts, bias, 105.0) == [0.5, 0.25]   # no detections: untouched
+    assert tg.estimate_ts_bias(boxes, cams, objs[:0], ts, bias, 105.0) == [0.5, 0.25]       # empty filter: untouched
+
+
+@pytest.mark.parametrize("graph", [True, False])
+def test_frame_geometry_equals_separate_calls_and_oracle(graph):
+    from geom3d_b200 import ops, tracker_geometry as tg
+    from oracle import homography_oracle as ho, tracker_oracle as to
+    P, _ = synth.camera_matrices(6)
+    Pd = torch.from_numpy(P).cuda()
+    frame = tg.FrameGeometry(Pd, capacity_pre=640, capacity_det=700, phi_space=0.1, phi_im=0.3, graph=graph)
+    for k, (n_pre, n_det) in enumerate(((500, 700), (640, 300), (37, 41), (1, 1), (300, 0), (0, 129), (600, 699))):
+        g = synth.gen(700 + k)
+        det, cam = synth.vehicle_states(n_det, g, n_cams=6)
+        det[:, 0] = 100 + torch.rand(n_det, generator=g) * 900                 # dense enough for both NMS to bite
+        pre = det[torch.randint(0, max(n_det, 1), (n_pre,), generator=g)].clone() if n_det else synth.vehicle_states(n_pre, g)[0]
+        pre[:, :2] += torch.randn(n_pre, 2, generator=g) * torch.tensor([3.0, 0.5])
+        sc = torch.rand(n_det, generator=g)
+        out = frame(pre.cuda(), det.cuda(), sc.cuda(), cam.cuda())
+        assert out["cost"].shape == (n_pre, n_det)
+        if n_det == 0:
+            assert out["space_keep"].numel() == 0 and out["im_keep"].numel() == 0 and out["corners"].shape == (0, 8, 2)
+            continue
+        # the separate drop-in calls
+        assert torch.equal(out["space_keep"], tg.space_nms(det.cuda(), sc.cuda(), 0.1)), (k, "space")
+        corners = ops.state_to_im(det.cuda(), Pd, cam.cuda(), wrapper=True)
+        assert torch.equal(out["corners"], corners)
+        assert torch.equal(out["im_keep"], tg.im_nms(corners, sc.cuda(), 0.3)), (k, "im")
+        if n_pre and n_det:
+            assert torch.equal(out["cost"], tg.association_cost(pre.cuda(), det.cuda()))
+        # the oracle
+        if n_pre and n_det and k < 3:
+            assert torch.equal(out["cost"].cpu(), to.association_cost(pre, det))
+            assert torch.equal(out["space_keep"].cpu(), to.space_nms(det, sc, 0.1))
+            Pc = torch.from_numpy(P)[cam.long()]
+            assert torch.equal(out["im_keep"].cpu(), to.im_nms(ho.wrapper_state_to_im(det, Pc[:, 0], Pc[:, 1]), sc, 0.3))
+    with pytest.raises(ValueError):
+        frame(torch.zeros(641, 6).cuda(), torch.zeros(1, 6).cuda(), torch.zeros(1).cuda(), torch.zeros(1).cuda())

@@ -204,3 +204,17 @@ def test_anchors_oracle_and_host_generator_equal_reference_tables():
             assert hashlib.sha256(np.ascontiguousarray(table).tobytes()).digest() == gd[f"sha256_{h}x{w}"].tobytes(), (h, w)
             if f"anchors_{h}x{w}" in gd.files:
                 assert np.array_equal(table, gd[f"anchors_{h}x{w}"])
+
+
+def test_estimate_ts_bias(golden):
+    """MC3D_crop_tracker.py:237-315: the oracle's bias lists equal the unmodified method's, call after call"""
+    gd = golden("ts_bias")
+    boxes, cams, objs = gd["boxes"], gd["cams"], gd["objs"]
+    ts = [float(t) for t in gd["timestamps"]]
+    assert tracker_oracle.cross_camera_pairs(boxes, cams, 0.1).shape[0] > 20
+    for tag, view in (("both", objs), ("eastbound_only", objs[objs[:, 5] == 1])):
+        b1 = tracker_oracle.estimate_ts_bias(boxes, cams, view, ts, [0, 0, 0, 0], 105.0, 0.1, 0.05)
+        assert b1 == gd[f"bias1_{tag}"].tolist(), tag
+        ts2 = [t + 1 / 30.0 + 0.001 * k for k, t in enumerate(ts)]
+        b2 = tracker_oracle.estimate_ts_bias(boxes, cams, view, ts2, b1, 105.0, 0.1, 0.05)
+        assert b2 == gd[f"bias2_{tag}"].tolist(), tag
