@@ -380,6 +380,124 @@ __global__ void __launch_bounds__(32) nms_mask_scan_kernel(const uint64_t* __res
     if (lane == 0) keep_count[0] = total;
 }
 
+// Up to 64 blocks (n <= 4096): the scan above spends its time waiting - a 64-step shuffle chain per block, then
+// dependent L2 loads of the kept rows' words.  Here warps 1-3 copy the whole 64-row strip of the NEXT block into shared
+// memory while warp 0 - the only serial actor, so every instruction it does not execute is time saved -
+// resolves the current block from shared memory: the 64 diagonal words are broadcast reads at immediate offsets (the
+// strip's row stride SW is a compile-time constant), the chain tests one bit and ORs one word per row, and the kept
+// rows (compacted into a small index list) OR their words into the running "removed" set with one conflict-free read
+// per lane.  Same pair tests, same order, same keep list.
+template <int WPL>   // 64-bit words of the removed set per lane: blocks <= 32 * WPL
+__global__ void __launch_bounds__(128) nms_mask_scan_strip_kernel(const uint64_t* __restrict__ mask,
+                                                                  const int32_t* __restrict__ sidx_all,
+                                                                  const int32_t* __restrict__ seg, int nbs, int relative,
+                                                                  int64_t* __restrict__ keep_all,
+                                                                  int32_t* __restrict__ keep_count) {
+    constexpr int SW = 32 * WPL;                                // strip row stride in words
+    extern __shared__ __align__(16) uint64_t strip[];          // [2][64][SW]
+    __shared__ int kept_rows[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int off = seg[0], n = seg[1] - off;
+    const int nb = (n + 63) >> 6;
+    const int32_t* __restrict__ sidx = sidx_all + off;
+    int64_t* __restrict__ keep_out = keep_all + off;
+    const int add = relative ? 0 : off;
+    // words [blk & ~1, nb) of the block's valid rows, by warps 1-3: every 16-byte piece is an independent load held in
+    // registers, then stored (cp.async issues at ~200 cycles per instruction here and would be the critical path)
+    auto stage = [&](int blk) {
+        constexpr int CH = SW / 2, U = (64 * CH + 95) / 96;     // pieces per row, pieces per helper thread
+        const int base = blk << 6, w0 = blk & ~1;
+        const int rows = min(64, n - base), chunks = (nb - w0 + 1) >> 1;
+        uint64_t* dst = strip + (size_t)(blk & 1) * 64 * SW + w0;
+        const uint64_t* src = mask + (int64_t)base * nbs + w0;
+        const int t = tid - 32;
+        uint4 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int u = t + 96 * k, r = u / CH, c = u % CH;
+            if (u < 64 * CH && r < rows && c < chunks) v[k] = __ldcg(reinterpret_cast<const uint4*>(src + (int64_t)r * nbs + 2 * c));
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int u = t + 96 * k, r = u / CH, c = u % CH;
+            if (u < 64 * CH && r < rows && c < chunks) *reinterpret_cast<uint4*>(dst + r * SW + 2 * c) = v[k];
+        }
+    };
+    if (nb > 0 && warp != 0) stage(0);
+    uint64_t r0 = 0ull, r1 = 0ull;                              // removed-set words lane and lane + 32 (warp 0)
+    int total = 0;
+    int sA = (lane < n) ? sidx[lane] : 0, sB = (lane + 32 < n) ? sidx[lane + 32] : 0;
+    __syncthreads();
+    for (int blk = 0; blk < nb; ++blk) {
+        if (warp != 0) {
+            if (blk + 1 < nb) stage(blk + 1);
+        } else {
+            const int base = blk << 6;
+            const int m = min(64, n - base);
+            const uint64_t mmask = (m == 64) ? ~0ull : ((1ull << m) - 1ull);
+            const uint64_t* __restrict__ S = strip + (size_t)(blk & 1) * 64 * SW;
+            const int tA = sA, tB = sB;
+            if (blk + 1 < nb) {                                 // original indices of the next block, one block ahead
+                const int ra = base + 64 + lane, rb = ra + 32;
+                sA = (ra < n) ? sidx[ra] : 0;
+                sB = (rb < n) ? sidx[rb] : 0;
+            }
+            uint64_t rem = shfl64((WPL == 1 || blk < 32) ? r0 : r1, blk & 31);
+            if ((rem & mmask) != mmask) {
+                // 64 independent broadcast reads first, then the chain: test bit i, OR the row's diagonal word
+                const uint64_t* __restrict__ dg = S + blk;
+                uint64_t d[64];
+                if (m == 64) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) d[i] = dg[i * SW];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) d[i] = (i < m) ? dg[i * SW] : 0ull;
+                }
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (!((rem >> i) & 1ull)) rem |= d[i];
+            }
+            const uint64_t keep = ~rem & mmask;
+            const int kept = __popcll(keep);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = lane + 32 * half;
+                if ((keep >> i) & 1ull) {
+                    const int pos = __popcll(keep & ((1ull << i) - 1ull));
+                    keep_out[total + pos] = (half ? tB : tA) + add;
+                    kept_rows[pos] = i * SW;
+                }
+            }
+            total += kept;
+            __syncwarp();
+            // the kept rows suppress later blocks: OR their words into the removed set, 8 independent reads at a time
+            if (blk + 1 < nb) {
+                const uint64_t* __restrict__ mine = S + lane;
+                const bool u0 = lane > blk && lane < nb, u1 = WPL > 1 && lane + 32 > blk && lane + 32 < nb;
+                for (int k0 = 0; k0 < kept; k0 += 8) {
+                    uint64_t v0[8], v1[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const bool have = k0 + k < kept;
+                        const int ro = have ? kept_rows[k0 + k] : 0;
+                        v0[k] = (have && u0) ? mine[ro] : 0ull;
+                        v1[k] = (WPL > 1 && have && u1) ? mine[ro + 32] : 0ull;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        r0 |= v0[k];
+                        if (WPL > 1) r1 |= v1[k];
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    if (tid == 0) keep_count[0] = total;
+}
+
 struct NmsWorkspace {
     int32_t* sidx;
     float4* sbox;
@@ -408,7 +526,7 @@ static NmsWorkspace carve_nms(void* base, int64_t N, int64_t S, int64_t max_seg_
     w.mask = nullptr;
     if (use_mask_path(S, max_seg_len, N)) {
         w.mask = (uint64_t*)(p + off);
-        off += align_up(max_seg_len * ceil_div(max_seg_len, 64) * 8, 256);
+        off += align_up(max_seg_len * align_up(ceil_div(max_seg_len, 64), 2) * 8, 256);   // row stride: even word count
     }
     w.single = (int32_t*)(p + off);   // {0, N} for callers that pass seg_offsets == NULL with S == 1
     off += 256;
@@ -503,12 +621,20 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
     }
     if (use_mask_path(S, max_seg_len, N)) {
         const int nb = (int)ceil_div(N, 64);      // capacity: the segment's own length is read from seg_offsets on the device
-        nms_mask_kernel<<<dim3((unsigned)nb, (unsigned)nb), 64, 0, st>>>(w.sbox, seg_offsets, nb, thr_f, w.mask);
+        const int nbs = (int)align_up(nb, 2);     // row stride of the bit-matrix (rows start 16-byte aligned)
+        nms_mask_kernel<<<dim3((unsigned)nb, (unsigned)nb), 64, 0, st>>>(w.sbox, seg_offsets, nbs, thr_f, w.mask);
         G3D_LAUNCH_CHECK();
-        if (nb <= 32)       nms_mask_scan_kernel<1><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
-        else if (nb <= 64)  nms_mask_scan_kernel<2><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
-        else if (nb <= 128) nms_mask_scan_kernel<4><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
-        else                nms_mask_scan_kernel<8><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nb, relative, keep_out, keep_count);
+        if (nb <= 64) {
+            const size_t smem = (size_t)2 * 64 * (nb <= 32 ? 32 : 64) * 8;   // two strips of 64 rows x SW words
+            if (nb <= 32) {
+                nms_mask_scan_strip_kernel<1><<<1, 128, smem, st>>>(w.mask, w.sidx, seg_offsets, nbs, relative, keep_out, keep_count);
+            } else {
+                G3D_CUDA(cudaFuncSetAttribute(nms_mask_scan_strip_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                nms_mask_scan_strip_kernel<2><<<1, 128, smem, st>>>(w.mask, w.sidx, seg_offsets, nbs, relative, keep_out, keep_count);
+            }
+        }
+        else if (nb <= 128) nms_mask_scan_kernel<4><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nbs, relative, keep_out, keep_count);
+        else                nms_mask_scan_kernel<8><<<1, 32, 0, st>>>(w.mask, w.sidx, seg_offsets, nbs, relative, keep_out, keep_count);
         G3D_LAUNCH_CHECK();
         return G3D_OK;
     }

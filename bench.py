@@ -301,21 +301,32 @@ def other_workloads(dev, hbm_peak):
 
     def frame():
         cost = tracker_geometry.association_cost(s5, j5)
-        k1 = tracker_geometry.space_nms(s5, sc5, 0.1)
-        corners = ops.state_to_im(s5, Pd, c5, wrapper=True)
+        k1 = tracker_geometry.space_nms(j5, sc5, 0.1)          # NMS runs on the detections, the cost is tracked x detected
+        corners = ops.state_to_im(j5, Pd, c5, wrapper=True)
         k2 = tracker_geometry.im_nms(corners, sc5, 0.3)
         return cost, k1, k2
     t_frame = timed(frame, 10)
+    # the same frame as ONE CUDA graph (tracker_geometry.FrameGeometry: three forked streams, device-side lengths,
+    # one 8-byte read of the two keep-list lengths per frame); inputs already on the device
+    fg = tracker_geometry.FrameGeometry(Pd, 2000, 2000, phi_space=0.1, phi_im=0.3)
+    ref_frame = frame()
+    got_frame = fg(s5, j5, sc5, c5)
+    assert torch.equal(got_frame["cost"], ref_frame[0]) and torch.equal(got_frame["space_keep"], ref_frame[1]) \
+        and torch.equal(got_frame["im_keep"], ref_frame[2]), "graph frame differs from the separate calls"
+    t_graph = timed(lambda: fg(s5, j5, sc5, c5), 10)
     s5h, j5h, sc5h = s5.cpu(), j5.cpu(), sc5.cpu()
     P5 = torch.from_numpy(P)[c5.cpu().long()]
     t0 = time.perf_counter()
     tracker_oracle.association_cost(s5h, j5h)
-    tracker_oracle.space_nms(s5h, sc5h, 0.1)
-    tracker_oracle.im_nms(homography_oracle.wrapper_state_to_im(s5h, P5[:, 0], P5[:, 1]), sc5h, 0.3)
+    tracker_oracle.space_nms(j5h, sc5h, 0.1)
+    tracker_oracle.im_nms(homography_oracle.wrapper_state_to_im(j5h, P5[:, 0], P5[:, 1]), sc5h, 0.3)
     t_cpu5 = time.perf_counter() - t0
     out.append({"workload": "config 5: 2000 objects: footprint association matrix (f64) + space NMS 0.1 + image NMS 0.3",
-                "metric": "tracking-frame geometry frames/s", "value": 1e3 / t_frame, "unit": "frames/s",
-                "ms": {"frame": t_frame}, "note": "launch/latency bound (SURVEY.md §8d); includes 2 host syncs for the NMS lengths",
+                "metric": "tracking-frame geometry frames/s", "value": 1e3 / t_graph, "unit": "frames/s",
+                "ms": {"frame (one CUDA graph, FrameGeometry)": t_graph, "frame (separate drop-in calls)": t_frame},
+                "separate_calls_frames_per_s": 1e3 / t_frame,
+                "note": "launch/latency bound (SURVEY.md §8d); graph frame: 5 small input copies + one graph launch + one "
+                        "8-byte read of the keep-list lengths; separate calls: 2 host syncs for the NMS lengths",
                 "cpu_baseline": {"value": 1.0 / t_cpu5, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                                  "sample": f"one frame (oracle association_cost + space_nms + state_to_im + im_nms, {t_cpu5:.2f} s)"}})
     # ---- batched Kalman filter (Torch_KF.predict with per-object dt + update of every object)
