@@ -74,6 +74,49 @@ __global__ void __launch_bounds__(THREADS) seg_sort_kernel(const float* __restri
     }
 }
 
+// ---- one segment of up to kRankCap boxes, sorted by RANK: the keys (score descending, index ascending on ties) are
+// distinct, so the sorted position of element i is the number of elements before it.  Each thread counts them over all
+// n scores held in shared memory as monotone 32-bit words (broadcast 16-byte reads, no barrier inside the loops):
+// score_j >= score_i for the j below its warp's 32 indices, score_j > score_i above, the exact tie rule inside.  n^2
+// 32-bit compares spread over n/128 CTAs where the one-CTA bitonic network needs 66 barrier-separated steps.
+constexpr int kRankCap = 4096;
+__device__ __forceinline__ uint32_t score_word(float score) { return (uint32_t)(make_key(score, 0u) >> 32); }   // ascending = better
+__global__ void __launch_bounds__(128) rank_sort_kernel(const float* __restrict__ scores,
+                                                        const int32_t* __restrict__ seg,
+                                                        const float* __restrict__ boxes, int64_t stride, int64_t col,
+                                                        int32_t* __restrict__ sidx, float4* __restrict__ sbox) {
+    __shared__ __align__(16) uint32_t keys[kRankCap];
+    const int off = seg[0], n = seg[1] - off;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const int n4 = (n + 3) & ~3;
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) keys[j] = (j < n) ? score_word(__ldg(scores + off + j)) : 0xffffffffu;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float4 box = (i < n) ? load_box(boxes, stride, col, (int64_t)off + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (i >= n) return;
+    const uint32_t mine = keys[i];
+    const int wbase = i & ~31;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    int rank = 0;
+#pragma unroll 4
+    for (int j = 0; j < (wbase >> 2); ++j) {                    // earlier indices win ties
+        const uint4 k = k4[j];
+        rank += (k.x <= mine) + (k.y <= mine) + (k.z <= mine) + (k.w <= mine);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {                              // the warp's own 32 indices
+        const uint32_t k = keys[min(wbase + j, n4 - 1)];
+        rank += (wbase + j < n) && (k < mine || (k == mine && wbase + j < i));
+    }
+#pragma unroll 4
+    for (int j = (wbase + 32) >> 2; j < (n4 >> 2); ++j) {       // later indices lose ties (the 0xffffffff padding never counts)
+        const uint4 k = k4[j];
+        rank += (k.x < mine) + (k.y < mine) + (k.z < mine) + (k.w < mine);
+    }
+    sidx[off + rank] = i;
+    sbox[off + rank] = box;
+}
+
 // ---- multi-CTA sort for one long segment (S == 1): keys in global memory, padded to a power of two
 __global__ void __launch_bounds__(256) keys_init_kernel(const float* __restrict__ scores, int n, int P,
                                                         uint64_t* __restrict__ keys) {
@@ -580,7 +623,11 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
     // many segments: short ones (<= kShortSeg boxes) on small CTAs, several per SM; the rest on 1024-thread CTAs
     const bool two_size = (S >= 64) && (max_seg_len > kShortSeg);
     const bool all_short = (S >= 64) && (max_seg_len <= kShortSeg);
-    if (max_seg_len <= kSortCap) {
+    if (use_mask_path(S, max_seg_len, N) && N <= kRankCap) {
+        rank_sort_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(scores, seg_offsets, boxes, box_stride, box_col, w.sidx,
+                                                                   w.sbox);
+        G3D_LAUNCH_CHECK();
+    } else if (max_seg_len <= kSortCap) {
         int P = 2;
         while (P < max_seg_len) P <<= 1;
         const size_t smem = (size_t)P * 8;

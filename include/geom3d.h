@@ -237,8 +237,10 @@ int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_count, cons
  * seg_offsets is a DEVICE int32 array of S+1 entries (NULL is allowed for S == 1: one segment [0, N)); max_seg_len is a
  * host upper bound of the longest segment.
  * Three execution shapes, one result: many short segments (S >= 64) run one 256-thread CTA per segment; a single
- * segment of 256..16384 boxes (the trackers' calls) builds a 64x64-block suppression bit-matrix with the whole GPU and
- * scans it with one warp; everything else runs the one-CTA-per-segment greedy pass.
+ * segment with capacity max_seg_len == N of 256..16384 boxes (the trackers' calls) is rank-sorted (N <= 4096), builds a
+ * 64x64-block suppression bit-matrix with the whole GPU and scans it with one warp fed from shared memory; everything
+ * else runs the one-CTA-per-segment greedy pass.  The segment bounds are always read on the device, so a captured
+ * launch sequence (CUDA graph) with S == 1 and seg_offsets = {lo, hi} serves any hi - lo <= N.
  */
 int64_t g3d_nms_workspace_bytes(int64_t N, int64_t S, int64_t max_seg_len);
 int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t box_col, const float* scores, int64_t N,
