@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __res
     __shared__ float4 kbox[64];
     __shared__ float karea[64];
     __shared__ uint64_t s_keep;
+    __shared__ int dsrc[64];
 
     const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool thr_nonneg = thr >= 0.0f;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __res
             const float4 b = bsrc[base + tid];
             dbox[tid] = b;
             darea[tid] = box_area_rn(b.x, b.y, b.z, b.w);
+            dsrc[tid] = sidx[off + base + tid];     // original indices: fetched here, off the serial section below
         }
         __syncthreads();
         // 64x64 strictly-upper-triangular suppression bits: 16 lanes per row, lane l16 covers columns l16 + 16q
@@ -267,12 +269,17 @@ __global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __res
         }
         __syncthreads();
         if (warp == 0) {
-            const uint64_t dA = diag[lane], dB = diag[lane + 32];
+            // the serial part: 64 independent broadcast reads, then test bit i / OR word i (3 dependent instructions
+            // per row; a shuffle per row costs several times that)
             uint64_t rem = remword;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const uint64_t d = shfl64(i < 32 ? dA : dB, i & 31);
-                if (!((rem >> i) & 1ull)) rem |= d;
+            for (int g = 0; g < 4; ++g) {          // 16 rows at a time (the 1024-thread variant has 64 registers)
+                uint64_t d[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[i] = diag[16 * g + i];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (!((rem >> (16 * g + i)) & 1ull)) rem |= d[i];
             }
             const uint64_t keep = ~rem & mmask;
             if (lane == 0) s_keep = keep;
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(THREADS) nms_greedy_kernel(const float4* __res
                     const int pos = __popcll(keep & ((1ull << i) - 1ull));
                     kbox[pos] = dbox[i];
                     karea[pos] = darea[i];
-                    const int64_t src = sidx[off + base + i];
+                    const int64_t src = dsrc[i];
                     keep_out[off + total_kept + pos] = relative ? src : src + off;
                 }
             }
