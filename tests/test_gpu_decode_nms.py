@@ -65,13 +65,14 @@ def test_nms_golden(golden):
     assert pp.batched_nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0).long().cuda(), 0.5).numel() == 0
 
 
-@pytest.mark.parametrize("N", [1, 2, 63, 64, 65, 200, 1000, 5000, 9000, 20000])
+@pytest.mark.parametrize("N", [1, 2, 63, 64, 65, 200, 255, 256, 1000, 2048, 2049, 3000, 4096, 4097, 5000, 9000, 20000])
 def test_nms_sizes_vs_oracle(N):
-    """block edges of the 64-wide greedy pass, the shared-memory box cache limit (8192), and the global sort (> 16384)"""
+    """block edges of the 64-wide greedy pass, the bit-matrix path (>= 256) with its rank sort / strip scan (<= 2048 one
+    removed-set word per lane, <= 4096 two) and the shuffle scan above, the global sort (> 16384)"""
     ops, _ = _mods()
     from oracle import nms_oracle
     b, s = synth.clustered_boxes(N, synth.gen(N))
-    s = (s * 50).round() / 50 if N <= 5000 else s        # ties for the smaller cases
+    s = (s * 50).round() / 50 if N <= 5000 else s        # ties for the smaller cases (rank sort: index order on ties)
     for thr in (0.5, 0.2):
         assert torch.equal(ops.nms(b.cuda(), s.cuda(), thr).cpu(), nms_oracle.nms(b, s, thr)), (N, thr)
 
@@ -92,7 +93,7 @@ def test_nms_segmented_matches_per_segment():
         assert torch.equal(keep[o:o + exp.numel()], exp), f"segment {i}"
 
 
-@pytest.mark.parametrize("cap", [100, 2000, 5000])
+@pytest.mark.parametrize("cap", [100, 2000, 3000, 5000])
 def test_nms_single_segment_with_device_side_length(cap):
     """one segment whose bounds live on the device (capacity = buffer size, length read by the kernels): what a captured
     launch sequence replays for a varying number of boxes; bit-matrix path (cap >= 256) and greedy path (cap < 256)"""
