@@ -307,6 +307,28 @@ struct AssignCodesArgs {
     int B, A, Gmax, R;
 };
 
+// One-lane atomics as single instructions.  `if (lane == 0) atomicAdd(...)` makes nvcc wrap the call in its warp-aggregation
+// pattern (vote, leader election, popc, shuffle: ~15 instructions around one ATOMS), which at one ticket per 32-anchor
+// unit was 15 % of this issue-bound kernel's instructions.
+// The address is made lane-dependent in a way the compiler cannot fold (offset zero for lane 0, the one lane that executes
+// it; %laneid read through asm): ptxas then emits the bare ATOMS / ATOMG instead of its aggregation sequence.
+__device__ __forceinline__ int lane0_atomic_add_shared(int* addr, int v, int lane) {
+    int old;
+    unsigned l2;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l2));          // opaque to the front end: not folded under `lane == 0`
+    (void)lane;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(addr) + (l2 ? 4u : 0u);
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ int lane0_atomic_add_global(int* addr, int v) {
+    int old;
+    unsigned l2;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l2));
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr + (l2 ? 1 : 0)), "r"(v) : "memory");
+    return old;
+}
+
 struct StageSmem {
     float4 box[kImgPerCta][kTile];
     int idx[kImgPerCta][kTile];
@@ -438,7 +460,7 @@ __device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem&
 #pragma unroll
         for (int j = 0; j < kStageGroup; ++j) {
             base[j] = 0;
-            if (lane == 0 && bal[j]) base[j] = atomicAdd(&sm.total[i0 + j], __popc(bal[j]));
+            if (lane == 0 && bal[j]) base[j] = lane0_atomic_add_shared(&sm.total[i0 + j], __popc(bal[j]), lane);
         }
 #pragma unroll
         for (int j = 0; j < kStageGroup; ++j) {
@@ -460,7 +482,7 @@ __device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem&
 #pragma unroll 1
     for (;;) {
         int u = 0;
-        if (lane == 0) u = atomicAdd(&sm.next_unit, 1);
+        if (lane == 0) u = lane0_atomic_add_shared(&sm.next_unit, 1, lane);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= nunits) break;
         const int i = u / kWarps, slice = u - i * kWarps;
@@ -536,7 +558,7 @@ __device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem&
         const unsigned posmask = __ballot_sync(0xffffffffu, is_pos);
         if (posmask) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(p.npos + b, __popc(posmask));
+            if (lane == 0) base = lane0_atomic_add_global(p.npos + b, __popc(posmask));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (is_pos) p.pos_list[(int64_t)b * p.A + base + __popc(posmask & ((1u << lane) - 1u))] = a;
         }
