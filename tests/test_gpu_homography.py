@@ -140,3 +140,44 @@ def test_full_size_tracking_frame_properties():
     keep = tg.space_nms(st.cuda(), sc, 0.1)
     again = tg.space_nms(st.cuda()[keep], sc[keep], 0.1)
     assert torch.equal(again, torch.arange(keep.numel(), device="cuda"))
+
+
+def test_full_size_homography_properties_10M():
+    """BASELINE config 4: 10 M states over 18 cameras.  Too large for the oracle as a whole, so: (1) 4000 sampled rows
+    (incl. the first and the last 64) of state_to_im against the oracle, (2) the state -> image -> state round trip of ALL
+    rows (homography.py:554-604's own property), (3) the refined two-pass transform returns the heights it was given when
+    the template is the box itself"""
+    from geom3d_b200 import ops
+    from oracle import homography_oracle as ho
+    P, H = synth.camera_matrices(18)
+    Pd, Hd = torch.from_numpy(P).cuda(), torch.from_numpy(H).cuda()
+    g = synth.gen(44)
+    d = 10_000_000
+    st, cam = synth.vehicle_states(d, g)
+    std, camd = st.cuda(), cam.cuda()
+    im = ops.state_to_im(std, Pd, camd, wrapper=True)
+    assert im.shape == (d, 8, 2) and im.dtype == torch.float64 and bool(torch.isfinite(im).all())
+    rows = torch.cat((torch.arange(64), torch.randint(64, d - 64, (3872,), generator=g), torch.arange(d - 64, d)))
+    Pl = torch.from_numpy(P)[cam[rows].long()]
+    assert_close_rel(im[rows.cuda()].cpu(), ho.wrapper_state_to_im(st[rows], Pl[:, 0], Pl[:, 1]), TOL, "sampled rows vs oracle")
+    del im
+    # one correspondence per camera (Homography): the round trip holds for every row
+    im1 = ops.state_to_im(std, Pd, camd, wrapper=False)
+    back = ops.im_to_state(im1, std[:, 4].contiguous(), Hd, camd, wrapper=False)
+    assert back.shape == (d, 6) and torch.equal(back[:, 5], std[:, 5])
+    err = ((back[:, :4] - std[:, :4]).abs() / std[:, :4].abs().clamp_min(1.0)).amax()
+    assert float(err) < 1e-4, f"round trip of x, y, l, w: worst relative error {float(err):.3e}"
+    assert float((back[:, 4] - std[:, 4]).abs().amax()) < 1e-4
+    n2 = 1_000_000
+    ref_state, heights = ops.im_to_state_refined(im1[:n2], std[:n2, 4].contiguous(), Hd, Pd, camd[:n2], wrapper=False,
+                                                 return_heights=True)
+    assert float((heights.float() - std[:n2, 4]).abs().amax()) < 1e-3
+    assert float(((ref_state[:, :4] - std[:n2, :4]).abs() / std[:n2, :4].abs().clamp_min(1.0)).amax()) < 1e-3
+    del im1
+    # the two-correspondence wrapper picks a side of the roadway by y > 60 (homography.py:840-856, on different points
+    # in the two directions), so its round trip holds away from that line
+    imw = ops.state_to_im(std[:n2], Pd, camd[:n2], wrapper=True)
+    backw = ops.im_to_state(imw, std[:n2, 4].contiguous(), Hd, camd[:n2], wrapper=True)
+    far = (std[:n2, 1] - 60.0).abs() > 12.0
+    errw = ((backw[:, :4] - std[:n2, :4]).abs() / std[:n2, :4].abs().clamp_min(1.0))[far].amax()
+    assert int(far.sum()) > n2 // 2 and float(errw) < 1e-4, f"wrapper round trip: {float(errw):.3e}"
