@@ -79,6 +79,10 @@ SIGNATURES = {
     "g3d_md_iou": (_int, [_c_ptr, _c_ptr, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_kf_predict": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _f64, _f64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_kf_update": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr]),
+    "g3d_detect_tail_workspace_bytes": (_i64, [_i64, _i64]),
+    "g3d_detect_tail": (_int, [_c_ptr, _i64, _i64, _i64, _i64, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _int, _c_ptr, _c_ptr,
+                               _int, _f32, _f32, _f64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
+                               _c_ptr, _i64, _int, _c_ptr]),
     "g3d_cross_camera_pairs": (_int, [_c_ptr, _c_ptr, _i64, _f64, _c_ptr, _c_ptr, _c_ptr, _i64, _int, _c_ptr]),
     "g3d_generate_anchors": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _c_ptr, _i64, _int, _c_ptr]),
 }

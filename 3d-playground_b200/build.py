@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libgeom3d.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 
 SOURCES = ["core.cu", "iou_assign.cu", "focal_loss.cu", "decode.cu", "filter.cu", "nms.cu", "homography.cu",
-           "pairwise.cu", "kf.cu", "anchors.cu"]
+           "pairwise.cu", "kf.cu", "anchors.cu", "detect_tail.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -389,17 +389,64 @@ def gather_candidates_decoded(scores, outer, inner, N, outer_pitch, idx, count, 
     return seg_offsets, cand_scores, cand_boxes, cand_src
 
 
+def detect_tail(scores, outer, inner, N, outer_pitch, thr, cap, anchors, regression, iou_threshold, mean=None, std=None,
+                clip_wh=None):
+    """filter_compact -> gather_candidates_decoded -> nms_segmented(relative=False) -> detection_offsets in ONE library
+    call (g3d_detect_tail: the ~10 short launches are issued from C++ back to back).  Returns a dict with count,
+    seg_offsets, cand_scores, cand_src, keep, keep_count, out_offsets and summary i32[2] = (detections, max count)."""
+    dev = _need_cuda(scores, thr, anchors, regression)
+    if scores.dtype != torch.float32 or not scores.is_contiguous():
+        raise Geom3dError("detect_tail needs a contiguous float32 score tensor")
+    anc, reg, variant, mean_h, std_h, clip, cw, ch = _decode_args(anchors, regression, mean, std, clip_wh)
+    thr = _prep(thr, torch.float32)
+    S = outer * inner
+    T = S * cap
+    L = _lib.lib()
+    # one int32 block for the small arrays and the candidate tables, one int64 keep list, one workspace
+    small = torch.empty((4 * S + 4 + 2 * T + 64,), dtype=torch.int32, device=dev)
+    o = 0
+    count = small[o:o + S]; o += S
+    keep_count = small[o:o + S]; o += S
+    seg_offsets = small[o:o + S + 1]; o += S + 1
+    out_offsets = small[o:o + S + 1]; o += S + 1
+    summary = small[o:o + 2]; o += 2
+    o = (o + 3) & ~3                                        # 16-byte alignment of the two tables
+    cand_src = small[o:o + T]; o += T
+    o = (o + 3) & ~3
+    cand_scores = small[o:o + T].view(torch.float32)
+    keep = torch.empty((T,), dtype=torch.int64, device=dev)
+    ws = _workspace(L.g3d_detect_tail_workspace_bytes(S, cap), dev)
+    check(L.g3d_detect_tail(_p(scores), outer, inner, N, outer_pitch, _p(thr), cap, _p(anc), anc.shape[0], _p(reg), variant,
+                            mean_h, std_h, clip, cw, ch, float(iou_threshold), _p(count), _p(seg_offsets), _p(cand_scores),
+                            _p(cand_src), _p(keep), _p(keep_count), _p(out_offsets), _p(summary), _p(ws), ws.numel(),
+                            _idx(dev), _stream(dev)), "g3d_detect_tail")
+    return dict(count=count, seg_offsets=seg_offsets, cand_scores=cand_scores, cand_src=cand_src, keep=keep,
+                keep_count=keep_count, out_offsets=out_offsets, summary=summary)
+
+
+def detection_offsets(keep_count):
+    """out_offsets i32[S+1] = exclusive scan of the per-segment keep counts (out_offsets[S] = number of detections)."""
+    dev = _need_cuda(keep_count)
+    S = keep_count.numel()
+    out_offsets = torch.empty((S + 1,), dtype=torch.int32, device=dev)
+    check(_lib.lib().g3d_exclusive_scan_i32(_p(keep_count), S, _p(out_offsets), _idx(dev), _stream(dev)),
+          "g3d_exclusive_scan_i32")
+    return out_offsets
+
+
 def assemble_detections(keep, keep_count, seg_offsets, cand_scores, cand_src, outer, inner, N, anchors, regression,
-                        mean=None, std=None, clip_wh=None):
+                        mean=None, std=None, clip_wh=None, out_offsets=None, K=None):
     """Final (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K]) from the per-segment keep lists of
-    nms_segmented(relative=False): one scan, ONE 4-byte device->host read (K), one assembly launch."""
+    nms_segmented(relative=False): one scan, ONE 4-byte device->host read (K), one assembly launch.  A caller that
+    pipelines several batches passes out_offsets (detection_offsets) and K once it has read it."""
     dev = _need_cuda(keep, keep_count, seg_offsets, cand_scores, cand_src, anchors, regression)
     anc, reg, variant, mean_h, std_h, clip, cw, ch = _decode_args(anchors, regression, mean, std, clip_wh)
     S = outer * inner
     L = _lib.lib()
-    out_offsets = torch.empty((S + 1,), dtype=torch.int32, device=dev)
-    check(L.g3d_exclusive_scan_i32(_p(keep_count), S, _p(out_offsets), _idx(dev), _stream(dev)), "g3d_exclusive_scan_i32")
-    K = int(out_offsets[S].item())
+    if out_offsets is None:
+        out_offsets = detection_offsets(keep_count)
+    if K is None:
+        K = int(out_offsets[S].item())
     cols = 20 if variant == VARIANT_3D else 4
     scores = torch.empty((K,), dtype=torch.float32, device=dev)
     classes = torch.empty((K,), dtype=torch.int64, device=dev)

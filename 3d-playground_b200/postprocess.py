@@ -145,36 +145,61 @@ def detect_per_class(classification, boxes, box_col=0, score_threshold=None, lad
     return scores, classes, out_boxes, image_index
 
 
+_TAIL_HOST = {}
+
+
+def _tail_launch(cls, regression, anchors, score_threshold, ladder_start, keep_max, iou_threshold, cap, mean, std, clip_wh):
+    """everything of the detection tail that needs no host decision, on the current stream; the two integers the host
+    needs (number of detections, largest candidate count) go to pinned memory behind an event"""
+    dev = cls.device
+    B, A, C = cls.shape
+    if ladder_start is not None:
+        _, _, thr = ops.threshold_ladder(cls, B, C, A, A * C, ladder_start, keep_max)
+    else:
+        thr = torch.full((B * C,), float(np.float32(score_threshold)), dtype=torch.float32, device=dev)
+    t = ops.detect_tail(cls, B, C, A, A * C, thr, cap, anchors, regression, iou_threshold, mean, std, clip_wh)
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.index, stream.cuda_stream)
+    if key not in _TAIL_HOST:                                # one pinned pair + event per stream, reused (each call
+        _TAIL_HOST[key] = (torch.empty(2, dtype=torch.int32).pin_memory(), torch.cuda.Event())   # ends with its own wait)
+    host, done = _TAIL_HOST[key]
+    host.copy_(t["summary"], non_blocking=True)
+    done.record(stream)
+    t.update(B=B, A=A, C=C, regression=regression, host=host, done=done, cap=cap)
+    return t
+
+
+def _tail_finish(st, anchors, mean, std, clip_wh):
+    st["done"].synchronize()
+    K, most = int(st["host"][0]), int(st["host"][1])
+    if most > st["cap"]:
+        raise Geom3dError(f"a (image, class) segment has {most} candidates above the score threshold but the candidate "
+                          f"capacity is {st['cap']}; pass a larger `cap` (<= 16384) or raise the threshold")
+    return ops.assemble_detections(st["keep"], st["keep_count"], st["seg_offsets"], st["cand_scores"], st["cand_src"],
+                                   st["B"], st["C"], st["A"], anchors, st["regression"], mean, std, clip_wh,
+                                   out_offsets=st["out_offsets"], K=K)
+
+
 def detect_per_class_fused(classification, regression, anchors, score_threshold=None, ladder_start=None, keep_max=KEEP_MAX,
                            iou_threshold=NMS_IOU, cap=None, mean=None, std=None, clip_wh=None):
     """detect_per_class without the decoded tensor: the score filter runs first, only the candidates' NMS
     boxes and the kept rows are decoded - from regression[B,A,12] (3D directional model: NMS on columns 16..19, 20-column
     rows out) or regression[B,A,4] (2D model: mean / std / optional clip as BBoxTransform + ClipBoxes).
-    Same result, bit for bit, as decode -> detect_per_class; 7 launches and one 4-byte device->host read per batch.
+    Same result, bit for bit, as decode -> detect_per_class.  Everything up to the one host decision (how many rows to
+    allocate) is ONE library call (g3d_detect_tail: ~10 launches issued from C++), then one 8-byte device->host read
+    and the assembly launch.  (Pipelining half-batches on two streams was tried: the sort / NMS chain is latency-bound per
+    segment, so halves take as long as the whole and the pipeline only adds host time - 0.66 ms vs 0.46 ms at B = 64.)
     Returns (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K])."""
     if (score_threshold is None) == (ladder_start is None):
         raise ValueError("give exactly one of score_threshold / ladder_start")
-    dev = classification.device
     cls = ops._prep(classification, torch.float32)
-    B, A, C = cls.shape
-    if ladder_start is not None:
-        _, _, thr = ops.threshold_ladder(cls, B, C, A, A * C, ladder_start, keep_max)
-        cap = min(keep_max, 16384) if cap is None else cap
-    else:
-        thr = torch.full((B * C,), float(np.float32(score_threshold)), dtype=torch.float32, device=dev)
-        cap = 16384 if cap is None else cap
+    reg = ops._prep(regression, torch.float32)
+    A = cls.shape[1]
+    if cap is None:
+        cap = min(keep_max, 16384) if ladder_start is not None else 16384
     cap = int(min(cap, max(A, 1)))
-    idx, count = ops.filter_compact(cls, B, C, A, A * C, thr, cap)
-    seg_offsets, cand_scores, cand_boxes, cand_src = ops.gather_candidates_decoded(
-        cls, B, C, A, A * C, idx, count, cap, anchors, regression, mean, std, clip_wh)
-    keep, keep_count = ops.nms_segmented(cand_boxes, cand_scores, seg_offsets, cap, iou_threshold, 0, relative=False)
-    out = ops.assemble_detections(keep, keep_count, seg_offsets, cand_scores, cand_src, B, C, A, anchors, regression,
-                                  mean, std, clip_wh)
-    # candidate overflow is checked after the fact, on the same synchronisation point the result needs anyway
-    if int(count.max().item()) > cap:
-        raise Geom3dError(f"a (image, class) segment has {int(count.max().item())} candidates above the score threshold but "
-                          f"the candidate capacity is {cap}; pass a larger `cap` (<= 16384) or raise the threshold")
-    return out
+    st = _tail_launch(cls, reg, anchors, score_threshold, ladder_start, keep_max, iou_threshold, cap, mean, std, clip_wh)
+    return _tail_finish(st, anchors, mean, std, clip_wh)
 
 
 def detect_multi_frame(classification, boxes, box_col=16, ladder_start=LADDER_START_MULTI, keep_max=KEEP_MAX,
