@@ -89,3 +89,28 @@ def test_kf_kernels_vs_oracle(S, M):
     Xr, Pr = ko.update(Xr, Pr, rows, z, H, R, mu_R)
     assert_close_rel(Xd.cpu(), Xr, TOL, "X update")
     assert_close_rel(Pd.cpu(), Pr, 5 * TOL, "P update")
+
+
+@pytest.mark.parametrize("S,M", [(6, 5), (5, 3)])
+def test_kf_update_dense_measurement_matrix_vs_oracle(S, M):
+    """a measurement matrix that is not [I | 0] takes the general kernel (the trackers' selection matrices take the
+    specialised one, covered above); both against the oracle"""
+    from geom3d_b200 import ops
+    from oracle import kf_oracle as ko
+    g = synth.gen(300 + S)
+    n, m = 3000, 2000
+    H = torch.zeros(M, S); H[:M, :M] = torch.eye(M)
+    H = H + torch.randn(M, S, generator=g) * 0.2
+    Bm = torch.randn(M, M, generator=g) * 0.2
+    R = Bm @ Bm.t() + torch.eye(M) * 0.8
+    mu_R = torch.randn(M, generator=g) * 0.1
+    Cm = torch.randn(n, S, S, generator=g)
+    P = (Cm @ Cm.transpose(1, 2) + torch.eye(S) * 3.0).float()
+    X = torch.randn(n, S, generator=g) * 20
+    rows = torch.randperm(n, generator=g)[:m]
+    z = torch.randn(m, M, generator=g) * 20
+    Xd, Pd = X.cuda(), P.cuda()
+    ops.kf_update_(Xd, Pd, rows.cuda(), z.cuda(), H, R, mu_R)
+    Xr, Pr = ko.update(X, P, rows, z, H, R, mu_R)
+    assert_close_rel(Xd.cpu(), Xr, TOL, "X update (dense H)")
+    assert_close_rel(Pd.cpu(), Pr, 5 * TOL, "P update (dense H)")
