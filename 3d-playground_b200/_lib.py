@@ -37,10 +37,10 @@ SIGNATURES = {
     "g3d_assign": (_int, [_c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_focal_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "g3d_focal_loss_fwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
-                                  _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _int, _c_ptr]),
+                                  _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_focal_loss_fwd_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
                                       _f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr,
-                                      _int, _c_ptr]),
+                                      _c_ptr, _int, _c_ptr]),
     "g3d_focal_loss_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
                                   _c_ptr, _c_ptr, _int, _f32, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_combine_shard_stats": (_int, [_c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),

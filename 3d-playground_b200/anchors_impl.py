@@ -66,7 +66,9 @@ class Anchors(nn.Module):
                 rows = [(h + 2 ** x - 1) // (2 ** x) for x in self.pyramid_levels]
                 cols = [(w + 2 ** x - 1) // (2 ** x) for x in self.pyramid_levels]
                 shapes = np.stack([_level_shapes(size, ratios, scales) for size in self.sizes])
-                self._cache[key] = ops.generate_anchors(shapes, strides, rows, cols, image.device).unsqueeze(0)
+                table = ops.generate_anchors(shapes, strides, rows, cols, image.device).unsqueeze(0)
+                # host metadata: lets FocalLoss run its GT-centric assignment on this table (ops.anchor_pyramid_of)
+                self._cache[key] = ops.tag_anchor_pyramid(table, rows, cols, strides, shapes)
             else:
                 a = anchors_for_image(h, w, tuple(self.pyramid_levels), ratios, scales, self.strides, self.sizes)
                 self._cache[key] = torch.from_numpy(a).unsqueeze(0)

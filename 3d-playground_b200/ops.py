@@ -5,6 +5,7 @@ torch on the inputs' device, and enqueues the CUDA kernels on torch's current st
 computes on the CPU and nothing falls back: a CPU tensor raises.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -124,6 +125,32 @@ def assign(anchors, annotations, variant=None):
 
 
 # ------------------------------------------------------------------------------------------------ a2-a6: fused loss
+STATS = {"gt_centric_calls": 0, "anchor_centric_calls": 0}   # which assignment path focal_loss_forward took (for tests)
+
+
+def anchor_pyramid_of(anchors):
+    """the pyramid description `Anchors.forward` attaches to its table (None for any other anchor tensor, for a table
+    modified in place since, or with G3D_ASSIGN_GT_CENTRIC=0): float64 array {L, S, L x (rows, cols, stride), L x S x
+    (width, height)} - see g3d_focal_loss_fwd_bwd's pyramid_host"""
+    tag = getattr(anchors, "_g3d_pyramid", None)
+    if tag is None or os.environ.get("G3D_ASSIGN_GT_CENTRIC", "") == "0":
+        return None
+    desc, version = tag
+    return desc if anchors._version == version else None
+
+
+def tag_anchor_pyramid(table, rows, cols, strides, level_shapes):
+    """attach the pyramid description to an anchor table produced by Anchors.forward (host metadata only)"""
+    shp = np.asarray(level_shapes, dtype=np.float64)                       # [L,S,4]
+    L, S = shp.shape[0], shp.shape[1]
+    desc = np.concatenate(([float(L), float(S)],
+                           np.stack((np.asarray(rows, dtype=np.float64), np.asarray(cols, dtype=np.float64),
+                                     np.asarray(strides, dtype=np.float64)), axis=1).reshape(-1),
+                           np.stack((shp[..., 2] - shp[..., 0], shp[..., 3] - shp[..., 1]), axis=2).reshape(-1)))
+    table._g3d_pyramid = (np.ascontiguousarray(desc), table._version)
+    return table
+
+
 def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True, grad_cls_expected=None,
                        trace_events=None, want_shard_stats=False):
     """FocalLoss forward (assignment launch + streaming loss launch).  Returns dict(losses f32[4], per_image f32[B,4],
@@ -138,6 +165,16 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     dev = _need_cuda(classifications, regressions, anchors, annotations)
     cls = _prep(classifications, torch.float32)
     reg = _prep(regressions, torch.float32)
+    # GT-centric assignment (anchors tagged as the regular pyramid): faster when no gradient buffers are written; with
+    # them the anchor-centric kernel wins because it hides the zero-fill of dreg (focal_loss.cu).  G3D_ASSIGN_GT_CENTRIC=1
+    # forces it everywhere, =0 disables it.
+    pyr = anchor_pyramid_of(anchors)
+    if pyr is not None and grad_cls_expected is not None and os.environ.get("G3D_ASSIGN_GT_CENTRIC", "") != "1":
+        pyr = None
+    if pyr is not None and (annotations.shape[1] > 256 or int(pyr[0]) > 8 or int(pyr[1]) > 16):
+        pyr = None                                     # the library would fall back as well; keep the counter honest
+    pyr_p = pyr.ctypes.data_as(ctypes.c_void_p) if pyr is not None else ctypes.c_void_p(0)
+    STATS["gt_centric_calls" if pyr is not None else "anchor_centric_calls"] += 1
     anc = _prep(anchors, torch.float32).reshape(-1, 4)
     ann = _prep(annotations, torch.float32)
     if cls.dim() != 3 or reg.dim() != 3 or ann.dim() != 3:
@@ -157,13 +194,13 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     code = torch.empty((B, A), dtype=torch.int32, device=dev)
     gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
     out = dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
-               ann=ann, variant=variant, workspace=ws)   # the workspace holds the positive lists the backward reads
+               ann=ann, variant=variant, workspace=ws, gt_centric=pyr is not None)   # the workspace holds the positive lists the backward reads
     stats = torch.empty((5,), dtype=torch.float64, device=dev) if want_shard_stats else None
     out["shard_stats"] = stats
     if grad_cls_expected is None and not want_shard_stats:
         check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses),
-                                   _p(per_image), _p(code), _p(gt_count), _p(ws), ws.numel(), _idx(dev), _stream(dev)),
-              "g3d_focal_loss_fwd")
+                                   _p(per_image), _p(code), _p(gt_count), _p(ws), ws.numel(), pyr_p, _idx(dev),
+                                   _stream(dev)), "g3d_focal_loss_fwd")
     else:
         grads = grad_cls_expected is not None
         ge = ctypes.c_float(float(grad_cls_expected) if grads else 0.0)
@@ -177,7 +214,7 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
             ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in trace_events])
         check(L.g3d_focal_loss_fwd_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, ge, _p(losses),
                                        _p(per_image), _p(code), _p(gt_count), _p(stats), _p(dcls), _p(dreg), _p(ws),
-                                       ws.numel(), ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
+                                       ws.numel(), pyr_p, ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
         if grads:
             out.update(dcls=dcls, dreg=dreg, grad_cls_expected=ge.value)
     return out

@@ -380,7 +380,11 @@ def run_ours(args):
     hbm_peak, peak_src = _peaks()
     B = B_PER_GPU
     g = synth.gen(100 + rank)
-    anc = synth.anchors(H_IMG, W_IMG).to(dev)
+    # the anchor table as the model gets it (retinanet/model.py:306: self.anchors(img_batch)): the drop-in Anchors module
+    # writes it on the device and tags it as the regular pyramid, which lets the loss run its GT-centric assignment
+    from geom3d_b200.anchors_impl import Anchors
+    anc = Anchors()(torch.zeros(1, 3, H_IMG, W_IMG, device=dev))
+    assert torch.equal(anc.cpu(), synth.anchors(H_IMG, W_IMG))
     A = anc.shape[1]
     ann_h = synth.gt_annotations_3d(B, G_PER_IMG, H_IMG, W_IMG, g).pin_memory()
     torch.manual_seed(100 + rank)

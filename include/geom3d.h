@@ -100,17 +100,26 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *                           trace_events (nullable): 4 cudaEvent_t handles recorded on `stream` before the assignment
  *                           launch, after it, after the positives launch and after the streaming launch (per-kernel
  *                           timing without a profiler; bench.py's roofline figures come from these).
+ * pyramid_host (nullable, host doubles): tells the call that `anchors` is the regular pyramid table of Anchors.forward
+ *   (retinanet/anchors.py:21-40; g3d_generate_anchors): {L, S, L x (rows, cols, stride), L x S x (anchor width, height)},
+ *   L <= 8 levels, S <= 16 shapes per cell, sum rows*cols*S == A.  With it (and Gmax <= 256) the assignment runs
+ *   GT-centric: per GT row only the window of cells whose anchors can reach IoU 0.385 is evaluated (same arithmetic on
+ *   the table's values, same codes), the rest of the work is a fill at HBM speed.  Without it: the anchor-centric
+ *   kernel, valid for any anchor table.  Which is faster depends on dreg: the anchor-centric kernel is instruction-bound
+ *   and hides the 48 B/row zero-fill of dreg, the GT-centric path pays it at HBM speed - pass the pyramid for
+ *   forward-only calls (71 us vs 150+ us at cfg2), omit it for the training step (see focal_loss.cu).
  */
 int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax);
 int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                        float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
-                       void* workspace, int64_t workspace_bytes, int device, void* stream);
+                       void* workspace, int64_t workspace_bytes, const double* pyramid_host, int device, void* stream);
 int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                            int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                            float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
                            int32_t* gt_count_out, double* shard_stats, float* dcls, float* dreg,
-                           void* workspace, int64_t workspace_bytes, void* const* trace_events, int device, void* stream);
+                           void* workspace, int64_t workspace_bytes, const double* pyramid_host,
+                           void* const* trace_events, int device, void* stream);
 
 /* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
  * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory); grad_scale[3] (nullable, device)

@@ -324,3 +324,92 @@ def test_loss_random_small_configurations(seed):
     same = (_codes_from_oracle(ref64[-1], ann, three_d) == codes).all(dim=1)
     assert same.any()
     assert_close_rel(r1.grad.cpu()[same], r2.grad[same], 3 * TOL, "dreg vs FP64 formula")
+
+
+def _tagged_anchors(H, W):
+    """the [1,A,4] table as the model gets it: Anchors()(image) on the device, carrying the pyramid description"""
+    from geom3d_b200.anchors_impl import Anchors
+    return Anchors()(torch.zeros(1, 3, H, W, device="cuda"))
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_gt_centric_assignment_equals_anchor_centric_and_oracle(seed, monkeypatch):
+    """anchors from Anchors.forward carry the pyramid description -> GT-centric assignment (fill + window pairs +
+    resolve).  Codes, losses and gradients must equal the anchor-centric kernel's (same table without the tag) and the
+    oracle's, incl. ties between equal GT boxes (lower index wins), padded rows, an empty image, boxes that leave the
+    image, and the 2D variant"""
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "1")          # also with gradient buffers (default: forward-only calls)
+    g = synth.gen(7000 + seed)
+    r = lambda lo_, hi_: int(torch.randint(lo_, hi_ + 1, (1,), generator=g))   # noqa: E731
+    three_d = seed % 3 != 2
+    H, W = (540, 960) if seed == 0 else (32 * r(2, 6) + 8 * r(0, 3), 32 * r(2, 8) + 8 * r(0, 3))
+    B, G, n_pad = r(1, 6), r(1, 60), r(0, 3)
+    anc_t = _tagged_anchors(H, W)
+    assert ops.anchor_pyramid_of(anc_t) is not None
+    anc_plain = anc_t.clone()                                   # same values, no tag -> anchor-centric kernel
+    assert ops.anchor_pyramid_of(anc_plain) is None
+    A = anc_t.shape[1]
+    assert torch.equal(anc_t.cpu(), synth.anchors(H, W))
+    empty = (r(0, B - 1),) if (B > 1 and seed % 2) else ()
+    maker = synth.gt_annotations_3d if three_d else synth.gt_annotations_2d
+    kw = {} if H >= 540 else synth.TINY
+    ann = maker(B, G, H, W, g, n_pad=n_pad, empty_images=empty, **kw)
+    col = 16 if three_d else 0
+    if G >= 4:                                                  # exact duplicates (ties) and an out-of-image box
+        ann[0, 2, :] = ann[0, 0, :]
+        ann[0, 3, col:col + 4] = torch.tensor([-40.0, -30.0, 25.0, 20.0])
+    cls, reg = synth.head_outputs(B, A, 8, 12 if three_d else 4, g)
+    before = dict(ops.STATS)
+    f_gt = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda(), grad_cls_expected=1.0)
+    f_an = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_plain, ann.cuda(), grad_cls_expected=1.0)
+    assert f_gt["gt_centric"] and not f_an["gt_centric"]
+    assert ops.STATS["gt_centric_calls"] == before["gt_centric_calls"] + 1
+    assert torch.equal(f_gt["assign"], f_an["assign"]), "codes differ between the two assignment kernels"
+    assert torch.equal(f_gt["per_image"][:, 3], f_an["per_image"][:, 3])
+    assert torch.equal(f_gt["dreg"], f_an["dreg"]) and torch.equal(f_gt["dcls"], f_an["dcls"])
+    assert_close_rel(f_gt["losses"].cpu(), f_an["losses"].cpu(), 1e-6, "losses")
+    # default policy: GT-centric for forward-only calls, anchor-centric when gradient buffers are written
+    monkeypatch.delenv("G3D_ASSIGN_GT_CENTRIC")
+    f_fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda())
+    assert f_fwd["gt_centric"] and torch.equal(f_fwd["assign"], f_an["assign"]) and torch.equal(f_fwd["losses"], f_gt["losses"])
+    assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda(), grad_cls_expected=1.0)["gt_centric"]
+    monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "1")
+    ref = lo.focal_loss(cls, reg, anc_t.cpu(), ann)
+    assert torch.equal(f_gt["assign"].cpu(), _codes_from_oracle(ref[-1], ann, three_d)), "codes differ from the oracle"
+    # through the autograd module (the path a training step takes)
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    before = dict(ops.STATS)
+    out = li.FocalLoss(check_empty=False)(c1, r1, anc_t, ann.cuda())
+    assert ops.STATS["gt_centric_calls"] == before["gt_centric_calls"] + 1
+    sum(o.sum() for o in out).backward()
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref2 = lo.focal_loss(c0, r0, anc_t.cpu(), ann)
+    n = 3 if three_d else 2
+    sum(ref2[i].sum() for i in range(n)).backward()
+    assert_close_rel(torch.cat(out).detach().cpu(), torch.cat(ref2[:n]).detach(), TOL, "losses vs oracle")
+    assert_close_rel(c1.grad.cpu(), c0.grad, TOL, "dcls")
+    # (f_gt == f_an bit for bit above; against the FP32 autograd oracle the cancellation-prone rows need the 3e-5 of
+    # test_loss_random_small_configurations' FP64 comparison)
+    assert_close_rel(r1.grad.cpu(), r0.grad, 3 * TOL, "dreg", row_scale=True)
+
+
+def test_gt_centric_assignment_falls_back(monkeypatch):
+    """more than 256 annotation rows, or a table modified in place after Anchors produced it -> anchor-centric kernel"""
+    ops, _ = _mods()
+    g = synth.gen(7100)
+    H, W = 96, 128
+    anc = _tagged_anchors(H, W)
+    A = anc.shape[1]
+    cls, reg = synth.head_outputs(1, A, 8, 12, g)
+    big = synth.gt_annotations_3d(1, 300, H, W, g, **synth.TINY)
+    assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, big.cuda())["gt_centric"]
+    small = synth.gt_annotations_3d(1, 20, H, W, g, **synth.TINY)
+    assert ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, small.cuda())["gt_centric"]
+    monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "0")
+    assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, small.cuda())["gt_centric"]
+    monkeypatch.delenv("G3D_ASSIGN_GT_CENTRIC")
+    moved = _tagged_anchors(H, W + 8)
+    moved += 1.0                                                 # in-place edit bumps the tensor version
+    assert ops.anchor_pyramid_of(moved) is None

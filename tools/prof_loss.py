@@ -13,7 +13,8 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 dev = torch.device("cuda", 0)
 g = synth.gen(100)
-anc = synth.anchors(1080, 1920).to(dev)
+from geom3d_b200.anchors_impl import Anchors  # noqa: E402
+anc = Anchors()(torch.zeros(1, 3, 1080, 1920, device=dev))       # tagged pyramid table -> GT-centric assignment
 A = anc.shape[1]
 ann = synth.gt_annotations_3d(B, 200, 1080, 1920, g).to(dev)
 torch.manual_seed(100)
