@@ -593,6 +593,32 @@ def run_ours(args):
                                       "frac": bwd_bytes / (ms_bwd * 1e-3) / 1e9 / hbm_peak}},
             "losses": loss_vals, "e2e_losses": [float(x) for x in host_losses],
         }
+
+    # forward-only pass (validation loss, no gradient buffers): GT-centric assignment on the tagged pyramid table against
+    # the anchor-centric kernel on an untagged copy of the same table (same codes, same losses)
+    fwd_only = None
+    if rank == 0 and world == 1:
+        anc_plain = anc.clone()
+
+        def fwd_time(table):
+            with torch.no_grad():
+                for _ in range(3):
+                    out = ops.focal_loss_forward(cls_d, reg_d, table, ann_d)
+                torch.cuda.synchronize(dev)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(10):
+                    out = ops.focal_loss_forward(cls_d, reg_d, table, ann_d)
+                a1.record()
+                torch.cuda.synchronize(dev)
+            return a0.elapsed_time(a1) / 10, out
+        t_gt, o_gt = fwd_time(anc)
+        t_an, o_an = fwd_time(anc_plain)
+        assert o_gt["gt_centric"] and not o_an["gt_centric"] and torch.equal(o_gt["assign"], o_an["assign"])
+        fwd_only = {"ms_gt_centric": t_gt, "ms_anchor_centric": t_an,
+                    "G_pairs_per_s_gt_centric": pairs_per_step / (t_gt * 1e-3) / 1e9}
+        del anc_plain, o_gt, o_an
+        line["forward_only"] = fwd_only
     del cls_d, reg_d
     torch.cuda.empty_cache()
     if rank == 0:
