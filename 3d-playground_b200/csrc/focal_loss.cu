@@ -641,27 +641,43 @@ __global__ void __launch_bounds__(256) assign_pairs_kernel(const PairArgs p, con
     uint32_t* keys = p.keys + (int64_t)b * p.A;
     // The window only has to be a superset: FP32 with approximate reciprocals (relative error ~1e-6) against a threshold
     // 3.9 % below the 0.4 that matters, plus 0.05 px of slack on the centre range.
+    // The (level, shape) combinations are spread over the lanes - each lane derives the window of its own combination
+    // (all of them in one or two rounds instead of L*S uniform iterations) - and the warp then walks the non-empty
+    // windows together, 32 cells at a time.
     constexpr float kq = 0.385f / 1.385f, eps = 0.05f;
-#pragma unroll 1
-    for (int l = 0; l < pyr.L; ++l) {
-        const float inv_stride = pyr.inv_stride[l];
-        const int cols = pyr.cols[l], rows = pyr.rows[l];
-#pragma unroll 1
-        for (int s = 0; s < pyr.S; ++s) {
-            const float aw = pyr.aw[l * pyr.S + s], ah = pyr.ah[l * pyr.S + s];
+    const int ncombo = pyr.L * pyr.S;
+    for (int k0 = 0; k0 < ncombo; k0 += 32) {
+        const int k = k0 + lane;
+        int c0 = 0, r0 = 0, wc = 0, ncell = 0, l = 0;
+        if (k < ncombo) {
+            l = k / pyr.S;
+            const float aw = pyr.aw[k], ah = pyr.ah[k];
             const float imin = kq * fmaf(aw, ah, Ag);
             const float mw = fminf(aw, gw), mh = fminf(ah, gh);
-            if (mw * mh < imin) continue;
-            const float iw_min = 0.9999f * __fdividef(imin, mh), ih_min = 0.9999f * __fdividef(imin, mw);
-            const float lo_x = gk.x + iw_min - 0.5f * aw - eps, hi_x = gk.z - iw_min + 0.5f * aw + eps;
-            const float lo_y = gk.y + ih_min - 0.5f * ah - eps, hi_y = gk.w - ih_min + 0.5f * ah + eps;
-            const int c0 = max(0, (int)ceilf(lo_x * inv_stride - 0.5f)), c1 = min(cols - 1, (int)floorf(hi_x * inv_stride - 0.5f));
-            const int r0 = max(0, (int)ceilf(lo_y * inv_stride - 0.5f)), r1 = min(rows - 1, (int)floorf(hi_y * inv_stride - 0.5f));
-            if (c1 < c0 || r1 < r0) continue;
-            const int wc = c1 - c0 + 1, ncell = wc * (r1 - r0 + 1);
-            for (int tcell = lane; tcell < ncell; tcell += 32) {
-                const int r = r0 + tcell / wc, c = c0 + tcell % wc;
-                const int a = pyr.first[l] + (r * cols + c) * pyr.S + s;
+            if (mw * mh >= imin) {
+                const float inv_stride = pyr.inv_stride[l];
+                const float iw_min = 0.9999f * __fdividef(imin, mh), ih_min = 0.9999f * __fdividef(imin, mw);
+                const float lo_x = gk.x + iw_min - 0.5f * aw - eps, hi_x = gk.z - iw_min + 0.5f * aw + eps;
+                const float lo_y = gk.y + ih_min - 0.5f * ah - eps, hi_y = gk.w - ih_min + 0.5f * ah + eps;
+                c0 = max(0, (int)ceilf(lo_x * inv_stride - 0.5f));
+                r0 = max(0, (int)ceilf(lo_y * inv_stride - 0.5f));
+                const int c1 = min(pyr.cols[l] - 1, (int)floorf(hi_x * inv_stride - 0.5f));
+                const int r1 = min(pyr.rows[l] - 1, (int)floorf(hi_y * inv_stride - 0.5f));
+                if (c1 >= c0 && r1 >= r0) { wc = c1 - c0 + 1; ncell = wc * (r1 - r0 + 1); }
+            }
+        }
+        unsigned live = __ballot_sync(0xffffffffu, ncell > 0);
+        while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            const int kc = k0 + src;
+            const int lc = __shfl_sync(0xffffffffu, l, src), sc = kc - lc * pyr.S;
+            const int c0c = __shfl_sync(0xffffffffu, c0, src), r0c = __shfl_sync(0xffffffffu, r0, src);
+            const int wcc = __shfl_sync(0xffffffffu, wc, src), nc = __shfl_sync(0xffffffffu, ncell, src);
+            const int cols = pyr.cols[lc], first = pyr.first[lc];
+            for (int tcell = lane; tcell < nc; tcell += 32) {
+                const int r = r0c + tcell / wcc, c = c0c + tcell % wcc;
+                const int a = first + (r * cols + c) * pyr.S + sc;
                 const float4 an = __ldg(p.anchors + a);
                 const float iw = __fsub_rn(fminf(an.z, gk.z), fmaxf(an.x, gk.x));
                 const float ih = __fsub_rn(fminf(an.w, gk.w), fmaxf(an.y, gk.y));
@@ -692,47 +708,56 @@ struct ResolveArgs {
 // the image's list with one atomic per warp and round (order is irrelevant downstream: exact fixed-point sums, per-row
 // gradients)
 __global__ void __launch_bounds__(256) assign_resolve_kernel(const ResolveArgs p) {
+    constexpr int U = 4;                                        // 16-byte loads in flight per thread
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const uint32_t* __restrict__ keys = p.keys + (int64_t)b * p.A;
     const bool vec = (((int64_t)b * p.A) & 3) == 0;             // the image's key row starts 16-byte aligned
     const int nq = (p.A + 3) >> 2;
-    for (int q0 = blockIdx.x * blockDim.x; q0 < nq; q0 += gridDim.x * blockDim.x) {      // warp-uniform trip count
-        const int q = q0 + threadIdx.x, a0 = q << 2;
-        unsigned k[4] = {0u, 0u, 0u, 0u};
-        if (q < nq) {
-            if (vec && a0 + 3 < p.A) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(keys) + q);
-                k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
-            } else {
+    for (int q0 = blockIdx.x * blockDim.x * U; q0 < nq; q0 += gridDim.x * blockDim.x * U) {   // warp-uniform trip count
+        unsigned k[U][4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) if (a0 + e < p.A) k[e] = __ldcs(keys + a0 + e);
+        for (int u = 0; u < U; ++u) {
+            const int q = q0 + u * blockDim.x + threadIdx.x, a0 = q << 2;
+            k[u][0] = k[u][1] = k[u][2] = k[u][3] = 0u;
+            if (q < nq) {
+                if (vec && a0 + 3 < p.A) {
+                    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(keys) + q);
+                    k[u][0] = v.x; k[u][1] = v.y; k[u][2] = v.z; k[u][3] = v.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (a0 + e < p.A) k[u][e] = __ldcs(keys + a0 + e);
+                }
             }
         }
-        if (!__any_sync(0xffffffffu, (k[0] | k[1] | k[2] | k[3]) != 0u)) continue;
-        int npos_mine = 0, code[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            code[e] = G3D_ASSIGN_NEGATIVE;
-            if (k[e]) {
-                const float v = __uint_as_float((k[e] >> 8) - 1u + kIou04Bits);
-                const int g = 255 - (int)(k[e] & 255u);
-                code[e] = (v >= 0.5f) ? __ldg(p.gt_row + (int64_t)b * p.Gmax + g) : G3D_ASSIGN_IGNORE;
-                p.assign[(int64_t)b * p.A + a0 + e] = code[e];
-                npos_mine += code[e] >= 0;
+        for (int u = 0; u < U; ++u) {
+            if (!__any_sync(0xffffffffu, (k[u][0] | k[u][1] | k[u][2] | k[u][3]) != 0u)) continue;
+            const int a0 = (q0 + u * blockDim.x + threadIdx.x) << 2;
+            int npos_mine = 0, code[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                code[e] = G3D_ASSIGN_NEGATIVE;
+                if (k[u][e]) {
+                    const float v = __uint_as_float((k[u][e] >> 8) - 1u + kIou04Bits);
+                    const int g = 255 - (int)(k[u][e] & 255u);
+                    code[e] = (v >= 0.5f) ? __ldg(p.gt_row + (int64_t)b * p.Gmax + g) : G3D_ASSIGN_IGNORE;
+                    p.assign[(int64_t)b * p.A + a0 + e] = code[e];
+                    npos_mine += code[e] >= 0;
+                }
             }
+            // exclusive prefix of the per-lane positive counts, one atomic for the warp
+            int incl = npos_mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total == 0) continue;
+            int base = 0;
+            if (lane == 0) base = lane0_atomic_add_global(p.npos + b, total);
+            base = __shfl_sync(0xffffffffu, base, 0) + incl - npos_mine;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (code[e] >= 0) p.pos_list[(int64_t)b * p.A + base++] = a0 + e;
         }
-        // exclusive prefix of the per-lane positive counts, one atomic for the warp
-        int incl = npos_mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (total == 0) continue;
-        int base = 0;
-        if (lane == 0) base = lane0_atomic_add_global(p.npos + b, total);
-        base = __shfl_sync(0xffffffffu, base, 0) + incl - npos_mine;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-            if (code[e] >= 0) p.pos_list[(int64_t)b * p.A + base++] = a0 + e;
     }
 }
 
