@@ -623,9 +623,9 @@ def run_ours(args):
     torch.cuda.empty_cache()
     if rank == 0:
         if world == 1:
-            cpu_value, cpu_s = cpu_loss_sample(2)
+            cpu_value, cpu_s = cpu_loss_sample(8)
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"2 of the 32 images (oracle port, forward+backward, best of 2 after 1 warm-up, {cpu_s:.2f} s/run)"}
+                                    "sample": f"8 of the 32 images (oracle port, forward+backward, best of 2 after 1 warm-up, {cpu_s:.2f} s/run)"}
             if not args.no_extras:
                 try:
                     line["other_workloads"] = other_workloads(dev, hbm_peak)
