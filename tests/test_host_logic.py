@@ -132,3 +132,32 @@ def test_sharded_loss_reduction_gloo_world2():
         assert torch.allclose(torch.tensor(losses), expect, rtol=1e-6), (rank, losses, expect)
         assert total[3] == B and total[4] == 3
     assert results[0][1] == results[1][1], "every rank must hold bit-identical global losses"
+
+
+def test_anchor_pyramid_tag_is_host_metadata_with_version_check(monkeypatch):
+    """ops.tag_anchor_pyramid / anchor_pyramid_of: the description FocalLoss' GT-centric assignment needs travels as an
+    attribute of the anchor table; a copy, an in-place edit or G3D_ASSIGN_GT_CENTRIC=0 drops it"""
+    from geom3d_b200 import ops
+    from geom3d_b200.anchors_impl import _level_shapes, _RATIOS, _SCALES, anchors_for_image
+    H, W = 75, 133
+    levels = (3, 4, 5, 6, 7)
+    rows = [(H + 2 ** x - 1) // 2 ** x for x in levels]
+    cols = [(W + 2 ** x - 1) // 2 ** x for x in levels]
+    shapes = np.stack([_level_shapes(2 ** (x + 2), _RATIOS, _SCALES) for x in levels])
+    table = torch.from_numpy(anchors_for_image(H, W)).unsqueeze(0)
+    assert ops.anchor_pyramid_of(table) is None
+    ops.tag_anchor_pyramid(table, rows, cols, [2.0 ** x for x in levels], shapes)
+    desc = ops.anchor_pyramid_of(table)
+    assert desc is not None and desc.dtype == np.float64 and desc[0] == 5 and desc[1] == 9
+    assert desc.size == 2 + 3 * 5 + 2 * 5 * 9
+    lv = desc[2:17].reshape(5, 3)
+    assert int((lv[:, 0] * lv[:, 1]).sum()) * 9 == table.shape[1] and lv[0, 2] == 8.0
+    wh = desc[17:].reshape(5, 9, 2)
+    a = table[0].numpy()
+    assert np.allclose(wh[0, :, 0], a[:9, 2] - a[:9, 0], rtol=1e-6) and np.allclose(wh[0, :, 1], a[:9, 3] - a[:9, 1], rtol=1e-6)
+    assert ops.anchor_pyramid_of(table.clone()) is None                     # a copy is just a tensor
+    monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "0")
+    assert ops.anchor_pyramid_of(table) is None
+    monkeypatch.delenv("G3D_ASSIGN_GT_CENTRIC")
+    table += 0.5                                                             # in-place edit: version moves on
+    assert ops.anchor_pyramid_of(table) is None
