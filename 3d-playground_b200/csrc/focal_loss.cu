@@ -565,7 +565,7 @@ __device__ __forceinline__ void assign_item(const AssignCodesArgs& p, StageSmem&
     }
 }
 
-__global__ void __launch_bounds__(kTile, 5) assign_codes_kernel(const AssignCodesArgs p) {
+__global__ void __launch_bounds__(kTile, 6) assign_codes_kernel(const AssignCodesArgs p) {
     __shared__ StageSmem sm;
     assign_item(p, sm, blockIdx.x, blockIdx.y);
 }
