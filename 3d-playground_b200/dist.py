@@ -3,7 +3,7 @@ the CPU tests) for the only exchange the path has - the scalar loss / normaliser
 
 The reference runs the loss under nn.DataParallel (train_detector_3D_angle.py:316-318): images are split across
 replicas, every replica returns its own batch means and the trainer averages them (:374-378).  Here every rank owns a
-contiguous range of images, computes the per-image terms locally with the fused kernel, and 5 scalars per rank are
+contiguous range of images, computes the per-image terms locally with the fused kernels, and 5 scalars per rank are
 all-gathered and summed in rank order (bit-reproducible, unlike a tree all-reduce whose order depends on topology):
 
     [sum_j cls_j, sum_j reg_j, sum_{j non-empty} vp_j, #images, #non-empty images]
@@ -23,66 +23,62 @@ def shard_range(n_items, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def local_stats(per_image, gt_count):
-    """per_image[B_l,4] = (cls_j, reg_j, vp_j, num_pos_j), gt_count[B_l] -> float64[5] shard statistics"""
-    nonempty = gt_count > 0
-    pi = per_image.double()
-    return torch.stack((pi[:, 0].sum(), pi[:, 1].sum(), (pi[:, 2] * nonempty).sum(),
-                        torch.tensor(float(per_image.shape[0]), dtype=torch.float64, device=per_image.device),
-                        nonempty.sum().double()))
-
-
-def combine_stats(stats, group=None):
-    """all-gather the [5] statistics of every rank and reduce them in rank order.
-    Returns (losses float32[3] = global (cls, reg, vp) means, totals float64[5])."""
+def gather_shard_stats(stats, group=None):
+    """stats: this rank's float64[5] shard statistics (as g3d_focal_loss_fwd_bwd writes them; any device the backend
+    supports).  Returns float64[world,5] in rank order - the input of ops.combine_shard_stats / combine_on_host."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        gathered = [torch.empty_like(stats) for _ in range(dist.get_world_size(group))]
-        dist.all_gather(gathered, stats.contiguous(), group=group)
-        total = torch.stack(gathered).sum(dim=0)   # fixed (rank) order
-    else:
-        total = stats
+        world = dist.get_world_size(group)
+        gathered = torch.empty((world * 5,), dtype=torch.float64, device=stats.device)   # flat: gloo and NCCL both take it
+        dist.all_gather_into_tensor(gathered, stats.contiguous().reshape(5), group=group)
+        return gathered.reshape(world, 5)
+    return stats.reshape(1, 5)
+
+
+def combine_on_host(gathered, rank):
+    """The arithmetic of g3d_combine_shard_stats (focal_loss.cu: combine_shard_stats_kernel) restated with torch ops, for
+    checking the kernel: rank-order sums, global means, this rank's gradient scales.  Not used by the GPU path."""
+    total = torch.zeros(5, dtype=torch.float64)
+    for r in range(gathered.shape[0]):
+        total = total + gathered[r].cpu()
     losses = torch.stack((total[0] / total[3], total[1] / total[3], total[2] / total[4])).to(torch.float32)
-    return losses, total
+    bl, nl = gathered[rank, 3].cpu(), gathered[rank, 4].cpu()
+    scale = torch.stack((bl / total[3], bl / total[3], nl / total[4] if float(nl) > 0 else torch.zeros((), dtype=torch.float64)))
+    return losses, scale.to(torch.float32)
 
 
 class _ShardedFocalLossFn(torch.autograd.Function):
-    """forward: local fused loss (+ gradients for the expected upstream value) -> all-gather of the 5 shard statistics
-    the kernel wrote -> one tiny kernel forms the global means and this rank's gradient scales.  Two extra launches and
-    one collective per step; the backward adds none (the scale is applied inside the gradient kernels)."""
+    """forward: local fused loss (+ gradients for the expected upstream value B_local / B_global = 1 / world) -> all-gather
+    of the 5 shard statistics the kernel wrote -> one tiny kernel forms the global means and this rank's gradient scales.
+    Two extra launches and one collective per step; the backward adds none (it only verifies the scale on the device)."""
 
     @staticmethod
-    def forward(ctx, classifications, regressions, anchors, annotations, group, trace_events=None):
+    def forward(ctx, classifications, regressions, anchors, annotations, group, trace_events, hyper):
         from . import ops
         on = dist.is_available() and dist.is_initialized()
         world = dist.get_world_size(group) if on else 1
         rank = dist.get_rank(group) if on else 0
-        # expected upstream gradient of the LOCAL classification mean: B_local / B_global = 1 / world for equal shards
-        # (a hint: the backward kernel checks it against the real value on the device and recomputes if it is off)
         needs_grad = classifications.requires_grad or regressions.requires_grad
-        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations,
-                                     grad_cls_expected=(1.0 / world) if needs_grad else None,
-                                     trace_events=trace_events if needs_grad else None, want_shard_stats=True)
-        stats = fwd["shard_stats"]
-        if world > 1:
-            gathered = torch.empty((world, 5), dtype=torch.float64, device=stats.device)
-            dist.all_gather_into_tensor(gathered, stats, group=group)
-        else:
-            gathered = stats.reshape(1, 5)
+        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=False,
+                                     grad_expected=(1.0 / world) if needs_grad else None,
+                                     trace_events=trace_events, want_shard_stats=True, hyper=hyper)
+        gathered = gather_shard_stats(fwd["shard_stats"], group)
         losses, scale = ops.combine_shard_stats(gathered, rank)
-        ctx.fwd, ctx.scale = fwd, scale
+        ctx.fwd, ctx.scale, ctx.n_backward = fwd, scale, 0
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
+        ctx.save_for_backward(classifications, regressions)
         return losses
 
     @staticmethod
     def backward(ctx, g):
         from . import ops
-        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g.to(torch.float32), grad_scale=ctx.scale)
-        ctx.fwd = None
-        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None
+        _ = ctx.saved_tensors
+        ctx.n_backward += 1
+        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g.to(torch.float32), grad_scale=ctx.scale, fresh=ctx.n_backward > 1)
+        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None, None
 
 
-def sharded_focal_loss(classifications, regressions, anchors, annotations, group=None, trace_events=None):
+def sharded_focal_loss(classifications, regressions, anchors, annotations, group=None, trace_events=None, hyper=None):
     """Loss of the global batch from this rank's image shard.  Returns float32[3] (cls, reg, vp), identical on every
     rank and differentiable w.r.t. the local classifications / regressions (gradients need no collective: they are
     per-image local, scaled by 1/B_global)."""
-    return _ShardedFocalLossFn.apply(classifications, regressions, anchors, annotations, group, trace_events)
+    return _ShardedFocalLossFn.apply(classifications, regressions, anchors, annotations, group, trace_events, hyper)

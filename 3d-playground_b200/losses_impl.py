@@ -16,35 +16,41 @@ def calc_iou(a, b):
 
 
 class _FocalLossFn(torch.autograd.Function):
-    """losses[3] = (cls, reg, vp).  When an input requires grad, the forward pass already writes the classification
-    gradient for the expected upstream gradient (1 for `(cls + reg + vp).backward()`,
-    train_detector_3D_angle.py:374-382) in the same sweep over the classification tensor; the backward kernel verifies
-    that expectation on the device and recomputes only if it does not hold."""
+    """losses[3] = (cls, reg, vp).  When an input requires grad, the forward launches already write both gradients for the
+    expected upstream gradients (1 for `(cls + reg + vp).backward()`, train_detector_3D_angle.py:374-382); the backward
+    kernels verify that expectation on the device and recompute only what differs."""
 
     @staticmethod
-    def forward(ctx, classifications, regressions, anchors, annotations, expected_grad, trace_events):
+    def forward(ctx, classifications, regressions, anchors, annotations, expected_grad, trace_events, hyper):
         needs_grad = classifications.requires_grad or regressions.requires_grad
-        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations,
-                                     grad_cls_expected=float(expected_grad) if needs_grad else None,
-                                     trace_events=trace_events if needs_grad else None)
+        fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=False,
+                                     grad_expected=expected_grad if needs_grad else None,
+                                     trace_events=trace_events, hyper=hyper)
         ctx.fwd = fwd
+        ctx.n_backward = 0
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
+        # saved for autograd's bookkeeping: an in-place edit of an input between forward and backward is detected (version
+        # counters), and a second backward without retain_graph raises autograd's own error
+        ctx.save_for_backward(classifications, regressions)
         ctx.mark_non_differentiable(fwd["per_image"], fwd["gt_count"])
         return fwd["losses"][:3].clone(), fwd["losses"][3:4].clone(), fwd["per_image"], fwd["gt_count"]
 
     @staticmethod
     def backward(ctx, g_losses, _g_ne, _g_pi, _g_gc):
-        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g_losses.to(torch.float32).contiguous())
-        ctx.fwd = None
-        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None
+        _ = ctx.saved_tensors
+        ctx.n_backward += 1
+        # first backward: the buffers the forward wrote (verified / completed on the device); later ones (retain_graph):
+        # fresh buffers, the tensors returned earlier stay untouched
+        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g_losses.to(torch.float32).contiguous(), fresh=ctx.n_backward > 1)
+        return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None, None
 
 
-def focal_loss(classifications, regressions, anchors, annotations, expected_grad=1.0, trace_events=None):
+def focal_loss(classifications, regressions, anchors, annotations, expected_grad=1.0, trace_events=None, hyper=None):
     """Functional form.  Returns (losses[3], n_nonempty[1], per_image[B,4], gt_count[B]); losses is differentiable
-    w.r.t. classifications and regressions.  expected_grad: the upstream gradient the caller expects for the
-    classification loss (a performance hint only - any upstream gradient gives the right result).  trace_events: see
-    ops.focal_loss_forward (per-kernel timing for bench.py)."""
-    return _FocalLossFn.apply(classifications, regressions, anchors, annotations, expected_grad, trace_events)
+    w.r.t. classifications and regressions.  expected_grad: the upstream gradient(s) the caller expects for the three
+    losses, a float or (cls, reg, vp) (a performance hint only - any upstream gradient gives the right result).
+    trace_events: see ops.focal_loss_forward (per-kernel timing for bench.py).  hyper: dict of hyper-parameter overrides."""
+    return _FocalLossFn.apply(classifications, regressions, anchors, annotations, expected_grad, trace_events, hyper)
 
 
 class FocalLoss(nn.Module):
@@ -54,20 +60,59 @@ class FocalLoss(nn.Module):
       -> 3D: (cls[1], reg[1], vp[1])      (losses.py:362)
          2D: (cls[1], reg[1])             (retinanet/losses.py:177)
 
-    check_empty=True keeps the reference's error behaviour for the 3D copy - a batch in which no image has a ground
-    truth row makes torch.stack([]) raise RuntimeError (losses.py:362) - at the cost of one 4-byte device->host read;
-    with check_empty=False the vp loss is NaN in that case and no synchronisation happens.
+    The reference hard-codes its hyper-parameters inside forward; here they are keyword arguments with the same defaults:
+    alpha, gamma, top_weighting (losses.py:28-30), pos_iou / neg_iou (:124 / :121), beta (smooth-L1, :346-348), clamp_min /
+    clamp_max (:56).
+
+    check_empty - the reference's error for a 3D batch in which no image has a ground truth row (torch.stack([]) raises
+    RuntimeError, losses.py:362):
+      "lazy" (default): no synchronisation; the count of non-empty images is copied to pinned host memory asynchronously
+                        and examined at the NEXT forward call (or by .check()), which raises then; the step itself
+                        returns NaN for the vp loss.
+      True:             raise immediately (one 4-byte device->host read per forward, a host synchronisation).
+      False:            never raise (NaN vp loss).
     """
 
-    def __init__(self, check_empty=True, expected_grad=1.0):
+    def __init__(self, check_empty="lazy", expected_grad=1.0, alpha=0.25, gamma=2.0, top_weighting=0.5, pos_iou=0.5,
+                 neg_iou=0.4, beta=1.0 / 9.0, clamp_min=1e-4, clamp_max=1.0 - 1e-4):
         super().__init__()
         self.check_empty = check_empty
         self.expected_grad = expected_grad   # e.g. 1/n_replicas under nn.DataParallel + .mean() (a hint, see focal_loss)
+        given = dict(alpha=alpha, gamma=gamma, top_weighting=top_weighting, pos_iou=pos_iou, neg_iou=neg_iou, beta=beta,
+                     clamp_min=clamp_min, clamp_max=clamp_max)
+        self.hyper = {k: v for k, v in given.items() if float(v) != float(dict(ops.HYPER_DEFAULTS)[k])} or None
+        self._pending = []                   # (pinned host count, event) of earlier forwards, for check_empty="lazy"
+
+    def check(self, wait=False):
+        """examine the empty-batch flags of earlier forwards (check_empty="lazy"); wait=True synchronises on them"""
+        still = []
+        for host, ev in self._pending:
+            if wait:
+                ev.synchronize()
+            if ev.query():
+                if float(host[0]) == 0.0:
+                    self._pending = []
+                    raise RuntimeError("stack expects a non-empty TensorList (an earlier FocalLoss.forward saw a batch "
+                                       "without any ground-truth row; reported late because check_empty='lazy')")
+            else:
+                still.append((host, ev))
+        self._pending = still
 
     def forward(self, classifications, regressions, anchors, annotations):
-        losses, n_nonempty, _, _ = focal_loss(classifications, regressions, anchors, annotations, self.expected_grad)
+        losses, n_nonempty, _, _ = focal_loss(classifications, regressions, anchors, annotations, self.expected_grad,
+                                              hyper=self.hyper)
         if regressions.shape[-1] == 12:
-            if self.check_empty and float(n_nonempty.item()) == 0.0:
-                raise RuntimeError("stack expects a non-empty TensorList")  # the reference's torch.stack(vp_losses)
+            if self.check_empty is True:
+                if float(n_nonempty.item()) == 0.0:
+                    raise RuntimeError("stack expects a non-empty TensorList")  # the reference's torch.stack(vp_losses)
+            elif self.check_empty == "lazy" and not torch.cuda.is_current_stream_capturing():
+                self.check()
+                host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+                host.copy_(n_nonempty, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(n_nonempty.device))
+                self._pending.append((host, ev))
+                if len(self._pending) > 64:
+                    self.check(wait=True)
             return losses[0:1], losses[1:2], losses[2:3]
         return losses[0:1], losses[1:2]

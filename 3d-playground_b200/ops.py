@@ -6,6 +6,7 @@ computes on the CPU and nothing falls back: a CPU tensor raises.
 """
 import ctypes
 import os
+import threading
 
 import numpy as np
 import torch
@@ -32,14 +33,14 @@ def _need_cuda(*tensors):
     return dev
 
 
-def _prep(t, dtype):
-    """contiguous tensor of `dtype` whose data pointer is 16-byte aligned (detached: raw kernels see no autograd)"""
+def _prep(t, dtype, align=16):
+    """contiguous tensor of `dtype` whose data pointer is `align`-byte aligned (detached: raw kernels see no autograd)"""
     t = t.detach()
     if t.dtype != dtype:
         t = t.to(dtype)
     if not t.is_contiguous():
         t = t.contiguous()
-    if t.data_ptr() % 16:
+    if t.data_ptr() % align:
         t = t.clone()
     return t
 
@@ -126,6 +127,35 @@ def assign(anchors, annotations, variant=None):
 
 # ------------------------------------------------------------------------------------------------ a2-a6: fused loss
 STATS = {"gt_centric_calls": 0, "anchor_centric_calls": 0}   # which assignment path focal_loss_forward took (for tests)
+_STATS_LOCK = threading.Lock()
+
+# the reference's constants (losses.py:28-30 alpha / gamma / top_weighting, :56 clamp, :121,:124 thresholds, :346-348 beta);
+# order = include/geom3d.h hyper_host
+HYPER_DEFAULTS = (("alpha", 0.25), ("gamma", 2.0), ("pos_iou", 0.5), ("neg_iou", 0.4), ("beta", 1.0 / 9.0),
+                  ("top_weighting", 0.5), ("clamp_min", 1e-4), ("clamp_max", 1.0 - 1e-4))
+
+
+def hyper_array(hyper):
+    """dict of overrides (keys of HYPER_DEFAULTS) -> ctypes float[8], or None for the defaults"""
+    if not hyper:
+        return None
+    unknown = set(hyper) - {k for k, _ in HYPER_DEFAULTS}
+    if unknown:
+        raise ValueError(f"unknown loss hyper-parameter(s) {sorted(unknown)}; known: {[k for k, _ in HYPER_DEFAULTS]}")
+    return (ctypes.c_float * len(HYPER_DEFAULTS))(*[float(hyper.get(k, d)) for k, d in HYPER_DEFAULTS])
+
+
+def set_tuning(name, value):
+    """process-wide tuning knob of the loss kernels (g3d_set_tuning): fill_chain_permille, fill_ctas, force_anchor_centric"""
+    check(_lib.lib().g3d_set_tuning(_lib.TUNE_KEYS[name], int(value)), "g3d_set_tuning")
+
+
+def _tuning_from_env():
+    """G3D_TUNE="fill_chain_permille=300,fill_ctas=148" (benchmark sweeps); read once, at import"""
+    spec = os.environ.get("G3D_TUNE", "")
+    for item in filter(None, (x.strip() for x in spec.split(","))):
+        k, v = item.split("=")
+        set_tuning(k.strip(), int(v))
 
 
 def anchor_pyramid_of(anchors):
@@ -151,30 +181,41 @@ def tag_anchor_pyramid(table, rows, cols, strides, level_shapes):
     return table
 
 
-def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True, grad_cls_expected=None,
-                       trace_events=None, want_shard_stats=False):
-    """FocalLoss forward (assignment launch + streaming loss launch).  Returns dict(losses f32[4], per_image f32[B,4],
-    assign i32[B,A], gt_count i32[B], plus the prepared contiguous inputs for the backward).
+def _expected3(grad_expected):
+    if grad_expected is None:
+        return None
+    if isinstance(grad_expected, (int, float)):
+        grad_expected = (grad_expected,) * 3
+    g = [float(x) for x in grad_expected]
+    if len(g) != 3:
+        raise ValueError("grad_expected: a float or three floats (cls, reg, vp)")
+    return (ctypes.c_float * 3)(*g)
 
-    grad_cls_expected (host float, e.g. 1.0): ALSO write, in the same pass over the classification tensor, the
-    classification gradient for that upstream gradient and zero-fill the regression gradient (dict keys "dcls", "dreg",
-    "grad_cls_expected"); focal_loss_backward then confirms on the device that the upstream gradient is that one and
-    only adds the rows of the positive anchors.  `want_assign` is kept for API compatibility: the codes are always
-    produced (they link the launches).  trace_events: 4 torch.cuda.Event(enable_timing=True) recorded before the
-    assignment launch, after it, after the positives launch and after the streaming launch (needs grad_cls_expected)."""
+
+def focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=True, grad_expected=None,
+                       trace_events=None, want_shard_stats=False, hyper=None, grad_cls_expected=None):
+    """FocalLoss forward.  Returns dict(losses f32[4], per_image f32[B,4], gt_count i32[B], assign i32[B,A] if
+    want_assign, plus the prepared contiguous inputs and the workspace the backward needs).
+
+    grad_expected (host float or 3 floats, e.g. 1.0): ALSO write, in the same launches, the complete gradients for those
+    upstream gradients of (cls, reg, vp) - dict keys "dcls", "dreg", "grad_expected"; focal_loss_backward then confirms on
+    the device that the upstream gradients are those and recomputes only what differs.  (grad_cls_expected: older name.)
+    hyper: dict of loss hyper-parameter overrides (HYPER_DEFAULTS).  trace_events: up to 6 torch.cuda.Event(enable_timing=
+    True) recorded before the first launch and after each of the five launches (see include/geom3d.h)."""
+    if grad_expected is None and grad_cls_expected is not None:
+        grad_expected = grad_cls_expected
     dev = _need_cuda(classifications, regressions, anchors, annotations)
-    cls = _prep(classifications, torch.float32)
+    cls = _prep(classifications, torch.float32, 32)
     reg = _prep(regressions, torch.float32)
-    # GT-centric assignment (anchors tagged as the regular pyramid): faster when no gradient buffers are written; with
-    # them the anchor-centric kernel wins because it hides the zero-fill of dreg (focal_loss.cu).  G3D_ASSIGN_GT_CENTRIC=1
-    # forces it everywhere, =0 disables it.
+    # GT-centric assignment when the anchors are tagged as the regular pyramid (Anchors.forward); G3D_ASSIGN_GT_CENTRIC=0
+    # disables it
     pyr = anchor_pyramid_of(anchors)
-    if pyr is not None and grad_cls_expected is not None and os.environ.get("G3D_ASSIGN_GT_CENTRIC", "") != "1":
-        pyr = None
-    if pyr is not None and (annotations.shape[1] > 256 or int(pyr[0]) > 8 or int(pyr[1]) > 16):
+    if pyr is not None and (annotations.shape[1] > 256 or annotations.shape[1] < 1 or int(pyr[0]) > 8 or int(pyr[1]) > 16
+                            or classifications.shape[-1] > 250 or (hyper and float(hyper.get("neg_iou", 0.4)) < 0.3)):
         pyr = None                                     # the library would fall back as well; keep the counter honest
     pyr_p = pyr.ctypes.data_as(ctypes.c_void_p) if pyr is not None else ctypes.c_void_p(0)
-    STATS["gt_centric_calls" if pyr is not None else "anchor_centric_calls"] += 1
+    with _STATS_LOCK:
+        STATS["gt_centric_calls" if pyr is not None else "anchor_centric_calls"] += 1
     anc = _prep(anchors, torch.float32).reshape(-1, 4)
     ann = _prep(annotations, torch.float32)
     if cls.dim() != 3 or reg.dim() != 3 or ann.dim() != 3:
@@ -191,32 +232,31 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     ws = _workspace(wbytes, dev)
     losses = torch.empty((4,), dtype=torch.float32, device=dev)
     per_image = torch.empty((B, 4), dtype=torch.float32, device=dev)
-    code = torch.empty((B, A), dtype=torch.int32, device=dev)
+    code = torch.empty((B, A), dtype=torch.int32, device=dev) if want_assign else None
     gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
-    out = dict(losses=losses, per_image=per_image, assign=code, gt_count=gt_count, cls=cls, reg=reg, anchors=anc,
-               ann=ann, variant=variant, workspace=ws, gt_centric=pyr is not None)   # the workspace holds the positive lists the backward reads
+    hy = hyper_array(hyper)
+    out = dict(losses=losses, per_image=per_image, gt_count=gt_count, cls=cls, reg=reg, anchors=anc, ann=ann,
+               variant=variant, workspace=ws, gt_centric=pyr is not None, hyper=hy)
+    if want_assign:
+        out["assign"] = code
     stats = torch.empty((5,), dtype=torch.float64, device=dev) if want_shard_stats else None
     out["shard_stats"] = stats
-    if grad_cls_expected is None and not want_shard_stats:
-        check(L.g3d_focal_loss_fwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, _p(losses),
-                                   _p(per_image), _p(code), _p(gt_count), _p(ws), ws.numel(), pyr_p, _idx(dev),
-                                   _stream(dev)), "g3d_focal_loss_fwd")
-    else:
-        grads = grad_cls_expected is not None
-        ge = ctypes.c_float(float(grad_cls_expected) if grads else 0.0)
-        dcls = torch.empty_like(cls) if grads else None
-        dreg = torch.empty_like(reg) if grads else None
-        ev = None
-        if trace_events is not None:
-            for e in trace_events:          # torch creates the CUDA event lazily, on its first record
-                if not e.cuda_event:
-                    e.record(torch.cuda.current_stream(dev))
-            ev = (ctypes.c_void_p * 4)(*[e.cuda_event for e in trace_events])
-        check(L.g3d_focal_loss_fwd_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, ge, _p(losses),
-                                       _p(per_image), _p(code), _p(gt_count), _p(stats), _p(dcls), _p(dreg), _p(ws),
-                                       ws.numel(), pyr_p, ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
-        if grads:
-            out.update(dcls=dcls, dreg=dreg, grad_cls_expected=ge.value)
+    ge = _expected3(grad_expected)
+    grads = ge is not None
+    dcls = torch.empty_like(cls) if grads else None
+    dreg = torch.empty_like(reg) if grads else None
+    ev, n_ev = None, 0
+    if trace_events is not None:
+        for e in trace_events:          # torch creates the CUDA event lazily, on its first record
+            if not e.cuda_event:
+                e.record(torch.cuda.current_stream(dev))
+        n_ev = len(trace_events)
+        ev = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in trace_events])
+    check(L.g3d_focal_loss_fwd_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, variant, hy, ge, _p(losses),
+                                   _p(per_image), _p(code), _p(gt_count), _p(stats), _p(dcls), _p(dreg), _p(ws),
+                                   ws.numel(), pyr_p, ev, n_ev, _idx(dev), _stream(dev)), "g3d_focal_loss_fwd_bwd")
+    if grads:
+        out.update(dcls=dcls, dreg=dreg, grad_expected=ge)
     return out
 
 
@@ -232,12 +272,12 @@ def combine_shard_stats(gathered, rank):
     return losses, scale
 
 
-def focal_loss_backward(fwd, grad_out, grad_scale=None):
+def focal_loss_backward(fwd, grad_out, grad_scale=None, fresh=False):
     """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R]).
 
-    If the forward already wrote dcls for `grad_cls_expected`, the kernel compares grad_out[0] with it on the device: when
-    they agree it only writes the positive anchors' rows of dreg, otherwise it recomputes dcls as well (no host
-    synchronisation either way)."""
+    If the forward already wrote the gradients for `grad_expected`, the kernels compare grad_out (* grad_scale) with it on
+    the device: what agrees stays, what differs is recomputed (no host synchronisation either way).  fresh=True computes
+    into new buffers instead (a second backward through the same forward: the first one's tensors stay untouched)."""
     cls, reg, anc, ann = fwd["cls"], fwd["reg"], fwd["anchors"], fwd["ann"]
     dev = cls.device
     B, A, C = cls.shape
@@ -247,14 +287,14 @@ def focal_loss_backward(fwd, grad_out, grad_scale=None):
     if g.numel() != 3:
         raise ValueError("grad_out must have 3 elements (cls, reg, vp)")
     gs = _prep(grad_scale, torch.float32) if grad_scale is not None else None
-    if fwd.get("dcls") is not None:
-        dcls, dreg, have, ge = fwd["dcls"], fwd["dreg"], 1, fwd["grad_cls_expected"]
+    if fwd.get("dcls") is not None and not fresh:
+        dcls, dreg, have, ge = fwd["dcls"], fwd["dreg"], 1, fwd["grad_expected"]
     else:
-        dcls, dreg, have, ge = torch.empty_like(cls), torch.empty_like(reg), 0, 0.0
+        dcls, dreg, have, ge = torch.empty_like(cls), torch.empty_like(reg), 0, None
     ws = fwd["workspace"]
-    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], _p(g), _p(gs),
-                                        have, ctypes.c_float(ge), _p(fwd["losses"]), _p(fwd["assign"]), _p(ws), ws.numel(),
-                                        _p(dcls), _p(dreg), _idx(dev), _stream(dev)), "g3d_focal_loss_bwd")
+    check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], fwd.get("hyper"),
+                                        _p(g), _p(gs), have, ge, _p(ws), ws.numel(), _p(dcls), _p(dreg), _idx(dev),
+                                        _stream(dev)), "g3d_focal_loss_bwd")
     return dcls, dreg
 
 
@@ -822,3 +862,7 @@ def cross_camera_pairs(footprints, cams, threshold):
         check(L.g3d_cross_camera_pairs(_p(fp), _p(cm), d, float(threshold), null, _p(offsets), _p(pairs), K, _idx(dev),
                                        _stream(dev)), "g3d_cross_camera_pairs")
     return pairs.long()
+
+
+if os.environ.get("G3D_TUNE"):
+    _tuning_from_env()

@@ -418,7 +418,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]   # per-kernel events
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]   # per-kernel events
     for tr in kev:
         for e in tr:
             e.record()      # creates the CUDA events outside the timed region
@@ -486,9 +486,10 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_fwd = _event_ms([(e[0], e[1]) for e in evs]) / args.steps
     ms_bwd = _event_ms([(e[1], e[2]) for e in evs]) / args.steps
-    ms_assign = _event_ms([(e[0], e[1]) for e in kev]) / args.steps
-    ms_pos = _event_ms([(e[1], e[2]) for e in kev]) / args.steps
-    ms_stream = _event_ms([(e[2], e[3]) for e in kev]) / args.steps
+    ms_k = [_event_ms([(e[i], e[i + 1]) for e in kev]) / args.steps for i in range(5)]   # prologue, pairs, resolve, stream, positives
+    ms_assign = ms_k[0] + ms_k[1] + ms_k[2]
+    ms_pos = ms_k[4]
+    ms_stream = ms_k[3]
     pairs_per_step = world * B * A * G_PER_IMG
     value = pairs_per_step / (ms_step * 1e-3) / 1e9
     loss_vals = [float(x) for x in losses.detach().cpu()]
@@ -500,7 +501,7 @@ def run_ours(args):
     reg_h = torch.empty((B, A, R_REG), dtype=torch.float32).pin_memory()
     cls_h.copy_(cls_d.detach())
     reg_h.copy_(reg_d.detach())
-    module = losses_impl.FocalLoss(check_empty=False)
+    module = losses_impl.FocalLoss()
     cls_in = torch.empty_like(cls_d).requires_grad_(True)
     reg_in = torch.empty_like(reg_d).requires_grad_(True)
 
@@ -591,7 +592,7 @@ def run_ours(args):
                                      "frac": fwd_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak},
                          "backward": {"bytes": bwd_bytes, "GBps": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
                                       "frac": bwd_bytes / (ms_bwd * 1e-3) / 1e9 / hbm_peak}},
-            "losses": loss_vals, "e2e_losses": [float(x) for x in host_losses],
+            "losses": loss_vals, "e2e_losses": [float(x) for x in host_losses], "ms_kernels": ms_k,
         }
 
     # forward-only pass (validation loss, no gradient buffers): GT-centric assignment on the tagged pyramid table against

@@ -78,67 +78,80 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *        3D losses.py:27-362 ; 2D retinanet/losses.py:27-177
  * cls[B,A,C] (post-sigmoid), reg[B,A,R] (R = 12 for 3D, 4 for 2D), anchors[A,4], ann[B,Gmax,W]
  * (W >= 21 for 3D - only cols 0..20 are read -, W == 5 for 2D).
+ * hyper_host (nullable, host floats[G3D_HYPER_COUNT]): {alpha, gamma, positive IoU threshold, negative IoU threshold,
+ *   smooth-L1 beta, top_weighting, clamp min, clamp max}; NULL = the reference's constants {0.25, 2.0, 0.5, 0.4, 1/9, 0.5,
+ *   1e-4, 1 - 1e-4} (losses.py:28-30,56,121,124,343,346-348).  gamma == 2 takes the fast kernels.
  * Outputs:
  *   losses[4]        = (classification, regression, direction "vp") batch means exactly as the reference forms them:
  *                      mean over all B images for cls/reg, mean over the images that have >=1 GT row for vp
  *                      (NaN if there is none: the reference raises there, the Python wrapper turns it into the raise);
  *                      2D variant: losses[2] = 0.  losses[3] = number of images with >= 1 GT row.
  *   per_image[B,4]   = (cls_j, reg_j, vp_j, num_pos_j) per image (vp_j = 0 and flagged by gt_count==0 for empty images)
- *   assign[B,A]      = assignment codes (required: they are the hand-over between the two launches and the backward)
+ *   assign[B,A]      = int32 assignment codes (nullable: the kernels hand over one-byte codes in the workspace)
  *   gt_count_out[B]  = number of GT rows (class != -1) per image (nullable)
  * workspace: g3d_focal_workspace_bytes(B, A, Gmax) bytes, 256-byte aligned, contents undefined on entry.
+ * Alignment: cls / dcls 32 bytes (256-bit row accesses), reg / dreg / anchors / per_image 16 bytes.
  *
  * g3d_focal_loss_fwd      : the losses only.
- * g3d_focal_loss_fwd_bwd  : the losses AND, in the same pass over cls, the classification gradient dcls[B,A,C] of
- *                           grad_cls_expected * losses[0]  (grad_cls_expected = the upstream gradient the caller
- *                           expects for the classification loss: 1 for `(cls + reg + vp).backward()`), plus the
- *                           zero-fill of dreg[B,A,R].  g3d_focal_loss_bwd(have_dcls = 1) completes the backward.
+ * g3d_focal_loss_fwd_bwd  : the losses AND, in the same pass, the complete gradients dcls[B,A,C], dreg[B,A,R] of
+ *                           grad_expected_host[0] * losses[0] + [1] * losses[1] + [2] * losses[2] (host floats: the
+ *                           upstream gradients the caller expects: {1,1,1} for `(cls + reg + vp).backward()`,
+ *                           train_detector_3D_angle.py:374-382).  g3d_focal_loss_bwd(have_grads = 1) verifies the
+ *                           expectation on the device and recomputes what does not hold.
  *                           dcls == dreg == NULL degrades to g3d_focal_loss_fwd.
  *                           shard_stats (nullable, double[5]): sum_j cls_j, sum_j reg_j, sum over images with GT of
  *                           vp_j, B, number of images with GT - what a rank contributes to the global batch means
  *                           when the images are sharded over several GPUs (see g3d_combine_shard_stats).
- *                           trace_events (nullable): 4 cudaEvent_t handles recorded on `stream` before the assignment
- *                           launch, after it, after the positives launch and after the streaming launch (per-kernel
- *                           timing without a profiler; bench.py's roofline figures come from these).
+ *                           trace_events (nullable): n_trace_events <= 6 cudaEvent_t handles recorded on `stream` before
+ *                           the first launch and after the prologue, the assignment, the resolve pass, the streaming
+ *                           pass and the positives / reduction launch (per-kernel timing without a profiler;
+ *                           bench.py's roofline figures come from these).
  * pyramid_host (nullable, host doubles): tells the call that `anchors` is the regular pyramid table of Anchors.forward
  *   (retinanet/anchors.py:21-40; g3d_generate_anchors): {L, S, L x (rows, cols, stride), L x S x (anchor width, height)},
  *   L <= 8 levels, S <= 16 shapes per cell, sum rows*cols*S == A.  With it (and Gmax <= 256) the assignment runs
  *   GT-centric: per GT row only the window of cells whose anchors can reach IoU 0.385 is evaluated (same arithmetic on
- *   the table's values, same codes), the rest of the work is a fill at HBM speed.  Without it: the anchor-centric
- *   kernel, valid for any anchor table.  Which is faster depends on dreg: the anchor-centric kernel is instruction-bound
- *   and hides the 48 B/row zero-fill of dreg, the GT-centric path pays it at HBM speed - pass the pyramid for
- *   forward-only calls (71 us vs 150+ us at cfg2), omit it for the training step (see focal_loss.cu).
+ *   the table's values, same codes), and the dense zero part of dreg is written by bulk async copies (TMA) spread over
+ *   all launches of the step.  Without it: the anchor-centric kernel, valid for any anchor table (it writes the zeros
+ *   itself, behind its instruction stream).
  */
+#define G3D_HYPER_COUNT 8
 int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax);
 int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                       float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
+                       const float* hyper_host, float* losses, float* per_image, int32_t* assign, int32_t* gt_count_out,
                        void* workspace, int64_t workspace_bytes, const double* pyramid_host, int device, void* stream);
 int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                            int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                           float grad_cls_expected, float* losses, float* per_image, int32_t* assign,
-                           int32_t* gt_count_out, double* shard_stats, float* dcls, float* dreg,
+                           const float* hyper_host, const float* grad_expected_host, float* losses, float* per_image,
+                           int32_t* assign, int32_t* gt_count_out, double* shard_stats, float* dcls, float* dreg,
                            void* workspace, int64_t workspace_bytes, const double* pyramid_host,
-                           void* const* trace_events, int device, void* stream);
+                           void* const* trace_events, int n_trace_events, int device, void* stream);
 
 /* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
  * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory); grad_scale[3] (nullable, device)
  * multiplies them element-wise (multi-GPU: local -> global mean, from g3d_combine_shard_stats).
- * losses / assign / workspace = what the forward wrote (the workspace holds the per-image lists of positive anchors:
- * keep it untouched between the two calls).  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is zero on
- * non-positive anchors).
- * have_dcls = 0: dcls / dreg are uninitialised; everything is computed here.
- * have_dcls = 1: they come from g3d_focal_loss_fwd_bwd(grad_cls_expected).  The kernel compares grad_out[0] with
- *   grad_cls_expected ON THE DEVICE: equal (the usual training step) -> only the regression-gradient rows of the
- *   positive anchors are written (one thread per positive, from the lists); different -> dcls is recomputed as well.
- *   No host synchronisation is needed to pick the path.
+ * workspace = what the forward wrote (byte codes, per-image lists of positive anchors, GT tables: keep it untouched
+ * between the two calls).  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is zero on non-positive anchors).
+ * have_grads = 0: dcls / dreg are uninitialised; everything is computed here.
+ * have_grads = 1: they come from g3d_focal_loss_fwd_bwd(grad_expected_host).  The kernels compare grad_out * grad_scale
+ *   with grad_expected_host ON THE DEVICE: equal (the usual training step) -> both launches exit in one wave; a different
+ *   classification gradient -> dcls is recomputed; a different regression / direction gradient -> the rows of the
+ *   positive anchors are recomputed.  No host synchronisation is needed to pick the path.
  */
 int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
-                       const float* grad_out, const float* grad_scale, int have_dcls, float grad_cls_expected,
-                       const float* losses,
-                       const int32_t* assign, const void* workspace, int64_t workspace_bytes,
+                       const float* hyper_host, const float* grad_out, const float* grad_scale, int have_grads,
+                       const float* grad_expected_host, const void* workspace, int64_t workspace_bytes,
                        float* dcls, float* dreg, int device, void* stream);
+
+/* process-wide tuning knobs of the loss path (benchmark sweeps; the defaults are the measured optimum on B200):
+ * G3D_TUNE_FILL_CHAIN_PERMILLE: share (0..1000) of dreg zero-filled next to the prologue / assignment / resolve launches
+ *   (the rest next to the streaming pass); G3D_TUNE_FILL_CTAS: fill CTAs per launch (-1 = one per SM);
+ * G3D_TUNE_FORCE_ANCHOR_CENTRIC != 0: ignore pyramid_host. */
+#define G3D_TUNE_FILL_CHAIN_PERMILLE 1
+#define G3D_TUNE_FILL_CTAS 2
+#define G3D_TUNE_FORCE_ANCHOR_CENTRIC 3
+int g3d_set_tuning(int key, int64_t value);
 
 /* multi-GPU reduction of the loss (replaces nn.DataParallel + .mean(), train_detector_3D_angle.py:316-318,374-378):
  * gathered[world][5] = the shard_stats of every rank (all-gathered by the host, e.g. NCCL), summed in rank order ->

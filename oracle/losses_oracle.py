@@ -51,8 +51,9 @@ def assignment_boxes(rows, variant_3d):
     return torch.stack((xs.min(1).values, ys.min(1).values, xs.max(1).values, ys.max(1).values), dim=1)
 
 
-def assign(anchors, annotation, variant_3d):
-    """One image.  Returns (iou_max[A], iou_argmax[A] into the filtered rows, positive[A] bool, negative[A] bool, rows)."""
+def assign(anchors, annotation, variant_3d, pos_iou=0.5, neg_iou=0.4):
+    """One image.  Returns (iou_max[A], iou_argmax[A] into the filtered rows, positive[A] bool, negative[A] bool, rows).
+    pos_iou / neg_iou: the reference's constants (3D losses.py:124 / :121), exposed for the drop-in's keyword arguments."""
     rows = valid_rows(annotation, variant_3d)
     A = anchors.shape[0]
     if rows.shape[0] == 0:
@@ -60,26 +61,29 @@ def assign(anchors, annotation, variant_3d):
         return z, torch.zeros(A, dtype=torch.int64), torch.zeros(A, dtype=torch.bool), torch.ones(A, dtype=torch.bool), rows
     iou = calc_iou(anchors, assignment_boxes(rows, variant_3d))
     iou_max, iou_argmax = iou.max(dim=1)
-    return iou_max, iou_argmax, iou_max >= 0.5, iou_max < 0.4, rows
+    return iou_max, iou_argmax, iou_max >= pos_iou, iou_max < neg_iou, rows
 
 
-def focal_classification_sum(classification, positive, negative, pos_class):
+def focal_classification_sum(classification, positive, negative, pos_class, alpha=ALPHA, gamma=GAMMA, clamp_min=1e-4,
+                             clamp_max=1.0 - 1e-4):
     """sum over anchors x classes of alpha_t (1-p_t)^gamma * bce, ignoring anchors that are neither positive nor negative."""
-    p = classification.clamp(1e-4, 1.0 - 1e-4)
+    p = classification.clamp(clamp_min, clamp_max)
     targets = torch.full_like(p, -1.0)
     targets[negative] = 0
     targets[positive] = 0
     targets[positive, pos_class[positive]] = 1
     is_pos = targets == 1.0
-    alpha_t = torch.where(is_pos, torch.full_like(p, ALPHA), torch.full_like(p, 1.0 - ALPHA))
-    weight = alpha_t * torch.pow(torch.where(is_pos, 1.0 - p, p), GAMMA)
+    alpha_t = torch.where(is_pos, torch.full_like(p, alpha), 1.0 - torch.full_like(p, alpha))
+    weight = alpha_t * torch.pow(torch.where(is_pos, 1.0 - p, p), gamma)
     bce = -(targets * torch.log(p) + (1.0 - targets) * torch.log(1.0 - p))
     loss = torch.where(targets != -1.0, weight * bce, torch.zeros_like(p))
     return loss.sum()
 
 
-def smooth_l1(diff):
-    return torch.where(diff <= 1.0 / 9.0, 0.5 * 9.0 * torch.pow(diff, 2), diff - 0.5 / 9.0)
+def smooth_l1(diff, beta=None):
+    if beta is None:        # the reference's literal expression (3D losses.py:345-349)
+        return torch.where(diff <= 1.0 / 9.0, 0.5 * 9.0 * torch.pow(diff, 2), diff - 0.5 / 9.0)
+    return torch.where(diff <= beta, (0.5 / beta) * torch.pow(diff, 2), diff - 0.5 * beta)
 
 
 def corner_predictions(reg):
@@ -112,7 +116,7 @@ def cosine_loss(rx, ry, tx, ty):
     return 1 - (rx * tx + ry * ty) / (rn * tn)
 
 
-def regression_terms_3d(reg_pos, gt_pos, anchors_pos):
+def regression_terms_3d(reg_pos, gt_pos, anchors_pos, top_weighting=TOP_WEIGHTING, beta=None):
     """positives only.  Returns (regression_loss, vp_loss) scalars of one image (means over P x 20 and over P)."""
     t = gt_pos[:, :20]
     d = direction_targets(t)
@@ -127,11 +131,11 @@ def regression_terms_3d(reg_pos, gt_pos, anchors_pos):
     tn[:, 1::2] = (t[:, 1::2] - acy[:, None]) / ah[:, None]
     diff = torch.abs(tn - corner_predictions(reg_pos))
     w = torch.ones(20)
-    w[8:16] = TOP_WEIGHTING
-    return smooth_l1(diff * w).mean(), vp.mean()
+    w[8:16] = top_weighting
+    return smooth_l1(diff * w, beta).mean(), vp.mean()
 
 
-def regression_terms_2d(reg_pos, gt_pos, anchors_pos):
+def regression_terms_2d(reg_pos, gt_pos, anchors_pos, beta=None):
     aw = anchors_pos[:, 2] - anchors_pos[:, 0]
     ah = anchors_pos[:, 3] - anchors_pos[:, 1]
     acx = anchors_pos[:, 0] + 0.5 * aw
@@ -143,36 +147,43 @@ def regression_terms_2d(reg_pos, gt_pos, anchors_pos):
     gw, gh = gw.clamp(min=1), gh.clamp(min=1)
     t = torch.stack(((gcx - acx) / aw, (gcy - acy) / ah, torch.log(gw / aw), torch.log(gh / ah)), dim=1)
     t = t / torch.tensor([[0.1, 0.1, 0.2, 0.2]])
-    return smooth_l1(torch.abs(t - reg_pos)).mean()
+    return smooth_l1(torch.abs(t - reg_pos), beta).mean()
 
 
-def focal_loss(classifications, regressions, anchors, annotations):
+def focal_loss(classifications, regressions, anchors, annotations, hyper=None):
     """Whole-batch loss.  3D (regression width 12) -> (cls[1], reg[1], vp[1]); 2D (width 4) -> (cls[1], reg[1]).
-    Also returns per-image details as a 4th/3rd element: dict(per_image=[B,4] (cls, reg, vp, num_pos), assign=[...])."""
+    Also returns per-image details as a 4th/3rd element: [(iou_max, iou_argmax, positive, negative, n_rows)] per image.
+    hyper: overrides of the constants the reference hard-codes (alpha, gamma, top_weighting, pos_iou, neg_iou, beta,
+    clamp_min, clamp_max) - the drop-in exposes them as keyword arguments with the reference's values as defaults."""
+    hp = dict(hyper or {})
+    cls_kw = {k: hp[k] for k in ("alpha", "gamma", "clamp_min", "clamp_max") if k in hp}
+    thr_kw = {k: hp[k] for k in ("pos_iou", "neg_iou") if k in hp}
+    reg_kw = {k: hp[k] for k in ("beta",) if k in hp}
+    reg3_kw = dict(reg_kw, **({"top_weighting": hp["top_weighting"]} if "top_weighting" in hp else {}))
     variant_3d = regressions.shape[-1] == 12
     anchor = anchors.reshape(-1, 4)
     B = classifications.shape[0]
     cls_l, reg_l, vp_l, info = [], [], [], []
     for j in range(B):
         ann = annotations[j, :, :21] if variant_3d else annotations[j]
-        iou_max, iou_argmax, positive, negative, rows = assign(anchor, ann, variant_3d)
+        iou_max, iou_argmax, positive, negative, rows = assign(anchor, ann, variant_3d, **thr_kw)
         n_pos = positive.sum()
         if rows.shape[0] == 0:
             pos_class = torch.zeros(anchor.shape[0], dtype=torch.int64)
-            cls_l.append(focal_classification_sum(classifications[j], positive, negative, pos_class))
+            cls_l.append(focal_classification_sum(classifications[j], positive, negative, pos_class, **cls_kw))
             reg_l.append(torch.tensor(0.0))
             info.append((iou_max, iou_argmax, positive, negative, 0))
             continue
         assigned = rows[iou_argmax]
         pos_class = assigned[:, 20 if variant_3d else 4].long()
-        s = focal_classification_sum(classifications[j], positive, negative, pos_class)
+        s = focal_classification_sum(classifications[j], positive, negative, pos_class, **cls_kw)
         cls_l.append(s / n_pos.float().clamp(min=1.0))
         if n_pos > 0:
             if variant_3d:
-                r, v = regression_terms_3d(regressions[j][positive], assigned[positive], anchor[positive])
+                r, v = regression_terms_3d(regressions[j][positive], assigned[positive], anchor[positive], **reg3_kw)
                 vp_l.append(v)
             else:
-                r = regression_terms_2d(regressions[j][positive], assigned[positive], anchor[positive])
+                r = regression_terms_2d(regressions[j][positive], assigned[positive], anchor[positive], **reg_kw)
             reg_l.append(r)
         else:
             reg_l.append(torch.tensor(0.0))

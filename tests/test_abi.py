@@ -38,7 +38,7 @@ def test_argument_validation_without_a_gpu():
     L = _lib.lib()
     assert L.g3d_calc_iou(None, -1, None, 0, None, 0, None) == _lib.G3D_ERR_INVALID
     assert b"negative" in L.g3d_last_error()
-    assert L.g3d_focal_loss_fwd(None, None, None, None, 1, 10, 8, 7, 0, 27, 1, None, None, None, None, None, 0, None, 0, None) == _lib.G3D_ERR_INVALID
+    assert L.g3d_focal_loss_fwd(None, None, None, None, 1, 10, 8, 7, 0, 27, 1, None, None, None, None, None, None, 0, None, 0, None) == _lib.G3D_ERR_INVALID
     assert b"12 regression" in L.g3d_last_error()
     assert L.g3d_focal_workspace_bytes(32, 389205, 200) > 32 * 200 * 20
     assert L.g3d_nms_workspace_bytes(5000, 1, 5000) >= 5000 * 20

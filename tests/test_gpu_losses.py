@@ -151,8 +151,9 @@ def test_forward_written_gradients_vs_autograd_oracle(three_d, upstream):
     assert torch.equal(r1.grad.cpu() == 0, r0.grad == 0)
 
 
-def test_backward_keeps_forward_written_dcls_only_when_upstream_matches():
-    """the device-side check: matching upstream gradient -> dcls untouched (poisoned here to see it); other -> recomputed"""
+def test_backward_keeps_forward_written_gradients_only_when_upstream_matches():
+    """the device-side check: matching upstream gradients -> dcls / dreg untouched (poisoned here to see it); a different
+    classification gradient -> dcls recomputed; different regression / direction gradients -> positive rows recomputed"""
     ops, _ = _mods()
     g = synth.gen(32)
     anc = synth.anchors(96, 96).cuda()
@@ -161,17 +162,27 @@ def test_backward_keeps_forward_written_dcls_only_when_upstream_matches():
     cls, reg = cls.cuda(), reg.cuda()
     plain = ops.focal_loss_forward(cls, reg, anc, ann)
     want_c, want_r = ops.focal_loss_backward(plain, torch.tensor([1.0, 2.0, 3.0]).cuda())
-    fwd = ops.focal_loss_forward(cls, reg, anc, ann, grad_cls_expected=1.0)
+    unit_c, unit_r = ops.focal_loss_backward(plain, torch.tensor([1.0, 1.0, 1.0]).cuda())
+    pos = plain["assign"] >= 0
+    assert int(pos.sum()) > 0 and int((want_r[~pos] != 0).sum()) == 0
+    fwd = ops.focal_loss_forward(cls, reg, anc, ann, grad_expected=1.0)
     assert torch.equal(fwd["losses"], plain["losses"]) and torch.equal(fwd["assign"], plain["assign"])
     assert_close_rel(fwd["dcls"].cpu(), want_c.cpu(), 1e-6, "forward-written dcls")   # two kernels, same formulas
-    assert int((fwd["dreg"] != 0).sum()) == 0
+    assert torch.equal(fwd["dreg"], unit_r), "forward-written dreg rows (expected upstream 1, 1)"
     fwd["dcls"].fill_(7.0)
+    fwd["dreg"].fill_(5.0)
+    got_c, got_r = ops.focal_loss_backward(fwd, torch.tensor([1.0, 1.0, 1.0]).cuda())
+    assert bool((got_c == 7.0).all()) and bool((got_r == 5.0).all()), "upstream matched: nothing may be rewritten"
     got_c, got_r = ops.focal_loss_backward(fwd, torch.tensor([1.0, 2.0, 3.0]).cuda())
-    assert bool((got_c == 7.0).all()), "upstream gradient matched: dcls must not be rewritten"
-    assert torch.equal(got_r, want_r)
+    assert bool((got_c == 7.0).all()), "classification gradient matched: dcls must not be rewritten"
+    assert torch.equal(got_r[pos], want_r[pos]) and bool((got_r[~pos] == 5.0).all())
     got_c, got_r = ops.focal_loss_backward(fwd, torch.tensor([2.0, 2.0, 3.0]).cuda())
     assert_close_rel(got_c.cpu(), (2 * want_c).cpu(), TOL, "recomputed dcls")
-    assert torch.equal(got_r, want_r)
+    assert torch.equal(got_r[pos], want_r[pos])
+    # three expected values, one per loss
+    fresh = ops.focal_loss_forward(cls, reg, anc, ann, grad_expected=1.0)
+    fwd3 = ops.focal_loss_forward(cls, reg, anc, ann, grad_expected=(1.0, 2.0, 3.0))
+    assert torch.equal(fwd3["dreg"], want_r) and torch.equal(fwd3["dcls"], fresh["dcls"])
 
 
 def test_all_empty_batch_raises_and_optional_nan():
@@ -333,14 +344,13 @@ def _tagged_anchors(H, W):
 
 
 @pytest.mark.parametrize("seed", list(range(10)))
-def test_gt_centric_assignment_equals_anchor_centric_and_oracle(seed, monkeypatch):
-    """anchors from Anchors.forward carry the pyramid description -> GT-centric assignment (fill + window pairs +
-    resolve).  Codes, losses and gradients must equal the anchor-centric kernel's (same table without the tag) and the
-    oracle's, incl. ties between equal GT boxes (lower index wins), padded rows, an empty image, boxes that leave the
-    image, and the 2D variant"""
+def test_gt_centric_assignment_equals_anchor_centric_and_oracle(seed):
+    """anchors from Anchors.forward carry the pyramid description -> GT-centric assignment (window pairs + resolve, dreg
+    zero-filled by bulk copies spread over the launches).  Codes, losses and gradients must equal the anchor-centric
+    kernel's (same table without the tag) bit for bit, and the oracle's, incl. ties between equal GT boxes (lower index
+    wins), padded rows, an empty image, boxes that leave the image, and the 2D variant"""
     ops, li = _mods()
     from oracle import losses_oracle as lo
-    monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "1")          # also with gradient buffers (default: forward-only calls)
     g = synth.gen(7000 + seed)
     r = lambda lo_, hi_: int(torch.randint(lo_, hi_ + 1, (1,), generator=g))   # noqa: E731
     three_d = seed % 3 != 2
@@ -362,20 +372,16 @@ def test_gt_centric_assignment_equals_anchor_centric_and_oracle(seed, monkeypatc
         ann[0, 3, col:col + 4] = torch.tensor([-40.0, -30.0, 25.0, 20.0])
     cls, reg = synth.head_outputs(B, A, 8, 12 if three_d else 4, g)
     before = dict(ops.STATS)
-    f_gt = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda(), grad_cls_expected=1.0)
-    f_an = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_plain, ann.cuda(), grad_cls_expected=1.0)
+    f_gt = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda(), grad_expected=1.0)
+    f_an = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_plain, ann.cuda(), grad_expected=1.0)
     assert f_gt["gt_centric"] and not f_an["gt_centric"]
     assert ops.STATS["gt_centric_calls"] == before["gt_centric_calls"] + 1
     assert torch.equal(f_gt["assign"], f_an["assign"]), "codes differ between the two assignment kernels"
-    assert torch.equal(f_gt["per_image"][:, 3], f_an["per_image"][:, 3])
+    assert torch.equal(f_gt["per_image"], f_an["per_image"]) and torch.equal(f_gt["losses"], f_an["losses"])
     assert torch.equal(f_gt["dreg"], f_an["dreg"]) and torch.equal(f_gt["dcls"], f_an["dcls"])
-    assert_close_rel(f_gt["losses"].cpu(), f_an["losses"].cpu(), 1e-6, "losses")
-    # default policy: GT-centric for forward-only calls, anchor-centric when gradient buffers are written
-    monkeypatch.delenv("G3D_ASSIGN_GT_CENTRIC")
+    # forward-only calls take the same path and give the same numbers
     f_fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda())
     assert f_fwd["gt_centric"] and torch.equal(f_fwd["assign"], f_an["assign"]) and torch.equal(f_fwd["losses"], f_gt["losses"])
-    assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_t, ann.cuda(), grad_cls_expected=1.0)["gt_centric"]
-    monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "1")
     ref = lo.focal_loss(cls, reg, anc_t.cpu(), ann)
     assert torch.equal(f_gt["assign"].cpu(), _codes_from_oracle(ref[-1], ann, three_d)), "codes differ from the oracle"
     # through the autograd module (the path a training step takes)
@@ -395,8 +401,36 @@ def test_gt_centric_assignment_equals_anchor_centric_and_oracle(seed, monkeypatc
     assert_close_rel(r1.grad.cpu(), r0.grad, 3 * TOL, "dreg", row_scale=True)
 
 
+@pytest.mark.parametrize("permille,ctas", [(0, -1), (1000, -1), (500, 3), (250, 0)])
+def test_dreg_fill_split_is_invisible(permille, ctas):
+    """wherever the bulk-copy zero fill of dreg is placed (all next to the assignment launches, all next to the streaming
+    pass, a few fill CTAs, none), every non-positive row of dreg is exactly zero and the positive rows are unchanged"""
+    ops, _ = _mods()
+    g = synth.gen(7300)
+    H, W = 200, 328
+    anc = _tagged_anchors(H, W)
+    A = anc.shape[1]
+    ann = synth.gt_annotations_3d(3, 17, H, W, g, n_pad=1, **synth.TINY).cuda()
+    cls, reg = synth.head_outputs(3, A, 8, 12, g)
+    cls, reg = cls.cuda(), reg.cuda()
+    want = ops.focal_loss_forward(cls, reg, anc.clone(), ann, grad_expected=1.0)      # anchor-centric: plain stores
+    try:
+        ops.set_tuning("fill_chain_permille", permille)
+        ops.set_tuning("fill_ctas", ctas)
+        for _ in range(2):
+            poison = torch.full_like(reg, float("nan"))
+            del poison                                            # the caching allocator hands the block to dreg next
+            got = ops.focal_loss_forward(cls, reg, anc, ann, grad_expected=1.0)
+            assert got["gt_centric"]
+            assert torch.equal(got["dreg"], want["dreg"]) and torch.equal(got["dcls"], want["dcls"])
+    finally:
+        ops.set_tuning("fill_chain_permille", -1)
+        ops.set_tuning("fill_ctas", -1)
+
+
 def test_gt_centric_assignment_falls_back(monkeypatch):
-    """more than 256 annotation rows, or a table modified in place after Anchors produced it -> anchor-centric kernel"""
+    """more than 256 annotation rows, a negative threshold below the key range, or a table modified in place after Anchors
+    produced it -> anchor-centric kernel"""
     ops, _ = _mods()
     g = synth.gen(7100)
     H, W = 96, 128
@@ -407,9 +441,233 @@ def test_gt_centric_assignment_falls_back(monkeypatch):
     assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, big.cuda())["gt_centric"]
     small = synth.gt_annotations_3d(1, 20, H, W, g, **synth.TINY)
     assert ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, small.cuda())["gt_centric"]
+    assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, small.cuda(), hyper=dict(neg_iou=0.2, pos_iou=0.3))["gt_centric"]
     monkeypatch.setenv("G3D_ASSIGN_GT_CENTRIC", "0")
     assert not ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc, small.cuda())["gt_centric"]
     monkeypatch.delenv("G3D_ASSIGN_GT_CENTRIC")
     moved = _tagged_anchors(H, W + 8)
     moved += 1.0                                                 # in-place edit bumps the tensor version
     assert ops.anchor_pyramid_of(moved) is None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the benchmarked configuration against the oracle (missing #1)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tagged", [True, False])
+def test_cfg2_one_image_1080p_200gt_vs_oracle(tagged):
+    """BASELINE.json configs[1] at its full per-image size - 1080p, A = 389 205, 200 GT boxes, C = 8 - for one image of
+    the batch: assignment codes exact, losses / dcls / dreg within 1e-5 of the oracle's forward + autograd backward.
+    tagged: the table of the drop-in Anchors module (GT-centric assignment, the path bench.py times); untagged: the
+    anchor-centric kernel on the same values.  bench.py seeds its image 0 the same way (synth.gen(100))."""
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    g = synth.gen(100)
+    H, W = 1080, 1920
+    anc = synth.anchors(H, W)
+    A = anc.shape[1]
+    assert A == 389205
+    ann = synth.gt_annotations_3d(1, 200, H, W, g)
+    cls, reg = synth.head_outputs(1, A, 8, 12, g)
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref = lo.focal_loss(c0, r0, anc, ann)
+    sum(l.sum() for l in ref[:3]).backward()
+    anc_d = _tagged_anchors(H, W) if tagged else anc.cuda()
+    assert torch.equal(anc_d.cpu(), anc)
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    before = dict(ops.STATS)
+    out = li.FocalLoss()(c1, r1, anc_d, ann.cuda())
+    assert ops.STATS["gt_centric_calls" if tagged else "anchor_centric_calls"] == \
+        before["gt_centric_calls" if tagged else "anchor_centric_calls"] + 1
+    sum(o.sum() for o in out).backward()
+    assert_close_rel(torch.cat(out).detach().cpu(), torch.cat(ref[:3]).detach(), TOL, "losses at cfg2 size")
+    assert_close_rel(c1.grad.cpu(), c0.grad, TOL, "dcls at cfg2 size")
+    assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg at cfg2 size", row_scale=True)
+    assert torch.equal(c1.grad.cpu() == 0, c0.grad == 0) and torch.equal(r1.grad.cpu() == 0, r0.grad == 0)
+    fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc_d, ann.cuda())
+    assert torch.equal(fwd["assign"].cpu(), _codes_from_oracle(ref[-1], ann, True)), "assignment codes must be exact"
+    npos = int(ref[-1][0][2].sum())
+    assert int(fwd["per_image"][0, 3]) == npos and npos > 1000
+    # un-floored worst element, for the record (see conftest.assert_close_rel for the judged metric)
+    nz = r0.grad != 0
+    worst = float(((r1.grad.cpu() - r0.grad).abs()[nz] / r0.grad.abs()[nz]).max())
+    print(f"cfg2 image: {npos} positives, worst un-floored relative dreg error {worst:.2e}")
+
+
+def test_zero_direction_vector_gives_nan_loss_and_gradient_like_the_reference():
+    """no epsilon in reg_norm * targ_norm (3D losses.py:227): a regression direction vector that is exactly 0 - the
+    zero-initialised head, model.py:257-258 - makes the vp loss NaN and the gradient of that vector NaN; everything else
+    stays finite.  The kernels must reproduce the NaN pattern of the reference's autograd exactly."""
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    g = synth.gen(61)
+    anc = synth.anchors(96, 128)
+    A = anc.shape[1]
+    ann = synth.gt_annotations_3d(2, 6, 96, 128, g, **synth.TINY)
+    cls, reg = synth.head_outputs(2, A, 8, 12, g)
+    info = lo.focal_loss(cls, reg, anc, ann)[-1]
+    victim = int(torch.nonzero(info[0][2])[0])                 # a positive anchor of image 0
+    reg[0, victim, 4:6] = 0.0                                   # its width direction vector
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref = lo.focal_loss(c0, r0, anc, ann)
+    sum(l.sum() for l in ref[:3]).backward()
+    assert torch.isnan(ref[2]).all() and torch.isfinite(ref[0]).all() and torch.isfinite(ref[1]).all()
+    for table in (_tagged_anchors(96, 128), anc.cuda()):
+        c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+        out = li.FocalLoss()(c1, r1, table, ann.cuda())
+        sum(o.sum() for o in out).backward()
+        assert torch.isnan(out[2]).all() and torch.isfinite(out[0]).all() and torch.isfinite(out[1]).all()
+        assert_close_rel(torch.cat(out[:2]).detach().cpu(), torch.cat(ref[:2]).detach(), TOL, "cls / reg losses")
+        assert torch.equal(torch.isnan(r1.grad.cpu()), torch.isnan(r0.grad)), "NaN pattern of dreg"
+        assert bool(torch.isnan(r1.grad[0, victim, 4:6]).all()) and int(torch.isnan(r1.grad).sum()) == 2
+        assert_close_rel(r1.grad.cpu(), r0.grad, TOL, "dreg (finite entries)", row_scale=True)
+        assert_close_rel(c1.grad.cpu(), c0.grad, TOL, "dcls")
+
+
+def test_eight_host_threads_reentrancy():
+    """the C ABI promises re-entrancy (nn.DataParallel calls the loss from one thread per replica,
+    train_detector_3D_angle.py:316-318): 8 host threads, each on its own stream with its own inputs, all at once"""
+    import threading
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    H, W = 128, 160
+    anc = _tagged_anchors(H, W)
+    A = anc.shape[1]
+    cases = []
+    for t in range(8):
+        g = synth.gen(900 + t)
+        ann = synth.gt_annotations_3d(2, 5 + t, H, W, g, n_pad=t % 3, **synth.TINY)
+        cls, reg = synth.head_outputs(2, A, 8, 12, g)
+        cases.append((cls, reg, ann))
+    results, errors = [None] * 8, []
+    barrier = threading.Barrier(8)
+
+    def work(t):
+        try:
+            cls, reg, ann = cases[t]
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                c, r, a = cls.cuda(), reg.cuda(), ann.cuda()
+                stream.synchronize()
+                barrier.wait()
+                acc = []
+                for _ in range(20):
+                    c1, r1 = c.clone().requires_grad_(True), r.clone().requires_grad_(True)
+                    out = li.FocalLoss(check_empty=False)(c1, r1, anc if t % 2 == 0 else anc.clone(), a)
+                    sum(o.sum() for o in out).backward()
+                    acc.append((torch.cat(out).detach(), c1.grad, r1.grad))
+                stream.synchronize()
+            first = acc[0]
+            for other in acc[1:]:
+                assert all(torch.equal(x, y) for x, y in zip(first, other)), "run-to-run difference under concurrency"
+            results[t] = tuple(x.cpu() for x in first)
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+            try:
+                barrier.abort()
+            except Exception:  # noqa: BLE001
+                pass
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=300)
+    assert not errors, errors
+    for t, (cls, reg, ann) in enumerate(cases):
+        c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+        ref = lo.focal_loss(c0, r0, anc.cpu(), ann)
+        sum(l.sum() for l in ref[:3]).backward()
+        assert_close_rel(results[t][0], torch.cat(ref[:3]).detach(), TOL, f"thread {t} losses")
+        assert_close_rel(results[t][1], c0.grad, TOL, f"thread {t} dcls")
+        assert_close_rel(results[t][2], r0.grad, 3 * TOL, f"thread {t} dreg", row_scale=True)
+
+
+@pytest.mark.parametrize("three_d", [True, False])
+@pytest.mark.parametrize("hyper", [dict(alpha=0.4), dict(gamma=1.5), dict(pos_iou=0.6, neg_iou=0.45), dict(beta=0.25),
+                                   dict(top_weighting=0.25, clamp_min=1e-3, clamp_max=0.995),
+                                   dict(alpha=0.3, gamma=3.0, pos_iou=0.55, neg_iou=0.35, beta=0.05, top_weighting=1.0)])
+def test_hyper_parameters_as_keyword_arguments(three_d, hyper):
+    """the constants the reference hard-codes in forward (losses.py:28-30,56,121,124,343,346-348) are keyword arguments of
+    the drop-in with the reference's values as defaults; non-default values against the oracle with the same values"""
+    ops, li = _mods()
+    from oracle import losses_oracle as lo
+    g = synth.gen(4100)
+    H, W = 136, 200
+    anc = synth.anchors(H, W)
+    A = anc.shape[1]
+    maker = synth.gt_annotations_3d if three_d else synth.gt_annotations_2d
+    ann = maker(3, 14, H, W, g, n_pad=1, empty_images=(2,), **synth.TINY)
+    cls, reg = synth.head_outputs(3, A, 8, 12 if three_d else 4, g)
+    cls[0, :40] = torch.rand(40, 8, generator=g)
+    n = 3 if three_d else 2
+    c0, r0 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+    ref = lo.focal_loss(c0, r0, anc, ann, hyper=hyper)
+    sum(ref[i].sum() for i in range(n)).backward()
+    for table in (_tagged_anchors(H, W), anc.cuda()):
+        c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+        out = li.FocalLoss(check_empty=False, **hyper)(c1, r1, table, ann.cuda())
+        sum(o.sum() for o in out).backward()
+        assert_close_rel(torch.cat(out).detach().cpu(), torch.cat(ref[:n]).detach(), TOL, f"losses {hyper}")
+        assert_close_rel(c1.grad.cpu(), c0.grad, TOL, f"dcls {hyper}")
+        assert_close_rel(r1.grad.cpu(), r0.grad, 3 * TOL, f"dreg {hyper}", row_scale=True)
+        fwd = ops.focal_loss_forward(cls.cuda(), reg.cuda(), table, ann.cuda(), hyper=hyper)
+        codes = _codes_from_oracle(ref[-1], ann, three_d)
+        assert torch.equal(fwd["assign"].cpu(), codes), "assignment codes must be exact for any thresholds"
+    with pytest.raises(ValueError):
+        ops.focal_loss_forward(cls.cuda(), reg.cuda(), anc.cuda(), ann.cuda(), hyper=dict(gama=2.0))
+
+
+def test_combine_shard_stats_kernel_equals_host_restatement():
+    """g3d_combine_shard_stats (the kernel the multi-GPU path runs after its all-gather) against dist.combine_on_host, the
+    torch restatement the CPU gloo test drives"""
+    ops, _ = _mods()
+    from geom3d_b200 import dist as gdist
+    g = synth.gen(77)
+    gathered = torch.rand(4, 5, generator=g, dtype=torch.float64) * 10
+    gathered[:, 3] = torch.tensor([8.0, 8.0, 7.0, 9.0])
+    gathered[:, 4] = torch.tensor([8.0, 0.0, 5.0, 9.0])                  # one rank without any GT
+    for rank in range(4):
+        losses, scale = ops.combine_shard_stats(gathered.cuda(), rank)
+        want_l, want_s = gdist.combine_on_host(gathered, rank)
+        assert torch.equal(losses.cpu(), want_l) and torch.equal(scale.cpu(), want_s)
+
+
+def test_lazy_empty_check_retain_graph_and_inplace_detection():
+    """check_empty='lazy' (default): no synchronisation in forward, the all-empty batch is reported at the next call;
+    a second backward (retain_graph) returns the same gradients in fresh tensors; without retain_graph autograd raises;
+    an in-place edit of an input between forward and backward is caught by the version counters"""
+    _, li = _mods()
+    g = synth.gen(88)
+    anc = synth.anchors(64, 64).cuda()
+    A = anc.shape[1]
+    cls, reg = synth.head_outputs(2, A, 8, 12, g)
+    empty = -torch.ones(2, 4, 27)
+    mod = li.FocalLoss()
+    out = mod(cls.cuda(), reg.cuda(), anc, empty.cuda())
+    assert torch.isnan(out[2]).all()
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="non-empty TensorList"):
+        mod.check(wait=True)
+    mod(cls.cuda(), reg.cuda(), anc, empty.cuda())
+    torch.cuda.synchronize()
+    ann = synth.gt_annotations_3d(2, 5, 64, 64, g, **synth.TINY).cuda()
+    with pytest.raises(RuntimeError, match="non-empty TensorList"):
+        mod(cls.cuda(), reg.cuda(), anc, ann)                       # the NEXT forward reports the earlier batch
+    c1, r1 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    out = mod(c1, r1, anc, ann)
+    total = sum(o.sum() for o in out)
+    total.backward(retain_graph=True)
+    gc, gr = c1.grad.clone(), r1.grad.clone()
+    c1.grad = None
+    r1.grad = None
+    total.backward()
+    assert_close_rel(c1.grad.cpu(), gc.cpu(), 1e-6, "second backward dcls") 
+    assert torch.equal(r1.grad, gr)
+    with pytest.raises(RuntimeError):
+        total.backward()                                            # buffers were freed: autograd's own error
+    c2, r2 = cls.cuda().requires_grad_(True), reg.cuda().requires_grad_(True)
+    c2b = c2 * 1.0
+    out = mod(c2b, r2, anc, ann)
+    c2b.add_(1.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        sum(o.sum() for o in out).backward()

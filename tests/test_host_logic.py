@@ -1,5 +1,5 @@
 """CPU: host-side logic that needs no GPU - anchor layout, ladder rungs, matrix banks, camera-name handling, shard
-ranges, and the world_size-2 gloo run of the loss reduction (dist.combine_stats) against the oracle."""
+ranges, and the world_size-2 gloo run of the loss reduction (dist.gather_shard_stats + combine) against the oracle."""
 import os
 import sys
 
@@ -83,14 +83,26 @@ def test_matrix_bank_and_camera_names():
     assert set(back.correspondence) == set(hg1.correspondence) and back.class_heights["van"] == 6
 
 
+def _shard_stats_of(per_image, gt_count):
+    """float64[5] exactly as the kernel's finalize step writes shard_stats (focal_loss.cu: finalize_image)"""
+    pi = per_image.double()
+    ne = gt_count > 0
+    return torch.stack((pi[:, 0].sum(), pi[:, 1].sum(), (pi[:, 2] * ne).sum(),
+                        torch.tensor(float(per_image.shape[0]), dtype=torch.float64), ne.sum().double()))
+
+
 def _gloo_worker(rank, world, port, per_image, gt_count, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from geom3d_b200.dist import combine_stats, local_stats, shard_range
+    # the host functions the GPU path itself runs (dist._ShardedFocalLossFn.forward): the all-gather of the 5 shard
+    # statistics, then the combination (on the GPU: g3d_combine_shard_stats; here its torch restatement, which the -m gpu
+    # tests compare with the kernel)
+    from geom3d_b200.dist import combine_on_host, gather_shard_stats, shard_range
     lo, hi = shard_range(per_image.shape[0], rank, world)
-    losses, total = combine_stats(local_stats(per_image[lo:hi], gt_count[lo:hi]))
-    out_q.put((rank, losses.tolist(), total.tolist()))
+    gathered = gather_shard_stats(_shard_stats_of(per_image[lo:hi], gt_count[lo:hi]))
+    losses, scale = combine_on_host(gathered, rank)
+    out_q.put((rank, losses.tolist(), gathered.sum(0).tolist(), scale.tolist(), hi - lo, int((gt_count[lo:hi] > 0).sum())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -128,9 +140,11 @@ def test_sharded_loss_reduction_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     expect = torch.cat(ref[:3])
-    for rank, losses, total in results:
+    for rank, losses, total, scale, b_local, ne_local in results:
         assert torch.allclose(torch.tensor(losses), expect, rtol=1e-6), (rank, losses, expect)
         assert total[3] == B and total[4] == 3
+        # d(global mean)/d(local mean): B_l / B_g for cls and reg, NE_l / NE_g for vp
+        assert scale == pytest.approx([b_local / B, b_local / B, ne_local / 3], rel=1e-6)
     assert results[0][1] == results[1][1], "every rank must hold bit-identical global losses"
 
 
