@@ -20,7 +20,7 @@ VARIANT_2D = 0
 VARIANT_3D = 1
 ASSIGN_IGNORE = -2
 ASSIGN_NEGATIVE = -1
-TUNE_KEYS = {"fill_chain_permille": 1, "fill_ctas": 2, "force_anchor_centric": 3}
+TUNE_KEYS = {"pdl": 1, "force_anchor_centric": 3}
 
 _c_ptr = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -43,7 +43,7 @@ SIGNATURES = {
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64,
                                       _c_ptr, _c_ptr, _int, _int, _c_ptr]),
     "g3d_focal_loss_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
-                                  _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
+                                  _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_set_tuning": (_int, [_int, _i64]),
     "g3d_combine_shard_stats": (_int, [_c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_decode3d": (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr, _int, _c_ptr]),

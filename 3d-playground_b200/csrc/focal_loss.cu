@@ -3,33 +3,37 @@
 //   3D: pytorch_retinanet_detector_directional/retinanet/losses.py:27-362
 //   2D: retinanet/losses.py:27-177
 //
-// One training step (forward + every gradient for the expected upstream gradients) is five launches; the backward
+// One training step (forward + every gradient for the expected upstream gradients) is four launches; the backward
 // call adds one that only verifies the expectation on the device.
 //
 //   K0 loss_prologue_kernel   one CTA per image: drop class == -1 rows, the 2D box each GT row is matched with, a
 //                             128-byte table row per GT (regression targets, direction vectors), the class; zero the
-//                             counters.
+//                             counters; `nfill` extra CTAs zero the keys / chunk mask of the GT-centric assignment with
+//                             bulk async copies.
 //   K1 assignment, one of
 //      assign_pairs_kernel    (anchors = the regular pyramid of Anchors.forward, <= 256 GT rows) GT-centric: one warp per
 //                             (image, GT row) evaluates only the window of cells whose anchors can reach the negative
-//                             threshold and atomicMax-es a 32-bit (IoU, GT index) key per (image, anchor);
-//      assign_codes_kernel    (any anchor table) anchor-centric tiles with GT culling.
-//   K2 assign_resolve_kernel  (GT-centric only) keys -> one byte code per (image, anchor) + the per-image lists of
-//                             positive anchors (anchor index, GT index).
-//   K3 focal_stream_kernel    the HBM-bound sweep: reads cls (one 8-class row per lane, 256-bit loads) and the byte
-//                             codes, evaluates focal terms AND their gradient from one -log(1-p) (packed FP32x2
-//                             arithmetic), writes dcls (256-bit stores) and per-CTA partial sums.
-//   K4 positives_kernel       one thread per positive anchor: 20 smooth-L1 terms + 3 direction cosines, their
-//                             gradient row written into dreg; exact fixed-point sums; the last CTA of an image reduces
-//                             the image, the last image forms the batch means (no host synchronisation).
+//                             threshold and atomicMax-es a 32-bit (IoU, GT index) key per (image, anchor); a chunk mask
+//                             records which 32-anchor chunks hold a key at all (a few percent);
+//      assign_codes_kernel    (any anchor table) anchor-centric tiles with GT culling -> byte codes + positives lists.
+//   K2 assign_resolve_kernel  (GT-centric only) touched chunks -> per-image lists of positive anchors (anchor, GT index),
+//                             their count (the normaliser of everything that follows).
+//   K3 focal_stream_kernel    the HBM-bound sweep AND, as a second CTA role in the same launch, the positive anchors:
+//        stream CTAs          read cls (one 8-class row per lane, 256-bit loads) and the keys of touched chunks, evaluate
+//                             focal terms AND their gradient from one -log(1-p) (packed FP32x2 arithmetic), write dcls
+//                             (256-bit stores), per-CTA partial sums, and zero-fill dreg (below);
+//        positives CTAs       one thread per positive anchor from the lists: 20 smooth-L1 terms + 3 direction cosines,
+//                             their gradient row written into dreg; exact fixed-point sums.  Latency-bound work that hides
+//                             completely behind the sweep.
+//        the last CTA of an image (ticket) reduces the image, the last image forms the batch means: no host
+//        synchronisation, no further launch.
 //
 // The regression gradient dreg is zero except on the ~1 % positive rows, but autograd needs it dense: 48 B/row of
-// zeros, 41 % of all bytes the step writes.  It is written by bulk async copies (cp.async.bulk shared -> global, TMA)
-// of a zeroed shared-memory tile, issued by ONE thread per CTA: no LSU issue slots, no registers.  The fill is spread
-// over the step so that HBM is busy all the time: the latency-bound kernels K0-K2 carry `nfill` extra CTAs (one per
-// SM) that fill the first part while the assignment runs, every CTA of K3 fills its share of the rest next to the
-// streaming work (which is limited by issue slots and latency, not by the store path).  The anchor-centric kernel
-// (issue-bound, HBM idle) writes the zeros itself.
+// zeros, 41 % of all bytes the step writes.  The stream CTAs write them with bulk async copies (cp.async.bulk shared ->
+// global, TMA) of a zeroed shared-memory tile, issued by ONE lane per warp for the warp's 256 rows: no LSU issue slots,
+// no registers.  Only chunks that hold a key are written with ordinary stores, lane by lane, and the lanes of positive
+// rows write nothing - those rows belong to the positives CTAs, so the two roles never touch the same bytes and need
+// no ordering.  The anchor-centric kernel (issue-bound, HBM idle) writes the zeros itself, before K3.
 //
 // Gradients written during the forward assume the upstream gradients the host announces (1 for `(cls + reg +
 // vp).backward()`, 1/world under dist.py).  g3d_focal_loss_bwd checks the assumption ON THE DEVICE and recomputes
@@ -50,12 +54,38 @@ constexpr int kCodeNegative = 0, kCodeIgnore = 1, kCodePositive = 2;   // positi
 
 __device__ __forceinline__ int code8_of_class(int cls, int C) { return (cls >= 0 && cls < C && cls < 253) ? kCodePositive + cls : 255; }
 
+// Where the streaming pass finds the assignment of a row.  Anchor-centric path: one byte per (image, anchor).  GT-centric
+// path: the 32-bit keys themselves, read only for the 32-anchor chunks whose bit is set in the chunk mask (a few percent
+// of all chunks hold a key at all).
+struct CodeSrc {
+    const uint8_t* code8;      // [B][Ap] or null
+    const uint32_t* keys;      // [B][Ap]
+    const uint32_t* mask;      // [B][MW]: bit (a >> 5) & 31 of word a >> 10 = chunk a >> 5 holds at least one key
+    const int32_t* gt_cls;     // [B][Gmax]
+    int Ap, MW, Gmax, C;
+    float pos_thr;
+    unsigned neg_thr_bits;
+};
+__device__ __forceinline__ float key_iou(unsigned key, unsigned neg_thr_bits) { return __uint_as_float((key >> 8) - 1u + neg_thr_bits); }
+__device__ __forceinline__ int key_gt(unsigned key) { return 255 - (int)(key & 255u); }
+// non-zero key -> byte code
+__device__ __forceinline__ int code_of_key(const CodeSrc& s, int b, unsigned key) {
+    if (!(key_iou(key, s.neg_thr_bits) >= s.pos_thr)) return kCodeIgnore;
+    return code8_of_class(__ldg(s.gt_cls + (int64_t)b * s.Gmax + key_gt(key)), s.C);
+}
+// any row (slow paths): byte code from whichever representation is present
+__device__ __forceinline__ int code_of_row(const CodeSrc& s, int b, int a) {
+    if (s.code8) return __ldg(s.code8 + (int64_t)b * s.Ap + a);
+    if (!((__ldg(s.mask + (int64_t)b * s.MW + (a >> 10)) >> ((a >> 5) & 31)) & 1u)) return kCodeNegative;
+    const unsigned key = __ldg(s.keys + (int64_t)b * s.Ap + a);
+    return key ? code_of_key(s, b, key) : kCodeNegative;
+}
+
 // =====================================================================================================================
 // tuning knobs (process-wide, set through g3d_set_tuning; read once per call)
 // =====================================================================================================================
-static std::atomic<int> g_fill_chain_permille{-1};   // share of dreg zero-filled by the fill CTAs of K0..K2 (-1: default)
-static std::atomic<int> g_fill_ctas{-1};             // fill CTAs per chain kernel (-1: one per SM)
-static std::atomic<int> g_force_anchor_centric{0};
+static std::atomic<int> g_force_anchor_centric{0};   // != 0: ignore pyramid_host (benchmark comparisons)
+static std::atomic<int> g_pdl{1};                     // 0: launch K4 without programmatic dependent launch
 
 // =====================================================================================================================
 // K0: prologue
@@ -70,15 +100,19 @@ struct PrologueArgs {
     int32_t* zero_ptr;     // counters to zero
     int zero_n;
     int B, Gmax, W, variant;
-    FillSlice fill_a, fill_b;
+    FillSlice fill;        // keys + chunk mask of the GT-centric assignment: zeroed by the first nfill CTAs
     int nfill;
 };
 
 __global__ void __launch_bounds__(kTile) loss_prologue_kernel(const PrologueArgs p) {
-    __shared__ __align__(128) unsigned char ztile[kZeroTile];
     __shared__ int wcount[kWarps];
     if ((int)blockIdx.x < p.nfill) {
-        fill_cta(p.fill_a, p.fill_b, blockIdx.x, p.nfill, ztile);
+        // keys + chunk mask: 50 MB that mostly stay in L2 - plain 16-byte stores from every thread (the per-SM bulk-copy
+        // path is the slower one for a fill that is not competing with anything)
+        float4* dst = reinterpret_cast<float4*>(p.fill.base);
+        const long long n16 = p.fill.bytes >> 4;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long i = (long long)blockIdx.x * kTile + threadIdx.x; i < n16; i += (long long)p.nfill * kTile) dst[i] = z;
         return;
     }
     const int b = blockIdx.x - p.nfill, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -472,21 +506,15 @@ struct PairArgs {
     const float4* gt_box;      // [B][Gmax] compacted valid rows
     const int32_t* gt_count;   // [B]
     uint32_t* keys;            // [B][Ap], zero on entry
-    int B, A, Ap, Gmax;
+    uint32_t* mask;            // [B][MW] chunk mask, zero on entry
+    int B, A, Ap, MW, Gmax;
     float win_q, cull_mul, neg_thr;
     unsigned neg_thr_bits;
-    FillSlice fill;
-    int nfill;
 };
 
 __global__ void __launch_bounds__(256) assign_pairs_kernel(const PairArgs p, const __grid_constant__ Pyramid pyr) {
-    __shared__ __align__(128) unsigned char ztile[kZeroTile];
-    if ((int)blockIdx.x < p.nfill) {
-        fill_cta(p.fill, FillSlice{nullptr, 0}, blockIdx.x, p.nfill, ztile);
-        return;
-    }
     const int lane = threadIdx.x & 31;
-    const int wid = (((int)blockIdx.x - p.nfill) * (int)blockDim.x + (int)threadIdx.x) >> 5;
+    const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (wid >= p.B * p.Gmax) return;
     const int b = wid / p.Gmax, g = wid - b * p.Gmax;
     if (g >= __ldg(p.gt_count + b)) return;
@@ -496,6 +524,7 @@ __global__ void __launch_bounds__(256) assign_pairs_kernel(const PairArgs p, con
     const float Ag = gw * gh;
     const float area_g = box_area_rn(gk.x, gk.y, gk.z, gk.w);
     uint32_t* keys = p.keys + (int64_t)b * p.Ap;
+    uint32_t* mask = p.mask + (int64_t)b * p.MW;
     // The window only has to be a superset: FP32 with approximate reciprocals (relative error ~1e-6) against a threshold
     // 3.75 % below the one that matters, plus 0.05 px of slack on the centre range.
     const float kq = p.win_q, eps = 0.05f;
@@ -561,80 +590,62 @@ __global__ void __launch_bounds__(256) assign_pairs_kernel(const PairArgs p, con
             if (!(v >= p.neg_thr)) continue;
             const unsigned key = ((__float_as_uint(v) - p.neg_thr_bits + 1u) << 8) | (unsigned)(255 - g);
             atomicMax(keys + a, key);      // result unused: a fire-and-forget RED, nothing waits on it
+            atomicOr(mask + (a >> 10), 1u << ((a >> 5) & 31));
         }
     }
 }
 
 struct ResolveArgs {
     const uint32_t* keys;      // [B][Ap]
+    const uint32_t* mask;      // [B][MW]
     const int32_t* gt_row;     // [B][Gmax] original annotation row of each compacted row
-    const int32_t* gt_cls;     // [B][Gmax]
-    uint8_t* code8;            // [B][Ap]
     int32_t* assign;           // [B][A] or null
     int32_t* pos_anchor;       // [B][A]
     int32_t* pos_gt;
     int32_t* npos;
-    int A, Ap, Gmax, C, tiles;
+    int B, A, Ap, MW, Gmax, tiles;
     float pos_thr;
     unsigned neg_thr_bits;
-    FillSlice fill;
-    int nfill;
 };
 
-constexpr int kResolveTile = 4096;   // anchors per CTA: 256 threads x 4 x 4
+constexpr int kResolveTile = 4096;   // anchors per CTA: 8 warps x 16 chunks of 32
 
-// one coalesced pass over the keys of image b = item / tiles: 16 keys per thread (four 16-byte loads; the per-image
-// pitch Ap is a multiple of 32, so every access is aligned); byte codes out (4 bytes per store); positives appended to
-// the image's list with ONE atomic per CTA (block-level scan)
+// Builds the per-image lists of positive anchors (and the optional int32 codes).  Item = (image, 4096-anchor tile); warp
+// w owns 16 consecutive 32-anchor chunks = 16 bits of one chunk-mask word and loads the keys of the touched chunks only
+// (one key per lane and chunk, all loads issued up front).  Positives are appended with ONE atomic per CTA (block scan).
+// Almost all CTAs see an empty mask and leave after the barrier.
 __global__ void __launch_bounds__(256) assign_resolve_kernel(const ResolveArgs p) {
-    __shared__ __align__(128) unsigned char ztile[kZeroTile];
     __shared__ int wsum[kWarps];
     __shared__ int s_base;
-    if ((int)blockIdx.x < p.nfill) {
-        fill_cta(p.fill, FillSlice{nullptr, 0}, blockIdx.x, p.nfill, ztile);
-        return;
-    }
-    const int item = (int)blockIdx.x - p.nfill;
+    const int item = (int)blockIdx.x;
     const int b = item / p.tiles, tile = item - b * p.tiles;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t* __restrict__ keys = p.keys + (int64_t)b * p.Ap;
-    uint4 kv[4];
-    int a0[4];
+    const int a_w = tile * kResolveTile + warp * 512;           // first anchor of this warp's 16 chunks
+    unsigned m16 = 0u;
+    if (a_w < p.Ap) m16 = (__ldg(p.mask + (int64_t)b * p.MW + (a_w >> 10)) >> ((a_w >> 5) & 31)) & 0xffffu;
+    // nothing in the whole tile (the usual case) and no dense codes wanted: done
+    if (!__syncthreads_or(m16 != 0u) && !p.assign) return;
+    unsigned key[16];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        a0[u] = tile * kResolveTile + (u * 256 + tid) * 4;
-        kv[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (a0[u] < p.Ap) kv[u] = __ldcs(reinterpret_cast<const uint4*>(keys + a0[u]));
-    }
+    for (int c = 0; c < 16; ++c) key[c] = 0u;
     int npos_mine = 0;
+    if (m16 != 0u) {               // warp-uniform: most warps hold nothing
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const unsigned kk[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
-        unsigned packed = 0u;
-        int code[4];
+        for (int c = 0; c < 16; ++c)
+            if ((m16 >> c) & 1u) key[c] = __ldcs(p.keys + (int64_t)b * p.Ap + a_w + 32 * c + lane);   // inside Ap: the bit was set
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            code[e] = G3D_ASSIGN_NEGATIVE;
-            int c8 = kCodeNegative;
-            if (kk[e] != 0u && a0[u] + e < p.A) {
-                const float v = __uint_as_float((kk[e] >> 8) - 1u + p.neg_thr_bits);
-                const int g = 255 - (int)(kk[e] & 255u);
-                if (v >= p.pos_thr) {
-                    code[e] = __ldg(p.gt_row + (int64_t)b * p.Gmax + g);
-                    c8 = code8_of_class(__ldg(p.gt_cls + (int64_t)b * p.Gmax + g), p.C);
-                    ++npos_mine;
-                } else {
-                    code[e] = G3D_ASSIGN_IGNORE;
-                    c8 = kCodeIgnore;
-                }
-            }
-            packed |= (unsigned)c8 << (8 * e);
-        }
-        if (a0[u] < p.Ap) *reinterpret_cast<uint32_t*>(p.code8 + (int64_t)b * p.Ap + a0[u]) = packed;
-        if (p.assign) {
+        for (int c = 0; c < 16; ++c)
+            if (((m16 >> c) & 1u) && key[c] != 0u && key_iou(key[c], p.neg_thr_bits) >= p.pos_thr) ++npos_mine;
+    }
+    if (p.assign) {                // dense int32 codes (tests, ops.assign-style consumers): every anchor gets one
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-                if (a0[u] + e < p.A) p.assign[(int64_t)b * p.A + a0[u] + e] = code[e];
+        for (int c = 0; c < 16; ++c) {
+            const int a = a_w + 32 * c + lane;
+            int code = G3D_ASSIGN_NEGATIVE;
+            if (key[c] != 0u)
+                code = key_iou(key[c], p.neg_thr_bits) >= p.pos_thr ? __ldg(p.gt_row + (int64_t)b * p.Gmax + key_gt(key[c]))
+                                                                    : G3D_ASSIGN_IGNORE;
+            if (a < p.A) p.assign[(int64_t)b * p.A + a] = code;
         }
     }
     // block-level exclusive scan of the positive counts, one atomic for the CTA
@@ -660,36 +671,63 @@ __global__ void __launch_bounds__(256) assign_resolve_kernel(const ResolveArgs p
     // second pass over the keys this thread still holds: append its positives
     int64_t slot = (int64_t)b * p.A + s_base + woff + incl - npos_mine;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const unsigned kk[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (kk[e] != 0u && a0[u] + e < p.A &&
-                __uint_as_float((kk[e] >> 8) - 1u + p.neg_thr_bits) >= p.pos_thr) {
-                p.pos_anchor[slot] = a0[u] + e;
-                p.pos_gt[slot] = 255 - (int)(kk[e] & 255u);
-                ++slot;
-            }
+    for (int c = 0; c < 16; ++c) {
+        const int a = a_w + 32 * c + lane;
+        if (key[c] != 0u && key_iou(key[c], p.neg_thr_bits) >= p.pos_thr) {
+            p.pos_anchor[slot] = a;
+            p.pos_gt[slot] = key_gt(key[c]);
+            ++slot;
         }
     }
 }
 
 // =====================================================================================================================
-// K3: the streaming classification pass (loss terms + gradient) - the dominant, HBM-bound kernel
+// K3: the streaming classification pass (loss terms + gradient, HBM-bound) + the positive anchors + the reductions
 // =====================================================================================================================
 constexpr int kChunksPerWarp = 8;                            // 32-row chunks handled by one warp
-constexpr int kRowsPerCta = kWarps * 32 * kChunksPerWarp;    // (image, anchor) rows per CTA
+constexpr int kRowsPerCta = kWarps * 32 * kChunksPerWarp;    // (image, anchor) rows per stream CTA
 
 struct StreamArgs {
     const float* cls;
-    const uint8_t* code8;      // [B][Ap]
+    CodeSrc src;
     const int32_t* npos;       // [B]
-    double* partials;          // [B][T]: classification partial sums, one per CTA
+    double* partials;          // [B][T]: classification partial sums, one per stream CTA
     float* dcls;               // [B][A][C]  (GRAD only)
+    float* dreg;               // [B][A][R]  (GRAD, GT-centric path only: zero-filled here; null otherwise)
     float g0;                  // upstream gradient of the classification loss that dcls is formed for
-    int B, A, Ap, C, T;
+    int B, A, C, R, T;
     LossHyper h;
-    FillSlice fill;            // the part of dreg this launch zero-fills (every CTA takes an equal share)
+};
+
+// Loss sums of the positives are accumulated in exact fixed point - two int64 limbs per sum, units 2^-20 and 2^-52 -
+// with integer atomics: integer addition is associative, so the result does not depend on the (non-deterministic)
+// order of the lists.  Range 2^43 per sum, absolute resolution 2^-52 per term.
+struct PosArgs {
+    const float* reg;
+    const float4* anchors;
+    const float* gt_tab;       // [B][Gmax][kTabW]
+    const int32_t* pos_anchor;
+    const int32_t* pos_gt;
+    const int32_t* npos;
+    const int32_t* gt_count;
+    long long* acc;            // [B][4]: reg_hi, reg_lo, vp_hi, vp_lo (forward)
+    int32_t* nonfinite;        // [B]: bit 0 / 1 set if a regression / direction term was NaN / Inf / out of range (forward)
+    float* dreg;               // gradient rows of the positives (null: losses only)
+    float g1, g2;              // (forward) upstream gradients of the regression / direction losses the rows are formed for
+    const float* grad_out;     // [3] device (backward)
+    const float* grad_scale;   // [3] device or null (backward): multiplies grad_out (dist.py: local -> global means)
+    float e1, e2;              // (backward) the values the forward assumed; have_rows: rows already written for them
+    int have_rows;
+    int B, A, R, Gmax;
+    LossHyper h;
+    // reduction (forward)
+    const double* partials;    // [B][T]
+    int32_t* counters;         // [B] image tickets + [1] batch ticket, zero on entry
+    float* losses;             // [4] : cls, reg, vp, number of non-empty images
+    float* per_image;          // [B][4]
+    int32_t* gt_count_out;     // [B] or null: copy of gt_count for the caller
+    double* shard_stats;       // [5] or null: sum cls_j, sum reg_j, sum vp_j (images with GT), B, #images with GT
+    int T;
 };
 
 // The fully general row (any class count, any gamma, probabilities beyond the series range): scalar, full logf.
@@ -726,166 +764,6 @@ __device__ __noinline__ FixOut positive_fix(float pe, float s_cls, const LossHyp
     o.ge = s_cls * focal_term_grad(pe, true, h);
     return o;
 }
-
-struct StreamSmem {
-    double dred[kWarps];
-    int arrive;
-};
-
-// C == 8, gamma == 2: lane l of a warp owns row l of a 32-row chunk - one 256-bit load, one byte code, one 256-bit
-// store per lane and chunk; the next chunk's loads are in flight while the current one is evaluated.
-template <bool GRAD>
-__global__ void __launch_bounds__(kTile, 4) focal_stream8_kernel(const __grid_constant__ StreamArgs p) {
-    __shared__ StreamSmem sm;
-    __shared__ __align__(128) unsigned char ztile[kZeroTile];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    const bool fill = GRAD && p.fill.bytes > 0;
-    if (tid == 0) sm.arrive = 0;
-    if (fill) zero_tile_init(ztile); else __syncthreads();
-    if (fill && tid == 0)
-        fill_part(p.fill, (long long)blockIdx.y * gridDim.x + blockIdx.x, (long long)gridDim.x * gridDim.y,
-                  (uint32_t)__cvta_generic_to_shared(ztile));
-    const float npos = (float)__ldg(p.npos + b);
-    const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
-    const float scale_neg = p.h.one_minus_alpha * s_cls;
-    const int wa0 = (blockIdx.x * kWarps + warp) * (32 * kChunksPerWarp);   // first anchor of this warp
-    const int nchunks = max(0, min(kChunksPerWarp, (p.A - wa0 + 31) >> 5));
-    float cls_acc = 0.0f;
-    if (nchunks > 0) {
-        int a = wa0 + lane;
-        const float* cp = p.cls + ((int64_t)b * p.A + a) * 8;
-        float* dp = p.dcls + ((int64_t)b * p.A + a) * 8;
-        const uint8_t* kp = p.code8 + (int64_t)b * p.Ap + a;
-        float cur[8], nxt[8];
-        int code = kCodeIgnore, ncode = kCodeIgnore;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) cur[c] = 0.0f;
-        if (a < p.A) { ld_row8(cp, cur); code = __ldg(kp); }
-#pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
-            const bool valid = a < p.A;
-            ncode = kCodeIgnore;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) nxt[e] = 0.0f;
-            if (c + 1 < nchunks && a + 32 < p.A) { ld_row8(cp + 32 * 8, nxt); ncode = __ldg(kp + 32); }
-            // every element as if its anchor were negative (the overwhelmingly common case); an ignored (or absent) row
-            // gets scale 0 and contributes nothing
-            float g[8], pmax;
-            const bool ign = code == kCodeIgnore;
-            float acc = focal_neg_row8<GRAD>(cur, p.h.pmin, p.h.pmax, ign ? 0.0f : scale_neg, g, pmax);
-            acc = ign ? 0.0f : p.h.one_minus_alpha * acc;
-            if (pmax >= 0.25f && valid) {
-                // a probability beyond the series range: the whole row again with the full logf (handles its code too)
-                acc = stream_row_general_ool<GRAD>(cp, dp, code, s_cls, p.h);
-            } else {
-                if (GRAD && valid) st_row8(dp, g);
-                if (code >= kCodePositive && code != 255) {
-                    const int e = code - kCodePositive;         // < 8 because C == 8
-                    const FixOut o = positive_fix(__ldg(cp + e), s_cls, p.h);
-                    acc += o.dacc;
-                    if (GRAD) dp[e] = o.ge;                      // after the row store of the same thread
-                }
-            }
-            cls_acc += acc;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
-            code = ncode;
-            a += 32; cp += 32 * 8; dp += 32 * 8; kp += 32;
-        }
-    }
-    const float cs = warp_sum_f(cls_acc);     // FP32 inside the warp (<= 2048 terms), FP64 from here on
-    if (fill && tid == 0) bulk_wait_read();
-    // ---- the last warp of the CTA to get here (shared-memory ticket, no block barrier: finished warps retire
-    // immediately) combines the 8 warp partials in warp order
-    int arrived = 0;
-    if (lane == 0) {
-        sm.dred[warp] = (double)cs;
-        __threadfence_block();
-        arrived = atomicAdd(&sm.arrive, 1);
-    }
-    arrived = __shfl_sync(0xffffffffu, arrived, 0);
-    if (arrived != kWarps - 1) return;
-    __threadfence_block();
-    if (lane == 0) {
-        const volatile double* dr = sm.dred;
-        double tc = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) tc += dr[w];
-        p.partials[(int64_t)b * p.T + blockIdx.x] = tc;
-    }
-}
-
-// any class count / any gamma: one thread per row, scalar accesses
-template <bool GRAD>
-__global__ void __launch_bounds__(kTile, 4) focal_stream_generic_kernel(const __grid_constant__ StreamArgs p) {
-    __shared__ StreamSmem sm;
-    __shared__ __align__(128) unsigned char ztile[kZeroTile];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    const bool fill = GRAD && p.fill.bytes > 0;
-    if (fill) zero_tile_init(ztile);
-    if (fill && tid == 0)
-        fill_part(p.fill, (long long)blockIdx.y * gridDim.x + blockIdx.x, (long long)gridDim.x * gridDim.y,
-                  (uint32_t)__cvta_generic_to_shared(ztile));
-    const float npos = (float)__ldg(p.npos + b);
-    const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
-    const int wa0 = (blockIdx.x * kWarps + warp) * (32 * kChunksPerWarp);
-    float cls_acc = 0.0f;
-#pragma unroll 1
-    for (int c = 0; c < kChunksPerWarp; ++c) {
-        const int a = wa0 + 32 * c + lane;
-        if (a < p.A) {
-            const int64_t row = (int64_t)b * p.A + a;
-            cls_acc += stream_row_general<GRAD>(p.cls + row * p.C, p.dcls + row * p.C, p.C,
-                                                __ldg(p.code8 + (int64_t)b * p.Ap + a), s_cls, p.h);
-        }
-    }
-    const float cs = warp_sum_f(cls_acc);
-    if (lane == 0) sm.dred[warp] = (double)cs;
-    if (fill && tid == 0) bulk_wait_read();
-    __syncthreads();
-    if (tid == 0) {
-        double tc = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) tc += sm.dred[w];
-        p.partials[(int64_t)b * p.T + blockIdx.x] = tc;
-    }
-}
-
-// =====================================================================================================================
-// K4: the positive anchors (dense: one thread per positive, from the lists K1 / K2 built) + the reductions
-// =====================================================================================================================
-// Loss sums of the positives are accumulated in exact fixed point - two int64 limbs per sum, units 2^-20 and 2^-52 -
-// with integer atomics: integer addition is associative, so the result does not depend on the (non-deterministic)
-// order of the lists.  Range 2^43 per sum, absolute resolution 2^-52 per term.
-struct PosArgs {
-    const float* reg;
-    const float4* anchors;
-    const float* gt_tab;       // [B][Gmax][kTabW]
-    const int32_t* pos_anchor;
-    const int32_t* pos_gt;
-    const int32_t* npos;
-    const int32_t* gt_count;
-    long long* acc;            // [B][4]: reg_hi, reg_lo, vp_hi, vp_lo (forward)
-    int32_t* nonfinite;        // [B]: set if a term was NaN / Inf / out of range (forward)
-    float* dreg;               // gradient rows of the positives (null: losses only)
-    float g1, g2;              // (forward) upstream gradients of the regression / direction losses the rows are formed for
-    const float* grad_out;     // [3] device (backward)
-    const float* grad_scale;   // [3] device or null (backward): multiplies grad_out (dist.py: local -> global means)
-    float e1, e2;              // (backward) the values the forward assumed; have_rows: rows already written for them
-    int have_rows;
-    int B, A, R, Gmax;
-    LossHyper h;
-    // reduction (forward)
-    const double* partials;    // [B][T]
-    int32_t* counters;         // [B] image tickets + [1] batch ticket, zero on entry
-    float* losses;             // [4] : cls, reg, vp, number of non-empty images
-    float* per_image;          // [B][4]
-    int32_t* gt_count_out;     // [B] or null: copy of gt_count for the caller
-    double* shard_stats;       // [5] or null: sum cls_j, sum reg_j, sum vp_j (images with GT), B, #images with GT
-    int T;
-};
 
 __device__ __forceinline__ void fixed_split(float t, long long& hi, long long& lo, bool& bad) {
     bad = !(fabsf(t) < 1.0e12f);            // NaN, Inf, or beyond the 2^43 range of the high limb
@@ -924,7 +802,9 @@ __device__ __forceinline__ void finalize_image(const PosArgs& p, int b) {
         const double lo_unit = 1.0 / 4503599627370496.0, hi_unit = 1.0 / 1048576.0;
         double tr = (double)__ldcg(acc + 0) * hi_unit + (double)__ldcg(acc + 1) * lo_unit;
         double tv = (double)__ldcg(acc + 2) * hi_unit + (double)__ldcg(acc + 3) * lo_unit;
-        if (__ldcg(p.nonfinite + b)) tr = tv = __longlong_as_double(0x7ff8000000000000LL);   // NaN
+        const int bad = __ldcg(p.nonfinite + b);         // bit 0: a regression term, bit 1: a direction term was NaN / Inf
+        if (bad & 1) tr = __longlong_as_double(0x7ff8000000000000LL);
+        if (bad & 2) tv = __longlong_as_double(0x7ff8000000000000LL);
         float4 o;
         o.x = (float)(tc / fmax(tn, 1.0));                      // losses.py:152 (and :70 for empty images)
         o.y = tn > 0.0 ? (float)(tr / (tn * per_pos)) : 0.0f;  // .mean() over P x 20 (:350) / P x 4
@@ -959,13 +839,17 @@ __device__ __forceinline__ void finalize_image(const PosArgs& p, int b) {
     }
 }
 
-// rows of the positives: loss terms (FWD) and / or gradient rows (s_reg, s_vp already include the normalisers)
+template <int VARIANT>
+__device__ __forceinline__ void positives_accumulate(const PosArgs& q, int b, float reg_sum, float vp_term);
+
+// rows of the positives straight from global memory: loss terms (FWD) and / or gradient rows (s_reg, s_vp already
+// include the normalisers)
 template <int VARIANT, bool FWD>
-__device__ __forceinline__ void positives_rows(const PosArgs& p, int b, int n, float s_reg, float s_vp, bool write_rows) {
+__device__ __forceinline__ void positives_rows(const PosArgs& p, int b, int n, float s_reg, float s_vp, bool write_rows,
+                                               int first, int stride) {
     constexpr int R = (VARIANT == G3D_VARIANT_3D) ? 12 : 4;
-    const int lane = threadIdx.x & 31;
     const int n_up = (n + 31) & ~31;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_up; i += gridDim.x * blockDim.x) {
+    for (int i = first; i < n_up; i += stride) {
         float reg_sum = 0.0f, vp_term = 0.0f;
         if (i < n) {
             const int a = __ldg(p.pos_anchor + (int64_t)b * p.A + i);
@@ -991,30 +875,40 @@ __device__ __forceinline__ void positives_rows(const PosArgs& p, int b, int n, f
                 for (int k = 0; k < R / 4; ++k) dp[k] = make_float4(dr[4 * k], dr[4 * k + 1], dr[4 * k + 2], dr[4 * k + 3]);
             }
         }
-        if (FWD) {
-            long long rh, rl, vh, vl;
-            bool bad_r, bad_v;
-            fixed_split(reg_sum, rh, rl, bad_r);
-            fixed_split(vp_term, vh, vl, bad_v);
-            rh = warp_sum_ll(rh); rl = warp_sum_ll(rl);
-            if (VARIANT == G3D_VARIANT_3D) { vh = warp_sum_ll(vh); vl = warp_sum_ll(vl); }
-            const bool any_bad = __any_sync(0xffffffffu, bad_r || bad_v);
-            if (lane == 0) {
-                unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.acc + 4 * b);
-                atomicAdd(acc + 0, (unsigned long long)rh);
-                atomicAdd(acc + 1, (unsigned long long)rl);
-                if (VARIANT == G3D_VARIANT_3D) {
-                    atomicAdd(acc + 2, (unsigned long long)vh);
-                    atomicAdd(acc + 3, (unsigned long long)vl);
-                }
-                if (any_bad) atomicOr(p.nonfinite + b, 1);
-            }
-        }
+        if (FWD) positives_accumulate<VARIANT>(p, b, reg_sum, vp_term);
     }
 }
 
-// forward: loss sums of the positives, their gradient rows for the expected upstream gradients (g1, g2), then the
-// reductions.  grid (x, B).
+// exact fixed-point accumulation of one warp's (reg_sum, vp_term) values
+template <int VARIANT>
+__device__ __forceinline__ void positives_accumulate(const PosArgs& q, int b, float reg_sum, float vp_term) {
+    long long rh, rl, vh, vl;
+    bool bad_r, bad_v;
+    fixed_split(reg_sum, rh, rl, bad_r);
+    fixed_split(vp_term, vh, vl, bad_v);
+    rh = warp_sum_ll(rh); rl = warp_sum_ll(rl);
+    if (VARIANT == G3D_VARIANT_3D) { vh = warp_sum_ll(vh); vl = warp_sum_ll(vl); }
+    const int any_bad = (__any_sync(0xffffffffu, bad_r) ? 1 : 0) | (__any_sync(0xffffffffu, bad_v) ? 2 : 0);
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long* acc = reinterpret_cast<unsigned long long*>(q.acc + 4 * b);
+        atomicAdd(acc + 0, (unsigned long long)rh);
+        atomicAdd(acc + 1, (unsigned long long)rl);
+        if (VARIANT == G3D_VARIANT_3D) {
+            atomicAdd(acc + 2, (unsigned long long)vh);
+            atomicAdd(acc + 3, (unsigned long long)vl);
+        }
+        if (any_bad) atomicOr(q.nonfinite + b, any_bad);
+    }
+}
+
+// Programmatic dependent launch (PDL): K4 is launched while K3 is still running - its CTAs move into the SM slots the
+// last wave of the sweep leaves free - and does everything that does not need K3's results (the rows of the positives:
+// dependent loads, ~1000 instructions of arithmetic, gradient rows, fixed-point sums) before it waits for K3 to finish.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// K4.  grid (x, B): loss sums of the positives, their gradient rows for the expected upstream gradients (g1, g2); then,
+// once K3 is complete, the reductions: the last CTA of an image reduces the image, the last image the batch.
 template <int VARIANT>
 __global__ void __launch_bounds__(128) positives_kernel(const __grid_constant__ PosArgs p) {
     __shared__ int s_last;
@@ -1027,14 +921,185 @@ __global__ void __launch_bounds__(128) positives_kernel(const __grid_constant__ 
         s_reg = p.g1 / ((float)p.B * per_pos * npos);
         if (VARIANT == G3D_VARIANT_3D) s_vp = p.g2 / ((float)count_nonempty(p.gt_count, p.B) * npos * 3.0f);
     }
-    positives_rows<VARIANT, true>(p, b, n, s_reg, s_vp, p.dreg != nullptr);
+    positives_rows<VARIANT, true>(p, b, n, s_reg, s_vp, p.dreg != nullptr, blockIdx.x * blockDim.x + threadIdx.x,
+                                  gridDim.x * blockDim.x);
+    __threadfence();          // every warp's fixed-point atomics are ordered before the CTA's ticket
+    pdl_wait_primary();       // from here on K3's partial sums are complete and visible
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = (atomicAdd(p.counters + b, 1) == (int)gridDim.x - 1);
-    }
+    if (threadIdx.x == 0) s_last = (atomicAdd(p.counters + b, 1) == (int)gridDim.x - 1);
     __syncthreads();
     if (s_last && threadIdx.x < 32) finalize_image<VARIANT>(p, b);
+}
+
+struct StreamSmem {
+    double dred[kWarps];
+    int arrive;
+};
+
+// zero rows of dreg in a chunk that holds keys: ordinary stores, lane by lane; the lanes of positive rows write nothing
+// (the positives CTAs own those rows)
+__device__ __forceinline__ void zero_row_unless_positive(float* dreg_row, int R, bool valid, int code) {
+    if (!valid || code >= kCodePositive) return;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* d4 = reinterpret_cast<float4*>(dreg_row);
+    if (R == 12) { st_stream(d4, z); st_stream(d4 + 1, z); st_stream(d4 + 2, z); }
+    else st_stream(d4, z);
+}
+
+// C == 8, gamma == 2.  grid (T, B): CTA x streams rows [x * kRowsPerCta, ...) of image b - lane l of a warp owns row l
+// of a 32-row chunk: one 256-bit load, one code, one 256-bit store per lane and chunk; the next chunk's loads are in
+// flight while the current one is evaluated; KEYS: the codes come from the GT-centric keys, read only for chunks whose
+// mask bit is set, and the warp zero-fills its 256 rows of dreg (bulk copies for chunks without keys); else from the byte
+// codes.
+template <bool GRAD, bool KEYS>
+__global__ void __launch_bounds__(kTile, 4) focal_stream8_kernel(const __grid_constant__ StreamArgs p) {
+    __shared__ StreamSmem sm;
+    __shared__ __align__(128) unsigned char ztile[kZeroTile];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int bx = (int)blockIdx.x;
+    const bool fill = GRAD && KEYS && p.dreg != nullptr;
+    pdl_launch_dependents();      // K4 (positives + reductions) may move in as soon as every CTA of this grid has started
+    if (tid == 0) sm.arrive = 0;
+    if (fill) zero_tile_init(ztile); else __syncthreads();
+    const uint32_t tile = (uint32_t)__cvta_generic_to_shared(ztile);
+    const float npos = (float)__ldg(p.npos + b);
+    const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
+    const float scale_neg = p.h.one_minus_alpha * s_cls;
+    const int wa0 = (bx * kWarps + warp) * (32 * kChunksPerWarp);   // first anchor of this warp (multiple of 256)
+    const int nchunks = max(0, min(kChunksPerWarp, (p.A - wa0 + 31) >> 5));
+    float cls_acc = 0.0f;
+    if (nchunks > 0) {
+        int a = wa0 + lane;
+        const float* cp = p.cls + ((int64_t)b * p.A + a) * 8;
+        float* dp = p.dcls + ((int64_t)b * p.A + a) * 8;
+        const int64_t kbase = (int64_t)b * p.src.Ap;
+        unsigned m8 = 0u;       // the 8 chunk-mask bits of this warp
+        if (KEYS) m8 = (__ldg(p.src.mask + (int64_t)b * p.src.MW + (wa0 >> 10)) >> ((wa0 >> 5) & 31)) & 0xffu;
+        char* dreg_w = nullptr;                 // this warp's rows of dreg
+        const int rb = p.R * 4;
+        if (fill) {
+            dreg_w = reinterpret_cast<char*>(p.dreg) + ((int64_t)b * p.A + wa0) * rb;
+            if (m8 == 0u && lane == 0) bulk_zero(dreg_w, (long long)min(32 * kChunksPerWarp, p.A - wa0) * rb, tile);
+        }
+        float cur[8], nxt[8];
+        unsigned raw = 0u, nraw = 0u;           // key (KEYS) or byte code of the row
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { cur[e] = 0.0f; nxt[e] = 0.0f; }
+        if (a < p.A) {
+            ld_row8(cp, cur);
+            if (KEYS) { if (m8 & 1u) raw = __ldg(p.src.keys + kbase + a); }
+            else raw = __ldg(p.src.code8 + kbase + a);
+        }
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+            const bool valid = a < p.A;
+            nraw = 0u;
+            if (c + 1 < nchunks && a + 32 < p.A) {
+                ld_row8(cp + 32 * 8, nxt);
+                if (KEYS) { if ((m8 >> (c + 1)) & 1u) nraw = __ldg(p.src.keys + kbase + a + 32); }
+                else nraw = __ldg(p.src.code8 + kbase + a + 32);
+            }
+            int code = kCodeNegative;
+            if (raw != 0u) code = KEYS ? code_of_key(p.src, b, raw) : (int)raw;
+            if (fill && m8 != 0u) {
+                if ((m8 >> c) & 1u) zero_row_unless_positive(reinterpret_cast<float*>(dreg_w + (int64_t)(32 * c + lane) * rb), p.R, valid, code);
+                else if (lane == 0) bulk_zero(dreg_w + (int64_t)(32 * c) * rb, (long long)min(32, p.A - (wa0 + 32 * c)) * rb, tile);
+            }
+            // every element as if its anchor were negative (the overwhelmingly common case); an ignored (or absent) row
+            // gets scale 0 and contributes nothing
+            float g[8], pmax;
+            const bool ign = code == kCodeIgnore || !valid;
+            float acc = focal_neg_row8<GRAD>(cur, p.h.pmin, p.h.pmax, ign ? 0.0f : scale_neg, g, pmax);
+            acc = ign ? 0.0f : p.h.one_minus_alpha * acc;
+            if (pmax >= 0.25f && valid) {
+                // a probability beyond the series range: the whole row again with the full logf (handles its code too)
+                acc = stream_row_general_ool<GRAD>(cp, dp, code, s_cls, p.h);
+            } else {
+                if (GRAD && valid) st_row8(dp, g);
+                if (code >= kCodePositive && code != 255) {
+                    const int e = code - kCodePositive;         // < 8 because C == 8
+                    const FixOut o = positive_fix(__ldg(cp + e), s_cls, p.h);
+                    acc += o.dacc;
+                    if (GRAD) dp[e] = o.ge;                      // after the row store of the same thread
+                }
+            }
+            cls_acc += acc;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cur[e] = nxt[e];
+            raw = nraw;
+            a += 32; cp += 32 * 8; dp += 32 * 8;
+        }
+    }
+    const float cs = warp_sum_f(cls_acc);     // FP32 inside the warp (<= 2048 terms), FP64 from here on
+    if (fill && lane == 0) bulk_wait_read();  // the zero tile must outlive the copies that read it
+    // ---- the last warp of the CTA to get here (shared-memory ticket, no block barrier: finished warps retire
+    // immediately) combines the 8 warp partials in warp order
+    int arrived = 0;
+    if (lane == 0) {
+        sm.dred[warp] = (double)cs;
+        __threadfence_block();
+        arrived = atomicAdd(&sm.arrive, 1);
+    }
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (arrived != kWarps - 1) return;
+    __threadfence_block();
+    if (lane == 0) {
+        const volatile double* dr = sm.dred;
+        double tc = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tc += dr[w];
+        __stcg(p.partials + (int64_t)b * p.T + bx, tc);
+    }
+}
+
+// any class count / any gamma: one thread per row, scalar accesses; same fill
+template <bool GRAD>
+__global__ void __launch_bounds__(kTile, 4) focal_stream_generic_kernel(const __grid_constant__ StreamArgs p) {
+    __shared__ StreamSmem sm;
+    __shared__ __align__(128) unsigned char ztile[kZeroTile];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int bx = (int)blockIdx.x;
+    pdl_launch_dependents();
+    const bool keys = p.src.code8 == nullptr;
+    const bool fill = GRAD && keys && p.dreg != nullptr;
+    if (fill) zero_tile_init(ztile);
+    const uint32_t tile = (uint32_t)__cvta_generic_to_shared(ztile);
+    const float npos = (float)__ldg(p.npos + b);
+    const float s_cls = GRAD ? p.g0 / ((float)p.B * fmaxf(npos, 1.0f)) : 0.0f;
+    const int wa0 = (bx * kWarps + warp) * (32 * kChunksPerWarp);
+    const int rb = p.R * 4;
+    unsigned m8 = 0u;
+    if (keys && wa0 < p.A) m8 = (__ldg(p.src.mask + (int64_t)b * p.src.MW + (wa0 >> 10)) >> ((wa0 >> 5) & 31)) & 0xffu;
+    char* dreg_w = fill ? reinterpret_cast<char*>(p.dreg) + ((int64_t)b * p.A + wa0) * rb : nullptr;
+    float cls_acc = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < kChunksPerWarp; ++c) {
+        const int a = wa0 + 32 * c + lane;
+        if (wa0 + 32 * c >= p.A) break;
+        const bool valid = a < p.A;
+        int code = kCodeNegative;
+        if (valid) code = code_of_row(p.src, b, a);
+        if (fill) {
+            if ((m8 >> c) & 1u) zero_row_unless_positive(reinterpret_cast<float*>(dreg_w + (int64_t)(32 * c + lane) * rb), p.R, valid, code);
+            else if (lane == 0) bulk_zero(dreg_w + (int64_t)(32 * c) * rb, (long long)min(32, p.A - (wa0 + 32 * c)) * rb, tile);
+        }
+        if (valid) {
+            const int64_t row = (int64_t)b * p.A + a;
+            cls_acc += stream_row_general<GRAD>(p.cls + row * p.C, p.dcls + row * p.C, p.C, code, s_cls, p.h);
+        }
+    }
+    const float cs = warp_sum_f(cls_acc);
+    if (lane == 0) sm.dred[warp] = (double)cs;
+    if (fill && lane == 0) bulk_wait_read();
+    __syncthreads();
+    if (tid == 0) {
+        double tc = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tc += sm.dred[w];
+        __stcg(p.partials + (int64_t)b * p.T + bx, tc);
+    }
 }
 
 // =====================================================================================================================
@@ -1045,56 +1110,62 @@ struct ClsGradArgs {
     const float* grad_out;   // [3] device
     const float* grad_scale; // [3] device or null
     const int32_t* npos;     // [B]
-    const uint8_t* code8;    // [B][Ap]
+    CodeSrc src;
     float* dcls;
     float* dreg;
     float e0;                // upstream classification gradient dcls was formed for (valid if have_dcls)
     int have_dcls;           // dcls already holds the gradient for e0 and dreg is already zero-filled
-    int B, A, Ap, C, R, T;
+    int B, A, C, R, T;
     LossHyper h;
 };
 
-// Persistent grid-stride kernel over (image, 256-row tile) items, one thread per row.  The usual training step
-// (dcls already right) exits at once: one wave of CTAs.
-__global__ void __launch_bounds__(256, 4) focal_cls_grad_kernel(const __grid_constant__ ClsGradArgs p) {
-    const float go0 = __ldg(p.grad_out + 0) * (p.grad_scale ? __ldg(p.grad_scale + 0) : 1.0f);
-    if (p.have_dcls && go0 == p.e0) return;
-    const int lane = threadIdx.x & 31;
-    const int64_t items = (int64_t)p.T * p.B;
-    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int b = (int)(item / p.T);
-        const int a = (int)(item - (int64_t)b * p.T) * 256 + threadIdx.x;
-        const bool valid = a < p.A;
-        const int64_t row = (int64_t)b * p.A + a;
-        if (!p.have_dcls) {
-            const int nrows = min(32, p.A - (a - lane));
-            if (nrows > 0) {
-                if (p.R == 12) zero_rows<12>(p.dreg + (row - lane) * 12, nrows, lane);
-                else           zero_rows<4>(p.dreg + (row - lane) * 4, nrows, lane);
-            }
-        }
-        if (!valid) continue;
-        const int code = __ldg(p.code8 + (int64_t)b * p.Ap + a);
-        const float npos = (float)__ldg(p.npos + b);
-        const float s_cls = go0 / ((float)p.B * fmaxf(npos, 1.0f));
-        stream_row_general<true>(p.cls + row * p.C, p.dcls + row * p.C, p.C, code, s_cls, p.h);
-    }
-}
-
-// gradient rows of the positives for the real upstream gradients; exits at once when the forward's rows already hold
+// Role 1 (the first n_cls CTAs): grid-stride over (image, 256-row tile) items, one thread per row: the classification
+// gradient for the real upstream gradient.  Role 2 (the other CTAs, kPosCtas per image): the gradient rows of the positives.
+// Both compare the real upstream gradients with the ones the forward assumed and leave at once when they agree - the usual
+// training step - so the whole backward is one launch that retires in one wave.
+constexpr int kPosCtas = 8;
 template <int VARIANT>
-__global__ void __launch_bounds__(128) positives_bwd_kernel(const __grid_constant__ PosArgs p) {
-    const float go1 = __ldg(p.grad_out + 1) * (p.grad_scale ? __ldg(p.grad_scale + 1) : 1.0f);
-    const float go2 = (VARIANT == G3D_VARIANT_3D) ? __ldg(p.grad_out + 2) * (p.grad_scale ? __ldg(p.grad_scale + 2) : 1.0f) : 0.0f;
-    if (p.have_rows && go1 == p.e1 && (VARIANT != G3D_VARIANT_3D || go2 == p.e2)) return;
-    const int b = blockIdx.y;
-    const int n = min(__ldg(p.npos + b), p.A);
+__global__ void __launch_bounds__(256, 4) focal_bwd_kernel(const __grid_constant__ ClsGradArgs p,
+                                                           const __grid_constant__ PosArgs q, int n_cls, int roles) {
+    if ((int)blockIdx.x < n_cls) {
+        if (!(roles & 1)) return;
+        const float go0 = __ldg(p.grad_out + 0) * (p.grad_scale ? __ldg(p.grad_scale + 0) : 1.0f);
+        if (p.have_dcls && go0 == p.e0) return;
+        const int lane = threadIdx.x & 31;
+        const int64_t items = (int64_t)p.T * p.B;
+        for (int64_t item = blockIdx.x; item < items; item += n_cls) {
+            const int b = (int)(item / p.T);
+            const int a = (int)(item - (int64_t)b * p.T) * 256 + threadIdx.x;
+            const bool valid = a < p.A;
+            const int64_t row = (int64_t)b * p.A + a;
+            if (!p.have_dcls) {
+                const int nrows = min(32, p.A - (a - lane));
+                if (nrows > 0) {
+                    if (p.R == 12) zero_rows<12>(p.dreg + (row - lane) * 12, nrows, lane);
+                    else           zero_rows<4>(p.dreg + (row - lane) * 4, nrows, lane);
+                }
+            }
+            if (!valid) continue;
+            const int code = code_of_row(p.src, b, a);
+            const float npos = (float)__ldg(p.npos + b);
+            const float s_cls = go0 / ((float)p.B * fmaxf(npos, 1.0f));
+            stream_row_general<true>(p.cls + row * p.C, p.dcls + row * p.C, p.C, code, s_cls, p.h);
+        }
+        return;
+    }
+    if (!(roles & 2)) return;
+    const float go1 = __ldg(q.grad_out + 1) * (q.grad_scale ? __ldg(q.grad_scale + 1) : 1.0f);
+    const float go2 = (VARIANT == G3D_VARIANT_3D) ? __ldg(q.grad_out + 2) * (q.grad_scale ? __ldg(q.grad_scale + 2) : 1.0f) : 0.0f;
+    if (q.have_rows && go1 == q.e1 && (VARIANT != G3D_VARIANT_3D || go2 == q.e2)) return;
+    const int idx = (int)blockIdx.x - n_cls;
+    const int b = idx / kPosCtas, x = idx - b * kPosCtas;
+    const int n = min(__ldg(q.npos + b), q.A);
     const float npos = (float)n;
     const float per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0f : 4.0f;
-    const float s_reg = go1 / ((float)p.B * per_pos * npos);
+    const float s_reg = go1 / ((float)q.B * per_pos * npos);
     float s_vp = 0.0f;
-    if (VARIANT == G3D_VARIANT_3D) s_vp = go2 / ((float)count_nonempty(p.gt_count, p.B) * npos * 3.0f);
-    positives_rows<VARIANT, false>(p, b, n, s_reg, s_vp, true);
+    if (VARIANT == G3D_VARIANT_3D) s_vp = go2 / ((float)count_nonempty(q.gt_count, q.B) * npos * 3.0f);
+    positives_rows<VARIANT, false>(q, b, n, s_reg, s_vp, true, x * 256 + threadIdx.x, kPosCtas * 256);
 }
 
 // =====================================================================================================================
@@ -1110,11 +1181,14 @@ struct FocalWorkspace {
     int32_t* pos_anchor; // [B][A]
     int32_t* pos_gt;     // [B][A]
     uint32_t* keys;      // [B][Ap]  GT-centric assignment: best (IoU, GT index) key per anchor
-    uint8_t* code8;      // [B][Ap]
+    uint32_t* mask;      // [B][MW]  GT-centric assignment: chunk mask (directly behind the keys: one fill covers both)
+    uint8_t* code8;      // [B][Ap]  anchor-centric assignment: byte codes
     int32_t* counters;   // zeroed per call: [B] image tickets, [1] batch ticket, [B] npos, [B] nonfinite flags, then
                          // (8-byte aligned) [B][4] int64 fixed-point sums
     int64_t n_counters;  // number of int32 words to zero
     int64_t Ap;          // per-image pitch of keys / code8 (multiple of 32)
+    int64_t MW;          // chunk-mask words per image
+    int64_t key_fill_bytes;   // keys + mask: zeroed together
     int64_t bytes;
 };
 
@@ -1132,7 +1206,10 @@ static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
     w.partials = (double*)(p + off); off += align_up(B * T * 8, 256);
     w.pos_anchor = (int32_t*)(p + off); off += align_up(B * A * 4, 256);
     w.pos_gt = (int32_t*)(p + off);  off += align_up(B * A * 4, 256);
-    w.keys = (uint32_t*)(p + off);   off += align_up(B * w.Ap * 4, 1024);
+    w.MW = ceil_div(w.Ap, 1024);
+    w.keys = (uint32_t*)(p + off);   off += align_up(B * w.Ap * 4, 256);
+    w.mask = (uint32_t*)(p + off);   off += align_up(B * w.MW * 4, 1024);
+    w.key_fill_bytes = (char*)w.mask - (char*)w.keys + align_up(B * w.MW * 4, 16);
     w.code8 = (uint8_t*)(p + off);   off += align_up(B * w.Ap, 256);
     w.counters = (int32_t*)(p + off);
     const int64_t head = align_up(3 * B + 1, 2);          // int32 words before the int64 sums
@@ -1142,6 +1219,14 @@ static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
     return w;
 }
 static inline int32_t* ws_npos(const FocalWorkspace& w, int64_t B) { return w.counters + B + 1; }
+static CodeSrc make_src(const FocalWorkspace& w, bool gt_centric, int64_t Gmax, int64_t C, const LossHyper& h) {
+    CodeSrc s;
+    s.code8 = gt_centric ? nullptr : w.code8;
+    s.keys = w.keys; s.mask = w.mask; s.gt_cls = w.gt_cls;
+    s.Ap = (int)w.Ap; s.MW = (int)w.MW; s.Gmax = (int)Gmax; s.C = (int)C;
+    s.pos_thr = h.pos_thr; s.neg_thr_bits = h.neg_thr_bits;
+    return s;
+}
 static inline int32_t* ws_nonfinite(const FocalWorkspace& w, int64_t B) { return w.counters + 2 * B + 1; }
 static inline long long* ws_acc(const FocalWorkspace& w, int64_t B) { return (long long*)(w.counters + align_up(3 * B + 1, 2)); }
 
@@ -1213,7 +1298,6 @@ static int check_focal_shapes(int64_t B, int64_t A, int64_t C, int64_t R, int64_
     return G3D_OK;
 }
 
-static dim3 positives_grid(int64_t B) { return dim3(64, (unsigned)B); }
 
 // pyramid_host (nullable): {L, S, then L x (rows, cols, stride), then L x S x (anchor width, anchor height)} as doubles -
 // the structure of Anchors.forward's table (anchors.py:21-40).  Accepted only if it accounts for exactly A anchors.
@@ -1237,14 +1321,18 @@ static bool load_pyramid(const double* h, int64_t A, Pyramid& pyr) {
     return first == A;
 }
 
+static bool use_gt_centric(const double* pyramid_host, int64_t A, int64_t C, int64_t Gmax, const LossHyper& h, Pyramid& pyr) {
+    return Gmax >= 1 && Gmax <= 256 && h.neg_thr >= 0.3f && C <= 250 && !g_force_anchor_centric.load() &&
+           load_pyramid(pyramid_host, A, pyr);
+}
+
 }  // namespace g3d
 
 using namespace g3d;
 
 extern "C" int g3d_set_tuning(int key, int64_t value) {
     switch (key) {
-        case G3D_TUNE_FILL_CHAIN_PERMILLE: g_fill_chain_permille.store((int)value); return G3D_OK;
-        case G3D_TUNE_FILL_CTAS: g_fill_ctas.store((int)value); return G3D_OK;
+        case G3D_TUNE_PDL: g_pdl.store((int)value); return G3D_OK;
         case G3D_TUNE_FORCE_ANCHOR_CENTRIC: g_force_anchor_centric.store((int)value); return G3D_OK;
         default: set_error("g3d_set_tuning: unknown key %d", key); return G3D_ERR_INVALID;
     }
@@ -1299,23 +1387,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     };
 
     Pyramid pyr;
-    const bool gt_centric = Gmax >= 1 && Gmax <= 256 && h.neg_thr >= 0.3f && C <= 250 && !g_force_anchor_centric.load() &&
-                            load_pyramid(pyramid_host, A, pyr);
-
-    // ---- how the zero-fill of dreg is spread over the launches (GT-centric path)
-    const long long dreg_bytes = grad ? (long long)B * A * R * 4 : 0;
-    int nfill = 0;
-    long long chain_bytes = 0;
-    if (gt_centric) {
-        nfill = g_fill_ctas.load() >= 0 ? g_fill_ctas.load() : sms;
-        int permille = g_fill_chain_permille.load();
-        if (permille < 0) permille = 250;
-        if (permille > 1000) permille = 1000;
-        chain_bytes = nfill > 0 ? ((dreg_bytes / 1000 * permille) & ~1023LL) : 0;
-    }
-    // K0 carries the key fill plus 20 % of the chain part, K1 50 %, K2 30 % (proportional to their durations)
-    const long long c0 = (chain_bytes / 5) & ~1023LL, c1 = (chain_bytes / 2) & ~1023LL, c2 = chain_bytes - c0 - c1;
-    char* dreg_c = (char*)dreg;
+    const bool gt_centric = use_gt_centric(pyramid_host, A, C, Gmax, h, pyr);
 
     G3D_CUDA(trace(0));
     // ---- K0
@@ -1323,12 +1395,11 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     pr.ann = ann; pr.gt_box = w.gt_box; pr.gt_row = w.gt_row; pr.gt_cls = w.gt_cls; pr.gt_tab = w.gt_tab;
     pr.gt_count = w.gt_count; pr.zero_ptr = w.counters; pr.zero_n = (int)w.n_counters;
     pr.B = (int)B; pr.Gmax = (int)Gmax; pr.W = (int)W; pr.variant = variant;
-    pr.fill_a = FillSlice{nullptr, 0}; pr.fill_b = FillSlice{nullptr, 0};
+    pr.fill = FillSlice{nullptr, 0};
     pr.nfill = 0;
     if (gt_centric) {
-        pr.nfill = nfill > 0 ? nfill : sms;          // the keys always need their zeros
-        pr.fill_a = FillSlice{(char*)w.keys, (long long)B * w.Ap * 4};
-        pr.fill_b = FillSlice{dreg_c, c0};
+        pr.nfill = sms * 8;      // fill CTAs zero the keys and the chunk mask
+        pr.fill = FillSlice{(char*)w.keys, (long long)w.key_fill_bytes};
     }
     loss_prologue_kernel<<<(unsigned)(B + pr.nfill), kTile, 0, st>>>(pr);
     G3D_LAUNCH_CHECK();
@@ -1338,21 +1409,19 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     if (gt_centric) {
         PairArgs pa;
         pa.anchors = (const float4*)anchors; pa.gt_box = w.gt_box; pa.gt_count = w.gt_count; pa.keys = w.keys;
-        pa.B = (int)B; pa.A = (int)A; pa.Ap = (int)w.Ap; pa.Gmax = (int)Gmax;
+        pa.mask = w.mask;
+        pa.B = (int)B; pa.A = (int)A; pa.Ap = (int)w.Ap; pa.MW = (int)w.MW; pa.Gmax = (int)Gmax;
         pa.win_q = h.win_q; pa.cull_mul = h.cull_mul; pa.neg_thr = h.neg_thr; pa.neg_thr_bits = h.neg_thr_bits;
-        pa.fill = FillSlice{dreg_c + c0, c1};
-        pa.nfill = c1 > 0 ? nfill : 0;
-        assign_pairs_kernel<<<(unsigned)(ceil_div(B * Gmax, 8) + pa.nfill), 256, 0, st>>>(pa, pyr);
+        assign_pairs_kernel<<<(unsigned)ceil_div(B * Gmax, 8), 256, 0, st>>>(pa, pyr);
         G3D_LAUNCH_CHECK();
         G3D_CUDA(trace(2));
         ResolveArgs ra;
-        ra.keys = w.keys; ra.gt_row = w.gt_row; ra.gt_cls = w.gt_cls; ra.code8 = w.code8; ra.assign = assign;
+        ra.keys = w.keys; ra.mask = w.mask; ra.gt_row = w.gt_row; ra.assign = assign;
         ra.pos_anchor = w.pos_anchor; ra.pos_gt = w.pos_gt; ra.npos = npos;
-        ra.A = (int)A; ra.Ap = (int)w.Ap; ra.Gmax = (int)Gmax; ra.C = (int)C; ra.tiles = (int)ceil_div(w.Ap, kResolveTile);
+        ra.B = (int)B; ra.A = (int)A; ra.Ap = (int)w.Ap; ra.MW = (int)w.MW; ra.Gmax = (int)Gmax;
+        ra.tiles = (int)ceil_div(w.Ap, kResolveTile);
         ra.pos_thr = h.pos_thr; ra.neg_thr_bits = h.neg_thr_bits;
-        ra.fill = FillSlice{dreg_c + c0 + c1, c2};
-        ra.nfill = c2 > 0 ? nfill : 0;
-        assign_resolve_kernel<<<(unsigned)((int64_t)ra.tiles * B + ra.nfill), 256, 0, st>>>(ra);
+        assign_resolve_kernel<<<(unsigned)((int64_t)ra.tiles * B), 256, 0, st>>>(ra);
         G3D_LAUNCH_CHECK();
         G3D_CUDA(trace(3));
     } else {
@@ -1369,25 +1438,14 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
         G3D_CUDA(trace(3));
     }
 
-    // ---- K3
+    // ---- K3: stream CTAs + positives CTAs + reductions
     StreamArgs p;
-    p.cls = cls; p.code8 = w.code8; p.npos = npos; p.partials = w.partials; p.dcls = dcls;
+    p.cls = cls; p.npos = npos; p.partials = w.partials; p.dcls = dcls;
+    p.dreg = (gt_centric && grad) ? dreg : nullptr;       // the anchor-centric kernel wrote the zeros already
+    p.src = make_src(w, gt_centric, Gmax, C, h);
     p.g0 = grad ? grad_expected_host[0] : 0.0f;
-    p.B = (int)B; p.A = (int)A; p.Ap = (int)w.Ap; p.C = (int)C; p.T = (int)ceil_div(A, kRowsPerCta);
+    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.T = (int)ceil_div(A, kRowsPerCta);
     p.h = h;
-    p.fill = (gt_centric && grad) ? FillSlice{dreg_c + chain_bytes, dreg_bytes - chain_bytes} : FillSlice{nullptr, 0};
-    const dim3 sgrid((unsigned)p.T, (unsigned)B);
-    if (C == 8 && h.gamma_is_two) {
-        if (grad) focal_stream8_kernel<true><<<sgrid, kTile, 0, st>>>(p);
-        else      focal_stream8_kernel<false><<<sgrid, kTile, 0, st>>>(p);
-    } else {
-        if (grad) focal_stream_generic_kernel<true><<<sgrid, kTile, 0, st>>>(p);
-        else      focal_stream_generic_kernel<false><<<sgrid, kTile, 0, st>>>(p);
-    }
-    G3D_LAUNCH_CHECK();
-    G3D_CUDA(trace(4));
-
-    // ---- K4
     PosArgs pp;
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.gt_tab = w.gt_tab; pp.pos_anchor = w.pos_anchor;
     pp.pos_gt = w.pos_gt; pp.npos = npos; pp.gt_count = w.gt_count; pp.acc = ws_acc(w, B); pp.nonfinite = ws_nonfinite(w, B);
@@ -1396,9 +1454,35 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.h = h;
     pp.partials = w.partials; pp.counters = w.counters; pp.losses = losses; pp.per_image = per_image;
     pp.gt_count_out = gt_count_out; pp.shard_stats = shard_stats; pp.T = p.T;
-    if (variant == G3D_VARIANT_3D) positives_kernel<G3D_VARIANT_3D><<<positives_grid(B), 128, 0, st>>>(pp);
-    else                           positives_kernel<G3D_VARIANT_2D><<<positives_grid(B), 128, 0, st>>>(pp);
+    const dim3 sgrid((unsigned)p.T, (unsigned)B);
+    if (C == 8 && h.gamma_is_two) {
+        if (gt_centric) {
+            if (grad) focal_stream8_kernel<true, true><<<sgrid, kTile, 0, st>>>(p);
+            else      focal_stream8_kernel<false, true><<<sgrid, kTile, 0, st>>>(p);
+        } else {
+            if (grad) focal_stream8_kernel<true, false><<<sgrid, kTile, 0, st>>>(p);
+            else      focal_stream8_kernel<false, false><<<sgrid, kTile, 0, st>>>(p);
+        }
+    } else {
+        if (grad) focal_stream_generic_kernel<true><<<sgrid, kTile, 0, st>>>(p);
+        else      focal_stream_generic_kernel<false><<<sgrid, kTile, 0, st>>>(p);
+    }
     G3D_LAUNCH_CHECK();
+    G3D_CUDA(trace(4));
+
+    // ---- K4: positives + reductions, as a programmatic dependent launch behind K3
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(64, (unsigned)B);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl.load() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (variant == G3D_VARIANT_3D) G3D_CUDA(cudaLaunchKernelEx(&cfg, positives_kernel<G3D_VARIANT_3D>, pp));
+    else                           G3D_CUDA(cudaLaunchKernelEx(&cfg, positives_kernel<G3D_VARIANT_2D>, pp));
     G3D_CUDA(trace(5));
     return G3D_OK;
 }
@@ -1417,7 +1501,8 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
                                   int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                                   const float* hyper_host, const float* grad_out, const float* grad_scale,
                                   int have_grads, const float* grad_expected_host, const void* workspace,
-                                  int64_t workspace_bytes, float* dcls, float* dreg, int device, void* stream) {
+                                  int64_t workspace_bytes, const double* pyramid_host, float* dcls, float* dreg,
+                                  int device, void* stream) {
     int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
     if (rc != G3D_OK) return rc;
     G3D_REQUIRE(cls && reg && anchors && grad_out && workspace && dcls && dreg, "null pointer");
@@ -1435,16 +1520,17 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     cudaStream_t st = (cudaStream_t)stream;
     int sms = 148;
     G3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    Pyramid pyr;
+    const bool gt_centric = use_gt_centric(pyramid_host, A, C, Gmax, h, pyr);    // the decision the forward took
     ClsGradArgs p;
-    p.cls = cls; p.grad_out = grad_out; p.grad_scale = grad_scale; p.npos = ws_npos(w, B); p.code8 = w.code8;
+    p.cls = cls; p.grad_out = grad_out; p.grad_scale = grad_scale; p.npos = ws_npos(w, B);
+    p.src = make_src(w, gt_centric, Gmax, C, h);
     p.dcls = dcls; p.dreg = dreg; p.e0 = have_grads ? grad_expected_host[0] : 0.0f; p.have_dcls = have_grads ? 1 : 0;
-    p.B = (int)B; p.A = (int)A; p.Ap = (int)w.Ap; p.C = (int)C; p.R = (int)R;
+    p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R;
     p.T = (int)ceil_div(A, 256);
     p.h = h;
     const int64_t items = (int64_t)p.T * B;
-    const int grid = (int)(items < (int64_t)sms * 8 ? items : (int64_t)sms * 8);
-    focal_cls_grad_kernel<<<grid, 256, 0, st>>>(p);
-    G3D_LAUNCH_CHECK();
+    const int n_cls = (int)(items < (int64_t)sms * 4 ? items : (int64_t)sms * 4);
     PosArgs pp;
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.gt_tab = w.gt_tab; pp.pos_anchor = w.pos_anchor;
     pp.pos_gt = w.pos_gt; pp.npos = ws_npos(w, B); pp.gt_count = w.gt_count; pp.acc = nullptr; pp.nonfinite = nullptr;
@@ -1454,8 +1540,19 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.h = h;
     pp.partials = nullptr; pp.counters = nullptr; pp.losses = nullptr; pp.per_image = nullptr; pp.gt_count_out = nullptr;
     pp.shard_stats = nullptr; pp.T = 0;
-    if (variant == G3D_VARIANT_3D) positives_bwd_kernel<G3D_VARIANT_3D><<<positives_grid(B), 128, 0, st>>>(pp);
-    else                           positives_bwd_kernel<G3D_VARIANT_2D><<<positives_grid(B), 128, 0, st>>>(pp);
+    const unsigned n_pos = (unsigned)(kPosCtas * B);
+    auto launch = [&](int roles) {
+        const unsigned grid = (roles == 1) ? (unsigned)n_cls : (unsigned)n_cls + n_pos;
+        if (variant == G3D_VARIANT_3D) focal_bwd_kernel<G3D_VARIANT_3D><<<grid, 256, 0, st>>>(p, pp, n_cls, roles);
+        else                           focal_bwd_kernel<G3D_VARIANT_2D><<<grid, 256, 0, st>>>(p, pp, n_cls, roles);
+    };
+    if (have_grads) {
+        launch(3);                 // both roles verify; usually one wave of early exits
+    } else {
+        launch(1);                 // zero-fill of dreg + dcls first ...
+        G3D_LAUNCH_CHECK();
+        launch(2);                 // ... then the rows of the positives
+    }
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

@@ -354,15 +354,4 @@ __device__ __forceinline__ void fill_part(const FillSlice& f, long long rank, lo
     const long long hi = lo + per < f.bytes ? lo + per : f.bytes;
     if (lo < hi) bulk_zero(f.base + lo, hi - lo, tile);
 }
-// a CTA whose only job is the fill (the leading `nfill` CTAs of the latency-bound kernels of the chain)
-__device__ __forceinline__ void fill_cta(const FillSlice& f0, const FillSlice& f1, int rank, int n, unsigned char* ztile) {
-    zero_tile_init(ztile);
-    if (threadIdx.x == 0) {
-        const uint32_t tile = (uint32_t)__cvta_generic_to_shared(ztile);
-        fill_part(f0, rank, n, tile);
-        fill_part(f1, rank, n, tile);
-        bulk_wait_read();
-    }
-}
-
 }  // namespace g3d

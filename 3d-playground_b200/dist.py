@@ -63,7 +63,7 @@ class _ShardedFocalLossFn(torch.autograd.Function):
                                      trace_events=trace_events, want_shard_stats=True, hyper=hyper)
         gathered = gather_shard_stats(fwd["shard_stats"], group)
         losses, scale = ops.combine_shard_stats(gathered, rank)
-        ctx.fwd, ctx.scale, ctx.n_backward = fwd, scale, 0
+        ctx.fwd, ctx.scale = fwd, scale
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
         ctx.save_for_backward(classifications, regressions)
         return losses
@@ -72,8 +72,7 @@ class _ShardedFocalLossFn(torch.autograd.Function):
     def backward(ctx, g):
         from . import ops
         _ = ctx.saved_tensors
-        ctx.n_backward += 1
-        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g.to(torch.float32), grad_scale=ctx.scale, fresh=ctx.n_backward > 1)
+        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g.to(torch.float32), grad_scale=ctx.scale, take=True)
         return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None, None
 
 

@@ -27,21 +27,20 @@ class _FocalLossFn(torch.autograd.Function):
                                      grad_expected=expected_grad if needs_grad else None,
                                      trace_events=trace_events, hyper=hyper)
         ctx.fwd = fwd
-        ctx.n_backward = 0
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
         # saved for autograd's bookkeeping: an in-place edit of an input between forward and backward is detected (version
         # counters), and a second backward without retain_graph raises autograd's own error
         ctx.save_for_backward(classifications, regressions)
-        ctx.mark_non_differentiable(fwd["per_image"], fwd["gt_count"])
-        return fwd["losses"][:3].clone(), fwd["losses"][3:4].clone(), fwd["per_image"], fwd["gt_count"]
+        n_nonempty = fwd["losses"][3:4].clone()
+        ctx.mark_non_differentiable(n_nonempty, fwd["per_image"], fwd["gt_count"])
+        return fwd["losses"][:3].clone(), n_nonempty, fwd["per_image"], fwd["gt_count"]
 
     @staticmethod
     def backward(ctx, g_losses, _g_ne, _g_pi, _g_gc):
         _ = ctx.saved_tensors
-        ctx.n_backward += 1
-        # first backward: the buffers the forward wrote (verified / completed on the device); later ones (retain_graph):
-        # fresh buffers, the tensors returned earlier stay untouched
-        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g_losses.to(torch.float32).contiguous(), fresh=ctx.n_backward > 1)
+        # first backward: the buffers the forward wrote (verified / completed on the device) leave ctx.fwd, so autograd can
+        # adopt them as .grad without a copy; later ones (retain_graph) compute into fresh buffers
+        dcls, dreg = ops.focal_loss_backward(ctx.fwd, g_losses.to(torch.float32).contiguous(), take=True)
         return dcls.to(ctx.in_dtypes[0]), dreg.to(ctx.in_dtypes[1]), None, None, None, None, None
 
 

@@ -236,7 +236,7 @@ def focal_loss_forward(classifications, regressions, anchors, annotations, want_
     gt_count = torch.empty((B,), dtype=torch.int32, device=dev)
     hy = hyper_array(hyper)
     out = dict(losses=losses, per_image=per_image, gt_count=gt_count, cls=cls, reg=reg, anchors=anc, ann=ann,
-               variant=variant, workspace=ws, gt_centric=pyr is not None, hyper=hy)
+               variant=variant, workspace=ws, gt_centric=pyr is not None, hyper=hy, pyramid=pyr)
     if want_assign:
         out["assign"] = code
     stats = torch.empty((5,), dtype=torch.float64, device=dev) if want_shard_stats else None
@@ -272,12 +272,13 @@ def combine_shard_stats(gathered, rank):
     return losses, scale
 
 
-def focal_loss_backward(fwd, grad_out, grad_scale=None, fresh=False):
+def focal_loss_backward(fwd, grad_out, grad_scale=None, take=False):
     """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R]).
 
     If the forward already wrote the gradients for `grad_expected`, the kernels compare grad_out (* grad_scale) with it on
-    the device: what agrees stays, what differs is recomputed (no host synchronisation either way).  fresh=True computes
-    into new buffers instead (a second backward through the same forward: the first one's tensors stay untouched)."""
+    the device: what agrees stays, what differs is recomputed (no host synchronisation either way).  take=True hands the
+    forward's buffers over to the caller (they leave `fwd`: autograd can then adopt them as .grad without a copy, and a
+    second backward through the same forward computes into fresh buffers)."""
     cls, reg, anc, ann = fwd["cls"], fwd["reg"], fwd["anchors"], fwd["ann"]
     dev = cls.device
     B, A, C = cls.shape
@@ -287,13 +288,16 @@ def focal_loss_backward(fwd, grad_out, grad_scale=None, fresh=False):
     if g.numel() != 3:
         raise ValueError("grad_out must have 3 elements (cls, reg, vp)")
     gs = _prep(grad_scale, torch.float32) if grad_scale is not None else None
-    if fwd.get("dcls") is not None and not fresh:
+    if fwd.get("dcls") is not None:
         dcls, dreg, have, ge = fwd["dcls"], fwd["dreg"], 1, fwd["grad_expected"]
+        if take:
+            del fwd["dcls"], fwd["dreg"]
     else:
         dcls, dreg, have, ge = torch.empty_like(cls), torch.empty_like(reg), 0, None
-    ws = fwd["workspace"]
+    ws, pyr = fwd["workspace"], fwd.get("pyramid")
+    pyr_p = pyr.ctypes.data_as(ctypes.c_void_p) if pyr is not None else ctypes.c_void_p(0)
     check(_lib.lib().g3d_focal_loss_bwd(_p(cls), _p(reg), _p(anc), _p(ann), B, A, C, R, G, W, fwd["variant"], fwd.get("hyper"),
-                                        _p(g), _p(gs), have, ge, _p(ws), ws.numel(), _p(dcls), _p(dreg), _idx(dev),
+                                        _p(g), _p(gs), have, ge, _p(ws), ws.numel(), pyr_p, _p(dcls), _p(dreg), _idx(dev),
                                         _stream(dev)), "g3d_focal_loss_bwd")
     return dcls, dreg
 

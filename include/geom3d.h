@@ -130,8 +130,8 @@ int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anch
 /* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
  * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory); grad_scale[3] (nullable, device)
  * multiplies them element-wise (multi-GPU: local -> global mean, from g3d_combine_shard_stats).
- * workspace = what the forward wrote (byte codes, per-image lists of positive anchors, GT tables: keep it untouched
- * between the two calls).  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is zero on non-positive anchors).
+ * workspace = what the forward wrote (keys / byte codes, per-image lists of positive anchors, GT tables: keep it
+ * untouched between the two calls); hyper_host / pyramid_host: the values the forward was given.  On return dcls[B,A,C] and dreg[B,A,R] are complete (dreg is zero on non-positive anchors).
  * have_grads = 0: dcls / dreg are uninitialised; everything is computed here.
  * have_grads = 1: they come from g3d_focal_loss_fwd_bwd(grad_expected_host).  The kernels compare grad_out * grad_scale
  *   with grad_expected_host ON THE DEVICE: equal (the usual training step) -> both launches exit in one wave; a different
@@ -142,14 +142,12 @@ int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
                        const float* hyper_host, const float* grad_out, const float* grad_scale, int have_grads,
                        const float* grad_expected_host, const void* workspace, int64_t workspace_bytes,
-                       float* dcls, float* dreg, int device, void* stream);
+                       const double* pyramid_host, float* dcls, float* dreg, int device, void* stream);
 
 /* process-wide tuning knobs of the loss path (benchmark sweeps; the defaults are the measured optimum on B200):
- * G3D_TUNE_FILL_CHAIN_PERMILLE: share (0..1000) of dreg zero-filled next to the prologue / assignment / resolve launches
- *   (the rest next to the streaming pass); G3D_TUNE_FILL_CTAS: fill CTAs per launch (-1 = one per SM);
+ * G3D_TUNE_PDL: 0 launches the positives / reduction kernel without programmatic dependent launch (default 1);
  * G3D_TUNE_FORCE_ANCHOR_CENTRIC != 0: ignore pyramid_host. */
-#define G3D_TUNE_FILL_CHAIN_PERMILLE 1
-#define G3D_TUNE_FILL_CTAS 2
+#define G3D_TUNE_PDL 1
 #define G3D_TUNE_FORCE_ANCHOR_CENTRIC 3
 int g3d_set_tuning(int key, int64_t value);
 

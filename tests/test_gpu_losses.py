@@ -191,7 +191,7 @@ def test_all_empty_batch_raises_and_optional_nan():
     cls, reg = synth.head_outputs(2, anc.shape[1], 8, 12, synth.gen(3))
     ann = -torch.ones(2, 4, 27)
     with pytest.raises(RuntimeError):
-        li.FocalLoss()(cls.cuda(), reg.cuda(), anc, ann.cuda())
+        li.FocalLoss(check_empty=True)(cls.cuda(), reg.cuda(), anc, ann.cuda())   # the reference's immediate error
     out = li.FocalLoss(check_empty=False)(cls.cuda(), reg.cuda(), anc, ann.cuda())
     assert torch.isnan(out[2]).all() and float(out[1]) == 0.0
     # the classification loss of empty images is the un-normalised negative-only sum (losses.py:58-70)
@@ -401,31 +401,33 @@ def test_gt_centric_assignment_equals_anchor_centric_and_oracle(seed):
     assert_close_rel(r1.grad.cpu(), r0.grad, 3 * TOL, "dreg", row_scale=True)
 
 
-@pytest.mark.parametrize("permille,ctas", [(0, -1), (1000, -1), (500, 3), (250, 0)])
-def test_dreg_fill_split_is_invisible(permille, ctas):
-    """wherever the bulk-copy zero fill of dreg is placed (all next to the assignment launches, all next to the streaming
-    pass, a few fill CTAs, none), every non-positive row of dreg is exactly zero and the positive rows are unchanged"""
+@pytest.mark.parametrize("shape", [(200, 328, 3, 17), (96, 96, 2, 60), (64, 64, 1, 250)])
+def test_dreg_fill_and_overlapped_positives_are_invisible(shape):
+    """GT-centric path: dreg is zero-filled by the streaming launch - bulk copies for chunks without keys, lane stores for
+    chunks with keys except the positive rows - while the positives launch, started behind it as a programmatic dependent
+    launch, writes the positive rows concurrently.  Whatever the buffer held before, with and without PDL, the result
+    equals the anchor-centric path's (plain stores, separate launches) bit for bit."""
     ops, _ = _mods()
     g = synth.gen(7300)
-    H, W = 200, 328
+    H, W, B, G = shape
     anc = _tagged_anchors(H, W)
     A = anc.shape[1]
-    ann = synth.gt_annotations_3d(3, 17, H, W, g, n_pad=1, **synth.TINY).cuda()
-    cls, reg = synth.head_outputs(3, A, 8, 12, g)
+    ann = synth.gt_annotations_3d(B, G, H, W, g, n_pad=1, **synth.TINY).cuda()
+    cls, reg = synth.head_outputs(B, A, 8, 12, g)
     cls, reg = cls.cuda(), reg.cuda()
-    want = ops.focal_loss_forward(cls, reg, anc.clone(), ann, grad_expected=1.0)      # anchor-centric: plain stores
+    want = ops.focal_loss_forward(cls, reg, anc.clone(), ann, grad_expected=1.0)      # anchor-centric
+    assert not want["gt_centric"]
     try:
-        ops.set_tuning("fill_chain_permille", permille)
-        ops.set_tuning("fill_ctas", ctas)
-        for _ in range(2):
+        for pdl in (1, 0, 1):
+            ops.set_tuning("pdl", pdl)
             poison = torch.full_like(reg, float("nan"))
             del poison                                            # the caching allocator hands the block to dreg next
             got = ops.focal_loss_forward(cls, reg, anc, ann, grad_expected=1.0)
             assert got["gt_centric"]
             assert torch.equal(got["dreg"], want["dreg"]) and torch.equal(got["dcls"], want["dcls"])
+            assert torch.equal(got["losses"], want["losses"]) and torch.equal(got["per_image"], want["per_image"])
     finally:
-        ops.set_tuning("fill_chain_permille", -1)
-        ops.set_tuning("fill_ctas", -1)
+        ops.set_tuning("pdl", 1)
 
 
 def test_gt_centric_assignment_falls_back(monkeypatch):
