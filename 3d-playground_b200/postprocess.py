@@ -226,6 +226,21 @@ def detect_multi_frame(classification, boxes, box_col=16, ladder_start=LADDER_ST
     return scores[keep], classes[keep], anchor_boxes[keep], im_indexes[keep]
 
 
+def _flatten_batch(classification, regression, anchors):
+    """The reference's default branch squeezes the batch dimension (`torch.squeeze(classification[:, :, i])`, 3D
+    model.py:366,381; 2D retinanet/model.py:288,295): for B == 1 that is one image, for B > 1 the boolean mask is [B,A] and
+    the masked scores / boxes of ALL images are concatenated (image-major) before the ladder and the per-class NMS - the
+    batch behaves like one image with B*A anchors.  Reproduced literally: the same tensors, flattened."""
+    B, A, C = classification.shape
+    if B == 1:
+        return classification, regression, anchors
+    anc = anchors.reshape(-1, A, anchors.shape[-1])
+    if anc.shape[0] == 1:
+        anc = anc.expand(B, A, anc.shape[-1])
+    return (classification.reshape(1, B * A, C), regression.reshape(1, B * A, regression.shape[-1]),
+            anc.reshape(1, B * A, anc.shape[-1]).contiguous())
+
+
 class PostProcess3D(nn.Module):
     """Everything ResNet.forward does after the heads in the 3D directional model (model.py:306-397):
     forward(classification[B,A,8], regression[B,A,12], anchors[1,A,4], LOCALIZE=False, MULTI_FRAME=False)."""
@@ -239,9 +254,11 @@ class PostProcess3D(nn.Module):
             return detect_multi_frame(classification, self.regressBoxes(anchors, regression))
         if LOCALIZE:
             return self.regressBoxes(anchors, regression), classification
-        # default branch: filter first, decode only what survives (no [B,A,20] tensor)
-        scores, classes, boxes, _ = detect_per_class_fused(classification[:1], regression[:1], anchors,
-                                                           ladder_start=LADDER_START_SINGLE)
+        # default branch: filter first, decode only what survives (no [B,A,20] tensor).  A batch is processed the way the
+        # reference processes it - as one flattened image (see _flatten_batch); for per-image detections of a batch use
+        # detect_per_class_fused, which also returns the image index.
+        cls1, reg1, anc1 = _flatten_batch(classification, regression, anchors)
+        scores, classes, boxes, _ = detect_per_class_fused(cls1, reg1, anc1, ladder_start=LADDER_START_SINGLE)
         return [scores, classes, boxes]
 
 
@@ -258,8 +275,7 @@ class PostProcess2D(nn.Module):
         if LOCALIZE:
             return self.regressBoxes(anchors, regression, clip_wh=(width, height)), classification  # decode + clip fused
         mean, std = self.regressBoxes._host_params()
-        anc = anchors if anchors.shape[0] == 1 else anchors[:1]
-        scores, classes, boxes, _ = detect_per_class_fused(classification[:1], regression[:1], anc,
-                                                           score_threshold=SCORE_THRESHOLD_2D, mean=mean, std=std,
-                                                           clip_wh=(width, height))
+        cls1, reg1, anc1 = _flatten_batch(classification, regression, anchors)      # see PostProcess3D
+        scores, classes, boxes, _ = detect_per_class_fused(cls1, reg1, anc1, score_threshold=SCORE_THRESHOLD_2D, mean=mean,
+                                                           std=std, clip_wh=(width, height))
         return [scores, classes, boxes]

@@ -66,11 +66,13 @@ def ladder_threshold(scores, start, keep=10000):
 
 
 def detect_3d(classification, transformed, iou=0.5, start=1e-25):
-    """default branch for one image: classification[1,A,C], transformed[1,A,20] -> [scores, classes, boxes]."""
+    """default branch: classification[B,A,C], transformed[B,A,20] -> [scores, classes, boxes].  `torch.squeeze` of the
+    reference (3D model.py:366,381) leaves [B,A] tensors for B > 1, and the boolean mask then concatenates the images:
+    the batch is one flattened image."""
     S, Cl, Bx = [], [], []
-    boxes = transformed[0]
+    boxes = transformed.reshape(-1, transformed.shape[-1])
     for c in range(classification.shape[2]):
-        sc = classification[0, :, c]
+        sc = classification[:, :, c].reshape(-1)
         mask, _ = ladder_threshold(sc, start)
         if mask.sum() == 0:
             continue
@@ -83,10 +85,11 @@ def detect_3d(classification, transformed, iou=0.5, start=1e-25):
 
 
 def detect_2d(classification, transformed, thr=0.05, iou=0.5):
+    """2D retinanet/model.py:287-309; a batch is flattened exactly as in detect_3d (:288,295)"""
     S, Cl, Bx = [], [], []
-    boxes = transformed[0]
+    boxes = transformed.reshape(-1, transformed.shape[-1])
     for c in range(classification.shape[2]):
-        sc = classification[0, :, c]
+        sc = classification[:, :, c].reshape(-1)
         mask = sc > thr
         if mask.sum() == 0:
             continue

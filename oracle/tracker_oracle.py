@@ -100,3 +100,27 @@ def estimate_ts_bias(boxes, camera_idxs, objs, timestamps, ts_bias, mu_v, phi, a
         if c1 != 0:
             ts_bias[c1] = float((1 - alpha) * ts_bias[c1] + alpha * (-te + ts_bias[c2]))
     return ts_bias
+
+
+def select_best_box(a_priori, preds, confs, classes, n_objs, W):
+    """MC3D_crop_tracker.py:974-1028: per object the detection maximising (1 - W) * IoU(footprint(pred), footprint(prior))
+    + W * conf (float64 IoU of the float32 footprints, first index on ties).  preds[n*d,6] or [n,d,6]."""
+    preds = preds.reshape(n_objs, -1, preds.shape[-1])
+    d = preds.shape[1]
+    fp_pred = footprint(preds.reshape(-1, preds.shape[-1])).reshape(n_objs, d, 4)
+    fp_prior = footprint(a_priori).unsqueeze(1).repeat(1, d, 1)
+    scores = (1 - W) * md_iou(fp_pred.double(), fp_prior.double()) + W * confs
+    keep = torch.argmax(scores, dim=1)
+    idx = torch.arange(n_objs)
+    return preds[idx, keep, :], classes[idx, keep], confs[idx, keep]
+
+
+def pairwise_iou_eps(a, b, eps=1e-6):
+    """mot_evaluator.py:87-118 for every (i, j): intersection / (area_a + area_b - intersection + eps), float64"""
+    a, b = a.double(), b.double()
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    iw = (torch.min(a[:, None, 2], b[None, :, 2]) - torch.max(a[:, None, 0], b[None, :, 0])).clamp(min=0)
+    ih = (torch.min(a[:, None, 3], b[None, :, 3]) - torch.max(a[:, None, 1], b[None, :, 1])).clamp(min=0)
+    inter = iw * ih
+    return inter / (area_a[:, None] + area_b[None, :] - inter + eps)

@@ -323,6 +323,51 @@ def golden_tracker():
          im_nms_groups=T.im_nms(me, corners, scores, threshold=0.3, groups=torch.zeros(120)))
 
 
+def best_box_inputs(seed=91, n=37, d=9):
+    """seeded select_best_box scenario shared with the tests: n tracked objects (a priori states), d candidate detections
+    per object (jittered copies, some far away), confidences and classes"""
+    g = synth.gen(seed)
+    prior, _ = synth.vehicle_states(n, g, n_cams=1)
+    preds = prior.unsqueeze(1).repeat(1, d, 1)
+    preds[:, :, :2] += torch.randn(n, d, 2, generator=g) * torch.tensor([6.0, 1.5])
+    preds[:, :, 2:5] *= 1.0 + 0.1 * torch.randn(n, d, 3, generator=g)
+    preds[:, d - 1, 0] += 500.0                                   # one detection per object without any overlap
+    confs = torch.rand(n, d, generator=g)
+    classes = torch.randint(0, 8, (n, d), generator=g)
+    return prior, preds, confs, classes
+
+
+def golden_best_box():
+    """MC_Crop_Tracker.select_best_box (MC3D_crop_tracker.py:974-1028) and MOT_Evaluator.iou (mot_evaluator.py:87-118, the
+    scalar IoU with 1e-6 added to the union) called unbound on seeded inputs."""
+    sys.path.insert(0, REF)
+    import homography as ref_h
+    import MC3D_crop_tracker as mc
+    import mot_evaluator as ev
+    sys.path.pop(0)
+    T = mc.MC_Crop_Tracker
+    prior, preds, confs, classes = best_box_inputs()
+    n, d = confs.shape
+    out = {}
+    for W in (0.4, 0.0, 1.0):
+        me = types.SimpleNamespace(hg=ref_h.Homography(), W=W)
+        me.md_iou = lambda a, b: T.md_iou(me, a, b)
+        best, cls, cf = T.select_best_box(me, prior.clone(), preds.clone().reshape(-1, 6), confs.clone(), classes.clone(), n)
+        tag = str(W).replace(".", "_")
+        out[f"best_{tag}"], out[f"cls_{tag}"], out[f"conf_{tag}"] = best, cls, cf
+    # the evaluator's scalar IoU on every (i, j) of two small box sets (float64 python arithmetic on tensor elements)
+    g = synth.gen(92)
+    a = torch.rand(23, 4, generator=g, dtype=torch.float64) * 50
+    a[:, 2:] += a[:, :2] + 1.0
+    b = a[torch.randperm(23, generator=g)][:17] + torch.randn(17, 4, generator=g, dtype=torch.float64) * 3
+    E = ev.MOT_Evaluator
+    eps_iou = torch.zeros(23, 17, dtype=torch.float64)
+    for i in range(23):
+        for j in range(17):
+            eps_iou[i, j] = E.iou(None, a[i], b[j])
+    save("best_box", prior=prior, preds=preds, confs=confs, classes=classes, eval_a=a, eval_b=b, eval_iou=eps_iou, **out)
+
+
 def ts_bias_inputs(seed=81, n_obj=45, n_cams=4):
     """seeded estimate_ts_bias scenario shared with the tests: objects seen by 1-3 cameras (jittered duplicates), a
     filter view with both directions, per-camera timestamps"""
@@ -451,6 +496,10 @@ if __name__ == "__main__":
         _shim()
         golden_anchors()
         sys.exit(0)
+    if "--only-best-box" in sys.argv:
+        _shim()
+        golden_best_box()
+        sys.exit(0)
     if "--only-ts-bias" in sys.argv:
         _shim()
         golden_ts_bias()
@@ -469,3 +518,4 @@ if __name__ == "__main__":
     golden_kf()
     golden_anchors()
     golden_ts_bias()
+    golden_best_box()

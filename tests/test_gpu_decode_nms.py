@@ -259,3 +259,83 @@ def test_fused_detection_tail_equals_decode_then_detect(three_d):
             assert w_.dtype == g_.dtype and torch.equal(w_, g_)
     none = pp.detect_per_class_fused(cls[2:3], reg[2:3], anc, score_threshold=0.05, **extra)
     assert none[0].numel() == 0 and none[2].shape == (0, 20 if three_d else 4)
+
+
+@pytest.mark.parametrize("three_d", [True, False])
+def test_postprocess_batch_is_flattened_like_the_reference(three_d):
+    """B > 1 through the drop-in modules: the reference squeezes the batch dimension and boolean-masks [B,A] tensors, so a
+    batch behaves like one image with B*A anchors (3D model.py:365-395, 2D retinanet/model.py:287-309) - every image's
+    detections are returned, none is dropped"""
+    _, pp = _mods()
+    from oracle import decode_oracle, nms_oracle
+    g = synth.gen(77)
+    H, W, B = 96, 128, 3
+    anc = synth.anchors(H, W)
+    A = anc.shape[1]
+    cls = synth.detection_scores(B, A, 8, g, objects=8, per_object=9)
+    if three_d:
+        reg = torch.randn(B, A, 12, generator=g) * 0.1
+        reg[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5]) + torch.randn(B, A, 4, generator=g) * 0.05
+        want = nms_oracle.detect_3d(cls, decode_oracle.decode3d(anc, reg))
+        got = pp.PostProcess3D()(cls.cuda(), reg.cuda(), anc.cuda())
+    else:
+        reg = torch.randn(B, A, 4, generator=g) * 0.5
+        boxes = decode_oracle.clip(decode_oracle.decode2d(anc, reg), H, W)
+        want = nms_oracle.detect_2d(cls, boxes)
+        got = pp.PostProcess2D()(cls.cuda(), reg.cuda(), anc.cuda(), torch.zeros(B, 3, H, W))
+    assert want[0].numel() > 0
+    one = (pp.PostProcess3D()(cls[:1].cuda(), reg[:1].cuda(), anc.cuda()) if three_d else
+           pp.PostProcess2D()(cls[:1].cuda(), reg[:1].cuda(), anc.cuda(), torch.zeros(1, 3, H, W)))
+    assert got[0].numel() > one[0].numel(), "the images after the first must not be dropped"
+    assert torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1])
+    if three_d:
+        assert torch.equal(got[2].cpu(), want[2])
+    else:
+        assert_close_rel(got[2].cpu(), want[2], 1e-6, "2D boxes")
+
+
+@pytest.mark.parametrize("three_d", [True, False])
+def test_cfg3_one_image_1080p_vs_oracle(three_d):
+    """BASELINE.json configs[2] at its full per-image size - 1080p, A = 389 205, ~5 000 boxes above 0.05, NMS 0.5 - for
+    one image (bench.py's image 0): the fused tail (filter -> decode the candidates -> per-class NMS -> assemble) against
+    the oracle's decode + torchvision-semantics NMS: identical scores / classes, boxes bit-exact (3D) or 1e-6 (2D expf)"""
+    _, pp = _mods()
+    from oracle import decode_oracle, nms_oracle
+    g = synth.gen(7)
+    H, W = 1080, 1920
+    anc = synth.anchors(H, W)
+    A = anc.shape[1]
+    assert A == 389205
+    cls = synth.detection_scores(1, A, 8, g)                       # 200 objects x 25 anchors scoring U(0.05, 1)
+    n_cand = int((cls > 0.05).sum())
+    assert 4000 < n_cand < 6000
+    if three_d:
+        reg = torch.randn(1, A, 12, generator=g) * 0.1
+        reg[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5]) + torch.randn(1, A, 4, generator=g) * 0.05
+        dec = decode_oracle.decode3d(anc, reg)
+        got = pp.detect_per_class_fused(cls.cuda(), reg.cuda(), anc.cuda(), score_threshold=0.05)
+        col = 16
+    else:
+        reg = torch.randn(1, A, 4, generator=g) * 0.5
+        dec = decode_oracle.clip(decode_oracle.decode2d(anc, reg), H, W)
+        t = pp.BBoxTransform2D()
+        mean, std = t._host_params()
+        got = pp.detect_per_class_fused(cls.cuda(), reg.cuda(), anc.cuda(), score_threshold=0.05, mean=mean, std=std,
+                                        clip_wh=(W, H))
+        col = 0
+    S, K, X = [], [], []
+    for c in range(8):                                             # retinanet/model.py:287-309 with the oracle's nms
+        m = cls[0, :, c] > 0.05
+        if int(m.sum()) == 0:
+            continue
+        sc, bx = cls[0, m, c], dec[0][m]
+        keep = nms_oracle.nms(bx[:, col:col + 4].contiguous(), sc, 0.5)
+        S.append(sc[keep]); K.append(torch.full((keep.numel(),), c, dtype=torch.int64)); X.append(bx[keep])
+    want = (torch.cat(S), torch.cat(K), torch.cat(X))
+    assert 0 < want[0].numel() < n_cand, "NMS must suppress something on this workload"
+    assert torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1])
+    if three_d:
+        assert torch.equal(got[2].cpu(), want[2])
+    else:
+        assert_close_rel(got[2].cpu(), want[2], 1e-6, "2D boxes")
+    assert int(got[3].max()) == 0

@@ -87,3 +87,68 @@ def test_frame_geometry_equals_separate_calls_and_oracle(graph):
             assert torch.equal(out["im_keep"].cpu(), to.im_nms(ho.wrapper_state_to_im(det, Pc[:, 0], Pc[:, 1]), sc, 0.3))
     with pytest.raises(ValueError):
         frame(torch.zeros(641, 6).cuda(), torch.zeros(1, 6).cuda(), torch.zeros(1).cuda(), torch.zeros(1).cuda())
+
+
+def test_select_best_box_golden_and_oracle():
+    """select_best_box (MC3D_crop_tracker.py:974-1028): identical rows to the unmodified method's (golden) for three
+    weights, CPU and CUDA inputs, and to the oracle on a larger seeded case"""
+    from geom3d_b200 import tracker_geometry as tg
+    from oracle import tracker_oracle as to
+    gd = load_golden("best_box")
+    n = gd["confs"].shape[0]
+    for W, tag in ((0.4, "0_4"), (0.0, "0_0"), (1.0, "1_0")):
+        for put in (lambda t: t.cuda(), lambda t: t):
+            best, cls, cf = tg.select_best_box(put(gd["prior"]), put(gd["preds"].reshape(-1, 6)), put(gd["confs"]),
+                                               put(gd["classes"]), n, W)
+            assert torch.equal(best.cpu(), gd[f"best_{tag}"]) and torch.equal(cls.cpu(), gd[f"cls_{tag}"])
+            assert torch.equal(cf.cpu(), gd[f"conf_{tag}"])
+    g = synth.gen(93)
+    n, d = 700, 13
+    prior, _ = synth.vehicle_states(n, g, n_cams=1)
+    preds = prior.unsqueeze(1).repeat(1, d, 1)
+    preds[:, :, :2] += torch.randn(n, d, 2, generator=g) * torch.tensor([8.0, 2.0])
+    confs, classes = torch.rand(n, d, generator=g), torch.randint(0, 8, (n, d), generator=g)
+    want = to.select_best_box(prior, preds, confs, classes, n, 0.3)
+    got = tg.select_best_box(prior.cuda(), preds.cuda(), confs.cuda(), classes.cuda(), n, 0.3)
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(got, want))
+
+
+def test_evaluator_iou_with_union_epsilon():
+    """the scalar iou of mot_evaluator.py:87-118 adds 1e-6 to the union; g3d_pairwise_iou_f64(eps) against the
+    unmodified function's values (golden, float64 boxes) and the oracle on float32 boxes incl. degenerate ones"""
+    from geom3d_b200 import tracker_geometry as tg
+    from oracle import tracker_oracle as to
+    gd = load_golden("best_box")
+    a, b = gd["eval_a"], gd["eval_b"]
+    # the kernel takes float32 boxes (promoted to float64 inside, as the trackers' .double()): compare on boxes that are
+    # exactly representable, i.e. the float32 roundings of the golden boxes, through the oracle pinned by the golden file
+    assert torch.equal(to.pairwise_iou_eps(a, b), gd["eval_iou"])
+    a32, b32 = a.float(), b.float()
+    got = tg.pairwise_iou(a32.cuda(), b32.cuda(), eps=1e-6)
+    assert got.dtype == torch.float64 and torch.equal(got.cpu(), to.pairwise_iou_eps(a32, b32, 1e-6))
+    deg = torch.tensor([[1.0, 1.0, 1.0, 1.0], [0.0, 0.0, 2.0, 2.0]])
+    got = tg.pairwise_iou(deg.cuda(), deg.cuda(), eps=1e-6).cpu()
+    assert float(got[0, 0]) == 0.0 and not torch.isnan(got).any()       # 0 / 1e-6, not the NaN of the eps-free md_iou
+    assert torch.isnan(tg.pairwise_iou(deg.cuda(), deg.cuda()).cpu()[0, 0])
+
+
+def test_cfg5_full_size_frame_vs_oracle():
+    """BASELINE.json configs[4] at its full size: 2000 tracked objects x 2000 detections over 18 cameras - the cost matrix
+    bit for bit, both keep lists identical to the oracle's"""
+    from geom3d_b200 import tracker_geometry as tg
+    from oracle import homography_oracle as ho, tracker_oracle as to
+    P, _ = synth.camera_matrices(18)
+    Pd = torch.from_numpy(P).cuda()
+    g = synth.gen(7)                                                  # bench.py's cfg5 generator
+    s5, c5 = synth.vehicle_states(2000, g)
+    j5 = s5.clone()
+    j5[:, :2] += torch.randn(2000, 2, generator=g) * torch.tensor([3.0, 0.5])
+    sc5 = torch.rand(2000, generator=g)
+    frame = tg.FrameGeometry(Pd, 2000, 2000, phi_space=0.1, phi_im=0.3)
+    out = frame(s5.cuda(), j5.cuda(), sc5.cuda(), c5.cuda())
+    assert torch.equal(out["cost"].cpu(), to.association_cost(s5, j5))
+    assert torch.equal(out["space_keep"].cpu(), to.space_nms(j5, sc5, 0.1))
+    Pc = torch.from_numpy(P)[c5.long()]
+    corners = ho.wrapper_state_to_im(j5, Pc[:, 0], Pc[:, 1])
+    assert torch.equal(out["im_keep"].cpu(), to.im_nms(corners, sc5, 0.3))
+    assert 0 < out["space_keep"].numel() < 2000 and 0 < out["im_keep"].numel() < 2000

@@ -218,3 +218,41 @@ def test_estimate_ts_bias(golden):
         ts2 = [t + 1 / 30.0 + 0.001 * k for k, t in enumerate(ts)]
         b2 = tracker_oracle.estimate_ts_bias(boxes, cams, view, ts2, b1, 105.0, 0.1, 0.05)
         assert b2 == gd[f"bias2_{tag}"].tolist(), tag
+
+
+def test_select_best_box_and_evaluator_iou(golden):
+    """tracker_oracle.select_best_box / pairwise_iou_eps against the UNMODIFIED MC_Crop_Tracker.select_best_box
+    (MC3D_crop_tracker.py:974-1028) and MOT_Evaluator.iou (mot_evaluator.py:87-118) - tests/golden/best_box.npz"""
+    gd = golden("best_box")
+    n = gd["confs"].shape[0]
+    for W, tag in ((0.4, "0_4"), (0.0, "0_0"), (1.0, "1_0")):
+        best, cls, cf = tracker_oracle.select_best_box(gd["prior"], gd["preds"], gd["confs"], gd["classes"], n, W)
+        assert torch.equal(best, gd[f"best_{tag}"]) and torch.equal(cls, gd[f"cls_{tag}"]) and torch.equal(cf, gd[f"conf_{tag}"])
+    got = tracker_oracle.pairwise_iou_eps(gd["eval_a"], gd["eval_b"], 1e-6)
+    assert torch.equal(got, gd["eval_iou"]), float((got - gd["eval_iou"]).abs().max())
+
+
+def test_postprocess_batch_flattening_equals_loop_over_the_reference_expressions():
+    """B > 1 in the default branch: the reference's squeeze / boolean-mask expressions (3D model.py:365-395) evaluated
+    literally on a small batch equal the oracle's flattened form"""
+    g = synth.gen(55)
+    B, A, C = 3, 400, 4
+    cls = synth.detection_scores(B, A, C, g, objects=6, per_object=7)
+    boxes = torch.rand(B, A, 20, generator=g) * 100
+    boxes[..., 18:20] = boxes[..., 16:18] + 5 + torch.rand(B, A, 2, generator=g) * 30
+    S, K, X = [], [], []
+    for i in range(C):                                             # the reference's loop, names and all
+        scores = torch.squeeze(cls[:, :, i])
+        keep, keep_count, threshold = 10000, 1000000, 1e-25
+        while keep_count > keep:
+            scores_over_thresh = (scores > threshold)
+            keep_count = scores_over_thresh.sum()
+            threshold *= (10 ** .2)
+        if scores_over_thresh.sum() == 0:
+            continue
+        scores = scores[scores_over_thresh]
+        anchorBoxes = torch.squeeze(boxes)[scores_over_thresh]
+        idx = nms_oracle.nms(anchorBoxes[:, 16:20], scores, 0.5)
+        S.append(scores[idx]); K.append(torch.tensor([i] * idx.shape[0])); X.append(anchorBoxes[idx])
+    got = nms_oracle.detect_3d(cls, boxes)
+    assert torch.equal(got[0], torch.cat(S)) and torch.equal(got[1], torch.cat(K)) and torch.equal(got[2], torch.cat(X))
