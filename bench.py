@@ -11,8 +11,10 @@ A step = FocalLoss forward + backward over one batch.  Metric: G anchor-GT pairs
           the host->device copies of classification / regression / annotations and the device->host read of the three
           losses inside the timed region.
 Multi-GPU: weak scaling - every rank owns its own 32-image shard (global batch 32 N); the only collective is the
-5-scalar all-gather of dist.sharded_focal_loss.
-Other workloads (configs 3-5: decode+NMS, homography, tracking frame) are reported in "other_workloads" (N = 1 only).
+5-scalar all-gather of dist.sharded_focal_loss.  "strong_scaling" (N > 1): the 32-image batch of BASELINE configs[1]
+sharded over the ranks (32 / N images each).
+Other workloads (configs 3-5: decode+NMS, homography, tracking frame) are reported in "other_workloads"; decode+NMS and
+the homography shard by image / state range at N > 1 (no collective), the tracking frame is replicas only.
 --impl reference: the oracle port of the reference's CPU implementation, timed on the host cores (rank 0 only).
 """
 import argparse
@@ -181,118 +183,179 @@ def _event_ms(pairs):
     return sum(a.elapsed_time(b) for a, b in pairs)
 
 
-def other_workloads(dev, hbm_peak):
-    """configs 3-5 on one GPU; each entry: metric, value, unit, roofline of its dominant kernel"""
+def _timed(fn, iters, dev, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1) / iters
+
+
+def _best_of(fn, repeats=3):
+    """CPU baseline timing: one warm-up call, then the best of `repeats`"""
+    fn()
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def _bind_to_gpu_numa_node(local):
+    """Pin this process (and with it the pinned host buffers it allocates afterwards: first touch) to the CPU cores of
+    the GPU's NUMA node, so that 8 ranks do not all pull their host->device copies through one socket.  Returns a
+    description for the bench line; silently does nothing where sysfs / affinity are not available."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            out = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip()
+            bus = out.lower()
+            if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+                bus = bus[4:]                                        # 00000000:1B:00.0 -> 0000:1b:00.0
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(base + "/numa_node").read())
+        cpulist = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed), "pci": bus}
+    except Exception as e:  # noqa: BLE001
+        return {"numa_node": None, "note": f"not bound ({type(e).__name__})"}
+
+
+def other_workloads(dev, hbm_peak, rank, world):
+    """configs 3-5 (+ the Kalman filter).  Work shards over the ranks with no collective: images for
+    decode + NMS (64 -> 64 / N per GPU), state ranges for the homography (10 M -> 10 M / N), replicas only for the
+    2000-object tracking frame and the filter (rank 0).  Every figure: device time, max over ranks, whole-job rate."""
     import synth
     from geom3d_b200 import ops, postprocess, tracker_geometry
     out = []
-
-    def timed(fn, iters, warm=3):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            fn()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        return e0.elapsed_time(e1) / iters
-
+    timed = lambda fn, iters, warm=3: _timed(fn, iters, dev, warm)   # noqa: E731
     g = synth.gen(7)
     anc = synth.anchors(H_IMG, W_IMG).to(dev)
     A = anc.shape[1]
     # ---- config 3: decode + score filter + NMS, batch 64 at 1080p, ~5k pre-NMS boxes per image
-    B3 = 64
+    B3_total = 64
+    B3 = B3_total // world
     cls = torch.rand(B3, A, C_CLS, device=dev) * 0.04
-    small = synth.detection_scores(1, A, C_CLS, g)           # 200 objects x 25 anchors scoring U(0.05, 1)
+    small = synth.detection_scores(1, A, C_CLS, g)           # 200 objects x 25 anchors scoring U(0.05, 1) - image 0 of the parity test
     hot = torch.nonzero(small[0] > 0.04)
     for b in range(B3):
-        shift = (hot[:, 0] + 1237 * b) % A
+        shift = (hot[:, 0] + 1237 * (b + rank * B3)) % A
         cls[b, shift.to(dev), hot[:, 1].to(dev)] = small[0][hot[:, 0], hot[:, 1]].to(dev)
     reg3 = torch.randn(B3, A, 12, device=dev) * 0.1
     reg3[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5], device=dev) + torch.randn(B3, A, 4, device=dev) * 0.05
-    t_dec = timed(lambda: ops.decode3d(anc, reg3), 5)
-    dec_bytes = B3 * A * (48 + 80) + 16 * A
-    boxes = ops.decode3d(anc, reg3)
-    t_pipe = timed(lambda: postprocess.detect_per_class(cls, boxes, box_col=16, score_threshold=0.05), 3, warm=2)
-    n_det = postprocess.detect_per_class(cls, boxes, box_col=16, score_threshold=0.05)[0].numel()
-    del boxes
     # the path PostProcess3D takes: filter first, decode only the candidates / kept rows (no [B,A,20] tensor)
-    t_fused = timed(lambda: postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05), 5, warm=2)
+    t_fused = _max_over_ranks(timed(lambda: postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05), 5, warm=2), world, dev)
     n_fused = postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05)[0].numel()
-    out.append({"workload": "config 3: 3D decode + scores>0.05 + per-class NMS 0.5, batch 64 at 1080p, ~5k pre-NMS boxes/img",
-                "metric": "decode+NMS img/s", "value": B3 / (t_fused * 1e-3), "unit": "img/s",
-                "ms": {"filter->decode-on-the-fly->nms->assemble (PostProcess path)": t_fused,
-                       "decode3d (full tensor, BBoxTransform alone)": t_dec,
-                       "filter+nms+assemble on the decoded tensor": t_pipe},
-                "unfused_img_per_s": B3 / ((t_dec + t_pipe) * 1e-3), "detections": n_fused, "detections_unfused": n_det,
-                "note": "the fused tail reads the class scores once (0.80 GB) - its HBM floor is 122 us per batch; "
-                        "the NMS chain is latency-bound (SURVEY.md §8d)",
-                "roofline": {"kernel": "decode3d_kernel", "bound": "hbm", "achieved": dec_bytes / (t_dec * 1e-3) / 1e9,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": dec_bytes / (t_dec * 1e-3) / 1e9 / hbm_peak}})
-    # CPU port of the reference on ONE of the 64 images (decode + scores > 0.05 + per-class nms + cat)
-    from oracle import decode_oracle, homography_oracle, nms_oracle, tracker_oracle
-    cls1, reg1, anc_h = cls[:1].cpu(), reg3[:1].cpu(), anc.cpu()
-    try:    # the reference calls torchvision.ops.nms (C++ CPU kernel); fall back to the oracle's restatement of it
-        from torchvision.ops import nms as cpu_nms
-        nms_name = "torchvision.ops.nms"
-    except Exception:   # noqa: BLE001
-        cpu_nms, nms_name = nms_oracle.nms, "oracle nms"
-    t0 = time.perf_counter()
-    dec1 = decode_oracle.decode3d(anc_h, reg1)[0]
-    for c in range(C_CLS):
-        m = cls1[0, :, c] > 0.05
-        if int(m.sum()):
-            kept = cpu_nms(dec1[m][:, 16:20].contiguous(), cls1[0, m, c], 0.5)
-            _ = dec1[m][kept]
-    t_cpu3 = time.perf_counter() - t0
-    out[-1]["cpu_baseline"] = {"value": 1.0 / t_cpu3, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"1 of the 64 images (oracle decode3d + scores>0.05 + per-class {nms_name} + gather, "
-                                         f"{t_cpu3:.2f} s)"}
-    del cls, reg3, cls1, reg1
+    # its HBM-bound launch on its own (compact8_kernel: every class score read once), and the stand-alone decode
+    thr3 = torch.full((B3 * C_CLS,), 0.05, dtype=torch.float32, device=dev)
+    t_filter = timed(lambda: ops.filter_compact(cls, B3, C_CLS, A, A * C_CLS, thr3, 16384), 10)
+    filt_bytes = B3 * A * C_CLS * 4
+    entry = {"workload": f"config 3: 3D decode + scores>0.05 + per-class NMS 0.5, batch {B3_total} at 1080p, ~5k pre-NMS boxes/img, "
+                         f"{B3} images per GPU",
+             "metric": "decode+NMS img/s", "value": B3_total / (t_fused * 1e-3), "unit": "img/s", "n_gpus": world,
+             "ms": {"filter->decode-on-the-fly->nms->assemble (PostProcess path)": t_fused, "compact8_kernel (score filter) alone": t_filter},
+             "detections_rank0": n_fused,
+             "note": "the fused tail reads the class scores once - that launch is the HBM-bound one; the sort / NMS chain "
+                     "behind it is latency-bound (SURVEY.md §8d)",
+             "roofline": {"kernel": "compact8_kernel", "bound": "hbm", "achieved": filt_bytes / (t_filter * 1e-3) / 1e9,
+                          "peak": hbm_peak, "unit": "GB/s", "frac": filt_bytes / (t_filter * 1e-3) / 1e9 / hbm_peak,
+                          "share_of_tail": t_filter / t_fused, "latency_bound_rest_ms": t_fused - t_filter}}
+    if rank == 0 and world == 1:
+        t_dec = timed(lambda: ops.decode3d(anc, reg3), 5)
+        dec_bytes = B3 * A * (48 + 80) + 16 * A
+        boxes = ops.decode3d(anc, reg3)
+        t_pipe = timed(lambda: postprocess.detect_per_class(cls, boxes, box_col=16, score_threshold=0.05), 3, warm=2)
+        del boxes
+        entry["ms"]["decode3d (full tensor, BBoxTransform alone)"] = t_dec
+        entry["ms"]["filter+nms+assemble on the decoded tensor"] = t_pipe
+        entry["unfused_img_per_s"] = B3 / ((t_dec + t_pipe) * 1e-3)
+        entry["decode3d_roofline"] = {"bytes": dec_bytes, "GBps": dec_bytes / (t_dec * 1e-3) / 1e9,
+                                      "frac": dec_bytes / (t_dec * 1e-3) / 1e9 / hbm_peak}
+        # CPU port of the reference on ONE of the 64 images (decode + scores > 0.05 + per-class nms + cat)
+        from oracle import decode_oracle, nms_oracle
+        cls1, reg1, anc_h = cls[:1].cpu(), reg3[:1].cpu(), anc.cpu()
+        try:    # the reference calls torchvision.ops.nms (C++ CPU kernel); fall back to the oracle's restatement of it
+            from torchvision.ops import nms as cpu_nms
+            nms_name = "torchvision.ops.nms"
+        except Exception:   # noqa: BLE001
+            cpu_nms, nms_name = nms_oracle.nms, "oracle nms"
+
+        def cpu3():
+            dec1 = decode_oracle.decode3d(anc_h, reg1)[0]
+            for c in range(C_CLS):
+                m = cls1[0, :, c] > 0.05
+                if int(m.sum()):
+                    kept = cpu_nms(dec1[m][:, 16:20].contiguous(), cls1[0, m, c], 0.5)
+                    _ = dec1[m][kept]
+        t_cpu3 = _best_of(cpu3)
+        entry["cpu_baseline"] = {"value": 1.0 / t_cpu3, "unit": "img/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"1 of the 64 images (oracle decode3d + scores>0.05 + per-class {nms_name} + gather; "
+                                           f"best of 3 after a warm-up, {t_cpu3:.3f} s)"}
+    out.append(entry)
+    del cls, reg3
     torch.cuda.empty_cache()
-    # ---- config 4: homography, 10 M states x 18 cameras
+    # ---- config 4: homography, 10 M states x 18 cameras, state ranges per rank
     P, Hm = synth.camera_matrices(18)
     Pd, Hd = torch.from_numpy(P).to(dev), torch.from_numpy(Hm).to(dev)
-    d = 10_000_000
-    st, cam = synth.vehicle_states(d, g)
+    d_total = 10_000_000
+    d = d_total // world
+    st, cam = synth.vehicle_states(d, synth.gen(7 + rank))
     st, cam = st.to(dev), cam.to(dev)
-    t_s2i = timed(lambda: ops.state_to_im(st, Pd, cam, wrapper=True), 5)
+    t_s2i = _max_over_ranks(timed(lambda: ops.state_to_im(st, Pd, cam, wrapper=True), 5), world, dev)
     s2i_bytes = d * (24 + 1 + 128)
     im = ops.state_to_im(st, Pd, cam, wrapper=True)
     hts = st[:, 4].contiguous()
-    t_i2s = timed(lambda: ops.im_to_state(im, hts, Hd, cam, wrapper=True), 5)
-    # SURVEY.md §8(d): 128 B of float64 image points + height + camera in, 24 B state out per object.  The fused kernel
-    # only needs the bottom face (64 B), but HBM delivers most of each 128-byte line anyway (ncu: ~137 B read / object).
+    t_i2s = _max_over_ranks(timed(lambda: ops.im_to_state(im, hts, Hd, cam, wrapper=True), 5), world, dev)
+    # SURVEY.md §8(d): 128 B of float64 image points + height + camera in, 24 B state out per object; the fused kernel
+    # needs only the bottom face (64 B of the 128)
     i2s_bytes = d * (128 + 8 + 1 + 24)
     i2s_touched = d * (64 + 8 + 1 + 24)
     del im
-    d_all = 1_000_000
-    t_all = timed(lambda: ops.state_to_im(st[:d_all], Pd, None, wrapper=True, all_cams=True), 3)
-    all_bytes = d_all * (24 + 18 * 128)
-    out.append({"workload": "config 4: state_to_im / im_to_state, 10M states, one of 18 cameras each (float64 out)",
-                "metric": "state_to_im M states/s", "value": d / (t_s2i * 1e-3) / 1e6, "unit": "M states/s",
-                "ms": {"state_to_im_10M": t_s2i, "im_to_state_10M": t_i2s, "state_to_im_all18_1M": t_all},
-                "im_to_state_M_per_s": d / (t_i2s * 1e-3) / 1e6,
-                "all_cameras_M_state_cams_per_s": d_all * 18 / (t_all * 1e-3) / 1e6,
-                "roofline": {"kernel": "state_to_im_kernel", "bound": "hbm", "achieved": s2i_bytes / (t_s2i * 1e-3) / 1e9,
-                             "peak": hbm_peak, "unit": "GB/s", "frac": s2i_bytes / (t_s2i * 1e-3) / 1e9 / hbm_peak,
-                             "im_to_state_frac": i2s_bytes / (t_i2s * 1e-3) / 1e9 / hbm_peak,
-                             "im_to_state_frac_bytes_touched": i2s_touched / (t_i2s * 1e-3) / 1e9 / hbm_peak,
-                             "all_cameras_frac": all_bytes / (t_all * 1e-3) / 1e9 / hbm_peak}})
-    # CPU port: 1 M of the 10 M states through the wrapper's state_to_im (per-object camera matrices)
-    n_cpu = 1_000_000
-    st_h, cam_h = st[:n_cpu].cpu(), cam[:n_cpu].cpu().long()
-    P_h = torch.from_numpy(P)[cam_h]
-    t0 = time.perf_counter()
-    homography_oracle.wrapper_state_to_im(st_h, P_h[:, 0], P_h[:, 1])
-    t_cpu4 = time.perf_counter() - t0
-    out[-1]["cpu_baseline"] = {"value": n_cpu / t_cpu4 / 1e6, "unit": "M states/s", "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"1 M of the 10 M states (oracle wrapper_state_to_im, {t_cpu4:.2f} s)"}
-    del st, cam, st_h, cam_h, P_h
+    entry = {"workload": f"config 4: state_to_im / im_to_state, {d_total // 1_000_000}M states, one of 18 cameras each (float64 out), "
+                         f"{d} states per GPU",
+             "metric": "state_to_im M states/s", "value": d_total / (t_s2i * 1e-3) / 1e6, "unit": "M states/s", "n_gpus": world,
+             "ms": {"state_to_im": t_s2i, "im_to_state": t_i2s},
+             "im_to_state_M_per_s": d_total / (t_i2s * 1e-3) / 1e6,
+             "roofline": {"kernel": "state_to_im_kernel", "bound": "hbm", "achieved": s2i_bytes / (t_s2i * 1e-3) / 1e9,
+                          "peak": hbm_peak, "unit": "GB/s", "frac": s2i_bytes / (t_s2i * 1e-3) / 1e9 / hbm_peak,
+                          "im_to_state_frac": i2s_bytes / (t_i2s * 1e-3) / 1e9 / hbm_peak,
+                          "im_to_state_frac_bytes_touched": i2s_touched / (t_i2s * 1e-3) / 1e9 / hbm_peak}}
+    if rank == 0 and world == 1:
+        d_all = 1_000_000
+        t_all = timed(lambda: ops.state_to_im(st[:d_all], Pd, None, wrapper=True, all_cams=True), 3)
+        all_bytes = d_all * (24 + 18 * 128)
+        entry["ms"]["state_to_im_all18_1M"] = t_all
+        entry["all_cameras_M_state_cams_per_s"] = d_all * 18 / (t_all * 1e-3) / 1e6
+        entry["roofline"]["all_cameras_frac"] = all_bytes / (t_all * 1e-3) / 1e9 / hbm_peak
+        from oracle import homography_oracle
+        n_cpu = 1_000_000
+        st_h, cam_h = st[:n_cpu].cpu(), cam[:n_cpu].cpu().long()
+        P_h = torch.from_numpy(P)[cam_h]
+        t_cpu4 = _best_of(lambda: homography_oracle.wrapper_state_to_im(st_h, P_h[:, 0], P_h[:, 1]))
+        entry["cpu_baseline"] = {"value": n_cpu / t_cpu4 / 1e6, "unit": "M states/s", "cores": os.cpu_count(), "kind": "port",
+                                 "sample": f"1 M of the 10 M states (oracle wrapper_state_to_im; best of 3 after a warm-up, {t_cpu4:.3f} s)"}
+    out.append(entry)
+    del st, cam
     torch.cuda.empty_cache()
-    # ---- config 5: tracking frame, 2000 objects: association matrix + space NMS + image NMS
+    if rank != 0:
+        return out
+    # ---- config 5: tracking frame, 2000 objects: association matrix + space NMS + image NMS (replicas only: rank 0)
+    from oracle import homography_oracle, tracker_oracle
     s5, c5 = synth.vehicle_states(2000, g)
     j5 = s5.clone()
     j5[:, :2] += torch.randn(2000, 2, generator=g) * torch.tensor([3.0, 0.5])
@@ -316,19 +379,23 @@ def other_workloads(dev, hbm_peak):
     t_graph = timed(lambda: fg(s5, j5, sc5, c5), 10)
     s5h, j5h, sc5h = s5.cpu(), j5.cpu(), sc5.cpu()
     P5 = torch.from_numpy(P)[c5.cpu().long()]
-    t0 = time.perf_counter()
-    tracker_oracle.association_cost(s5h, j5h)
-    tracker_oracle.space_nms(j5h, sc5h, 0.1)
-    tracker_oracle.im_nms(homography_oracle.wrapper_state_to_im(j5h, P5[:, 0], P5[:, 1]), sc5h, 0.3)
-    t_cpu5 = time.perf_counter() - t0
+
+    def cpu5():
+        tracker_oracle.association_cost(s5h, j5h)
+        tracker_oracle.space_nms(j5h, sc5h, 0.1)
+        tracker_oracle.im_nms(homography_oracle.wrapper_state_to_im(j5h, P5[:, 0], P5[:, 1]), sc5h, 0.3)
+    t_cpu5 = _best_of(cpu5)
     out.append({"workload": "config 5: 2000 objects: footprint association matrix (f64) + space NMS 0.1 + image NMS 0.3",
-                "metric": "tracking-frame geometry frames/s", "value": 1e3 / t_graph, "unit": "frames/s",
+                "metric": "tracking-frame geometry frames/s", "value": 1e3 / t_graph, "unit": "frames/s", "n_gpus": 1,
                 "ms": {"frame (one CUDA graph, FrameGeometry)": t_graph, "frame (separate drop-in calls)": t_frame},
                 "separate_calls_frames_per_s": 1e3 / t_frame,
-                "note": "launch/latency bound (SURVEY.md §8d); graph frame: 5 small input copies + one graph launch + one "
-                        "8-byte read of the keep-list lengths; separate calls: 2 host syncs for the NMS lengths",
+                "note": "replicas only (SURVEY.md §8e: the 2000 x 2000 matrix is too small to shard); launch/latency bound; graph "
+                        "frame: 5 small input copies + one graph launch + one 8-byte read of the keep-list lengths",
                 "cpu_baseline": {"value": 1.0 / t_cpu5, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
-                                 "sample": f"one frame (oracle association_cost + space_nms + state_to_im + im_nms, {t_cpu5:.2f} s)"}})
+                                 "sample": f"one frame (oracle association_cost + space_nms + state_to_im + im_nms; best of 3 "
+                                           f"after a warm-up, {t_cpu5:.3f} s)"}})
+    if world > 1:
+        return out
     # ---- batched Kalman filter (Torch_KF.predict with per-object dt + update of every object)
     nk, Sk, Mk = 1_000_000, 6, 5
     Fk = torch.eye(Sk)
@@ -349,108 +416,77 @@ def other_workloads(dev, hbm_peak):
     upd_bytes = nk * (2 * (Sk + Sk * Sk) * 4 + 8 + Mk * 8)          # X, P in and out, row index, measurement
     from oracle import kf_oracle
     n_cpu = 100_000
-    Xc, Pc, Dc, dtc = Xk[:n_cpu].cpu(), Pk[:n_cpu].cpu(), Dk[:n_cpu].cpu(), dtk[:n_cpu].cpu()
-    t0 = time.perf_counter()
-    Xc, Pc = kf_oracle.predict(Xc, Pc, Dc, dtc, Fk, Qk)
-    kf_oracle.update(Xc, Pc, torch.arange(n_cpu), zk[:n_cpu].cpu(), Hk, Rk, torch.zeros(Mk))
-    t_cpuk = time.perf_counter() - t0
+    Xc0, Pc0, Dc, dtc = Xk[:n_cpu].cpu(), Pk[:n_cpu].cpu(), Dk[:n_cpu].cpu(), dtk[:n_cpu].cpu()
+    zc = zk[:n_cpu].cpu()
+
+    def cpuk():
+        Xc, Pc = kf_oracle.predict(Xc0, Pc0, Dc, dtc, Fk, Qk)
+        kf_oracle.update(Xc, Pc, torch.arange(n_cpu), zc, Hk, Rk, torch.zeros(Mk))
+    t_cpuk = _best_of(cpuk)
     out.append({"workload": "SURVEY 8(f)-4: Torch_KF predict (per-object dt) + update, 1M objects, 6 states / 5 measurements",
                 "metric": "Kalman predict+update M objects/s", "value": nk / ((t_pred + t_upd) * 1e-3) / 1e6,
-                "unit": "M objects/s", "ms": {"predict": t_pred, "update": t_upd},
+                "unit": "M objects/s", "n_gpus": 1, "ms": {"predict": t_pred, "update": t_upd},
                 "roofline": {"kernel": "kf_predict_kernel", "bound": "hbm", "achieved": pred_bytes / (t_pred * 1e-3) / 1e9,
                              "peak": hbm_peak, "unit": "GB/s", "frac": pred_bytes / (t_pred * 1e-3) / 1e9 / hbm_peak,
                              "update_frac": upd_bytes / (t_upd * 1e-3) / 1e9 / hbm_peak},
                 "cpu_baseline": {"value": n_cpu / t_cpuk / 1e6, "unit": "M objects/s", "cores": os.cpu_count(), "kind": "port",
-                                 "sample": f"100 k of the 1 M objects (oracle predict + update, torch CPU bmm / inverse, {t_cpuk:.2f} s)"}})
+                                 "sample": f"100 k of the 1 M objects (oracle predict + update, torch CPU bmm / inverse; best of 3 "
+                                           f"after a warm-up, {t_cpuk:.3f} s)"}})
     return out
 
 
-def run_ours(args):
-    rank, world, local = _dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
+def _loss_inputs(B, A, rank, dev, first_image_from_cpu):
+    """synthetic batch of B images.  Image 0 of rank 0 is generated on the CPU exactly like the image of
+    tests/test_gpu_losses.py::test_cfg2_one_image_1080p_200gt_vs_oracle (synth.gen(100)), so the GPU arm's first image can be
+    cross-checked against the oracle before anything is timed; the rest comes from device generators."""
     import synth
-    from geom3d_b200 import dist as gdist
-    from geom3d_b200 import losses_impl, ops
-
-    hbm_peak, peak_src = _peaks()
-    B = B_PER_GPU
     g = synth.gen(100 + rank)
-    # the anchor table as the model gets it (retinanet/model.py:306: self.anchors(img_batch)): the drop-in Anchors module
-    # writes it on the device and tags it as the regular pyramid, which lets the loss run its GT-centric assignment
-    from geom3d_b200.anchors_impl import Anchors
-    anc = Anchors()(torch.zeros(1, 3, H_IMG, W_IMG, device=dev))
-    assert torch.equal(anc.cpu(), synth.anchors(H_IMG, W_IMG))
-    A = anc.shape[1]
-    ann_h = synth.gt_annotations_3d(B, G_PER_IMG, H_IMG, W_IMG, g).pin_memory()
+    ann0 = synth.gt_annotations_3d(1, G_PER_IMG, H_IMG, W_IMG, g)
+    cls0, reg0 = synth.head_outputs(1, A, C_CLS, R_REG, g)
+    ann_rest = synth.gt_annotations_3d(B - 1, G_PER_IMG, H_IMG, W_IMG, g) if B > 1 else ann0[:0]
+    ann_h = torch.cat((ann0, ann_rest)).contiguous().pin_memory()
     torch.manual_seed(100 + rank)
-    cls_d = (torch.rand(B, A, C_CLS, device=dev) * 0.1).requires_grad_(True)
-    reg_d = (torch.randn(B, A, R_REG, device=dev) * 0.1).requires_grad_(True)
-    ann_d = ann_h.to(dev)
-    ones = torch.ones(3, device=dev)
+    cls_d = torch.rand(B, A, C_CLS, device=dev) * 0.1
+    reg_d = torch.randn(B, A, R_REG, device=dev) * 0.1
+    if first_image_from_cpu:
+        cls_d[0].copy_(cls0[0])
+        reg_d[0].copy_(reg0[0])
+    return ann_h, cls_d, reg_d, (ann0, cls0, reg0)
 
-    def step_device(record=None, trace=None):
-        cls_d.grad = None
-        reg_d.grad = None
-        if record is not None:
-            record[0].record()
-        if world > 1:
-            losses = gdist.sharded_focal_loss(cls_d, reg_d, anc, ann_d, trace_events=trace)
-        else:
-            losses = losses_impl.focal_loss(cls_d, reg_d, anc, ann_d, trace_events=trace)[0]
-        if record is not None:
-            record[1].record()
-        losses.backward(ones)
-        if record is not None:
-            record[2].record()
-        return losses
 
-    for _ in range(args.warmup):
-        step_device()
+def _time_loss_steps(step, steps, warmup, world, dev, allow_graph=True):
+    """ms per step of `step()` (forward + backward): eager, and as one CUDA-graph replay per step.  Returns
+    (best ms, mode, eager ms, graph ms or None, losses of the last step)."""
+    for _ in range(warmup):
+        step()
     torch.cuda.synchronize(dev)
     if world > 1:
         torch.distributed.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]   # per-kernel events
-    for tr in kev:
-        for e in tr:
-            e.record()      # creates the CUDA events outside the timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(dev)
     e0.record()
-    for i in range(args.steps):
-        losses = step_device(evs[i], kev[i])
+    for _ in range(steps):
+        losses = step()
     e1.record()
     torch.cuda.synchronize(dev)
     if world > 1:
         torch.distributed.barrier()
-    losses = losses.detach().clone()    # drop the autograd graph (its AccumulateGrad nodes would pin the legacy stream)
-    ms_total = _max_over_ranks(e0.elapsed_time(e1), world, dev)
-    ms_step_eager = ms_total / args.steps
-    # ---- the same K steps as ONE CUDA graph launch per step (forward + backward, all kernels and the small torch ops):
-    # removes the host-side launch gaps between the six short kernels.  Falls back to the eager figure if capture fails.
-    ms_step, mode = ms_step_eager, "eager (one Python call per step)"
-    if not args.no_graph:
+    losses = losses.detach().clone()
+    ms_eager = _max_over_ranks(e0.elapsed_time(e1), world, dev) / steps
+    ms_step, mode, ms_graph = ms_eager, "eager (one Python call per step)", None
+    if allow_graph:
         graph, ok = None, 1
         try:
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 for _ in range(3):
-                    step_device()
+                    step()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             graph = torch.cuda.CUDAGraph()
             # thread_local: the NCCL watchdog thread's CUDA calls must not invalidate the capture (world > 1)
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                g_losses = step_device().detach()
+                g_losses = step().detach()
             torch.cuda.synchronize(dev)
         except Exception as e:   # noqa: BLE001 - any capture problem: keep the eager number
             ok, mode = 0, f"eager (graph capture failed: {type(e).__name__}: {str(e)[:200]})"
@@ -461,20 +497,20 @@ def run_ours(args):
                 mode = "eager (graph capture failed on another rank)"
             ok = int(flag.item())
         if ok:
-            for _ in range(args.warmup):
+            for _ in range(warmup):
                 graph.replay()
             torch.cuda.synchronize(dev)
             if world > 1:
                 torch.distributed.barrier()
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
-            for _ in range(args.steps):
+            for _ in range(steps):
                 graph.replay()
             g1.record()
             torch.cuda.synchronize(dev)
             if world > 1:
                 torch.distributed.barrier()
-            ms_graph = _max_over_ranks(g0.elapsed_time(g1), world, dev) / args.steps
+            ms_graph = _max_over_ranks(g0.elapsed_time(g1), world, dev) / steps
             same = torch.tensor([1 if torch.equal(g_losses, losses) else 0], dtype=torch.int32, device=dev)
             if world > 1:
                 torch.distributed.all_reduce(same, op=torch.distributed.ReduceOp.MIN)
@@ -483,20 +519,118 @@ def run_ours(args):
         if graph is not None:
             graph.reset()
             del graph
+    return ms_step, mode, ms_eager, ms_graph, losses
+
+
+def run_ours(args):
+    rank, world, local = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    numa = _bind_to_gpu_numa_node(local)          # before any pinned allocation
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import synth
+    from geom3d_b200 import dist as gdist
+    from geom3d_b200 import losses_impl, ops
+
+    hbm_peak, peak_src = _peaks()
+    B = B_PER_GPU
+    # the anchor table as the model gets it (retinanet/model.py:306: self.anchors(img_batch)): the drop-in Anchors module
+    # writes it on the device and tags it as the regular pyramid, which lets the loss run its GT-centric assignment
+    from geom3d_b200.anchors_impl import Anchors
+    anc = Anchors()(torch.zeros(1, 3, H_IMG, W_IMG, device=dev))
+    assert torch.equal(anc.cpu(), synth.anchors(H_IMG, W_IMG))
+    A = anc.shape[1]
+    ann_h, cls_raw, reg_raw, image0 = _loss_inputs(B, A, rank, dev, first_image_from_cpu=True)
+    cls_d, reg_d = cls_raw.requires_grad_(True), reg_raw.requires_grad_(True)
+    ann_d = ann_h.to(dev)
+    ones = torch.ones(3, device=dev)
+
+    # ---- parity gate: before anything is timed, image 0 of this arm against the oracle (the CPU arm's implementation)
+    parity = None
+    if rank == 0:
+        from oracle import losses_oracle
+        ann0, cls0, reg0 = image0
+        t0 = time.perf_counter()
+        ref = losses_oracle.focal_loss(cls0, reg0, anc.cpu(), ann0)
+        t_oracle = time.perf_counter() - t0
+        with torch.no_grad():
+            per_image = losses_impl.focal_loss(cls_d.detach(), reg_d.detach(), anc, ann_d)[2].cpu()
+        want = torch.tensor([float(ref[0]), float(ref[1]), float(ref[2]), float(ref[3][0][2].sum())])
+        err = ((per_image[0].double() - want.double()).abs() / want.double().abs().clamp(min=1e-30)).tolist()
+        assert max(err[:3]) < 1e-5 and err[3] == 0.0, f"GPU image 0 differs from the oracle: {per_image[0].tolist()} vs {want.tolist()}"
+        parity = {"image0_gpu": per_image[0].tolist(), "image0_oracle": want.tolist(), "max_rel_err_losses": max(err[:3]),
+                  "num_pos_equal": err[3] == 0.0, "oracle_seconds": t_oracle,
+                  "note": "(cls, reg, vp, num_pos) of image 0 of the timed batch, checked before timing; same image as "
+                          "tests/test_gpu_losses.py::test_cfg2_one_image_1080p_200gt_vs_oracle"}
+
+    def make_step(c, r, a_d, sharded, trace_holder=None):
+        def step():
+            c.grad = None
+            r.grad = None
+            tr = trace_holder[0] if trace_holder else None
+            if sharded:
+                losses = gdist.sharded_focal_loss(c, r, anc, a_d, trace_events=tr)
+            else:
+                losses = losses_impl.focal_loss(c, r, anc, a_d, trace_events=tr)[0]
+            losses.backward(ones)
+            return losses
+        return step
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- headline: weak scaling, B images per rank
+    step_device = make_step(cls_d, reg_d, ann_d, world > 1)
+    ms_step, mode, ms_step_eager, ms_graph, losses = _time_loss_steps(step_device, args.steps, args.warmup, world, dev,
+                                                                       allow_graph=not args.no_graph)
+    # ---- per-kernel times: traced eager steps (the event records serialise the launches that otherwise overlap)
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(args.steps)]
+    bwd_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    for tr in kev + bwd_ev:
+        for e in tr:
+            e.record()      # creates the CUDA events outside the timed region
+    torch.cuda.synchronize(dev)
+    for i in range(args.steps):
+        cls_d.grad = None
+        reg_d.grad = None
+        if world > 1:
+            l3 = gdist.sharded_focal_loss(cls_d, reg_d, anc, ann_d, trace_events=kev[i])
+        else:
+            l3 = losses_impl.focal_loss(cls_d, reg_d, anc, ann_d, trace_events=kev[i])[0]
+        bwd_ev[i][0].record()
+        l3.backward(ones)
+        bwd_ev[i][1].record()
+    torch.cuda.synchronize(dev)
+    del l3
     clocks = sampler.stop() if rank == 0 else None
-    ms_fwd = _event_ms([(e[0], e[1]) for e in evs]) / args.steps
-    ms_bwd = _event_ms([(e[1], e[2]) for e in evs]) / args.steps
-    ms_k = [_event_ms([(e[i], e[i + 1]) for e in kev]) / args.steps for i in range(5)]   # prologue, pairs, resolve, stream, positives
-    ms_assign = ms_k[0] + ms_k[1] + ms_k[2]
-    ms_pos = ms_k[4]
-    ms_stream = ms_k[3]
+    knames = ["loss_prologue_kernel", "assign_pairs_kernel", "assign_resolve_kernel", "focal_stream8_kernel", "positives_kernel"]
+    ms_k = [_event_ms([(e[i], e[i + 1]) for e in kev]) / args.steps for i in range(5)]
+    ms_bwd = _event_ms([(e[0], e[1]) for e in bwd_ev]) / args.steps
+    ms_fwd = sum(ms_k)
     pairs_per_step = world * B * A * G_PER_IMG
     value = pairs_per_step / (ms_step * 1e-3) / 1e9
     loss_vals = [float(x) for x in losses.detach().cpu()]
     with torch.no_grad():
         per_image_vals = losses_impl.focal_loss(cls_d.detach(), reg_d.detach(), anc, ann_d)[2].cpu().tolist()
 
-    # ---- end to end through the public module, from pinned host buffers
+    # ---- strong scaling (BASELINE configs[1] as written: the 32-image batch sharded over the GPUs, 32 / N images each)
+    strong = None
+    if world > 1 and B_PER_GPU % world == 0:
+        Bs = B_PER_GPU // world
+        cs = cls_d.detach()[:Bs].clone().requires_grad_(True)
+        rs = reg_d.detach()[:Bs].clone().requires_grad_(True)
+        step_strong = make_step(cs, rs, ann_d[:Bs].contiguous(), True)
+        ms_s, mode_s, ms_s_eager, _, _ = _time_loss_steps(step_strong, args.steps, args.warmup, world, dev, allow_graph=not args.no_graph)
+        strong = {"global_batch": B_PER_GPU, "images_per_gpu": Bs, "ms_per_step": ms_s, "ms_per_step_eager": ms_s_eager,
+                  "launch_mode": mode_s, "value": B_PER_GPU * A * G_PER_IMG / (ms_s * 1e-3) / 1e9, "unit": UNIT,
+                  "note": "same global batch as N = 1: speed-up = ms_per_step(N = 1) / this; the fixed part of a step (six "
+                          "launches of latency-bound work + the 5-scalar all-gather) does not shrink with the shard"}
+        del cs, rs
+
+    # ---- end to end through the public module (default constructor), from pinned host buffers
     cls_h = torch.empty((B, A, C_CLS), dtype=torch.float32).pin_memory()
     reg_h = torch.empty((B, A, R_REG), dtype=torch.float32).pin_memory()
     cls_h.copy_(cls_d.detach())
@@ -505,13 +639,16 @@ def run_ours(args):
     cls_in = torch.empty_like(cls_d).requires_grad_(True)
     reg_in = torch.empty_like(reg_d).requires_grad_(True)
 
-    def step_e2e():
-        cls_in.grad = None
-        reg_in.grad = None
+    def copy_in():
         with torch.no_grad():
             cls_in.copy_(cls_h, non_blocking=True)
             reg_in.copy_(reg_h, non_blocking=True)
-        ann_in = ann_h.to(dev, non_blocking=True)
+        return ann_h.to(dev, non_blocking=True)
+
+    def step_e2e():
+        cls_in.grad = None
+        reg_in.grad = None
+        ann_in = copy_in()
         if world > 1:
             l3 = gdist.sharded_focal_loss(cls_in, reg_in, anc, ann_in)
             l3.backward(ones)
@@ -532,37 +669,38 @@ def run_ours(args):
     t_e2e = _max_over_ranks((time.perf_counter() - t0) / e2e_steps, world, dev)
     e2e_value = pairs_per_step / t_e2e / 1e9
     h2d = cls_h.numel() * 4 + reg_h.numel() * 4 + ann_h.numel() * 4
+    # the roof of that number: the same host->device copies alone, all ranks at once
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_in()
+    torch.cuda.synchronize(dev)
+    t_copy_local = (time.perf_counter() - t0) / e2e_steps
+    t_copy = _max_over_ranks(t_copy_local, world, dev)
+    h2d_rates = [h2d / t_copy_local / 1e9]
+    if world > 1:
+        gathered = [None] * world
+        torch.distributed.all_gather_object(gathered, (h2d / t_copy_local / 1e9, numa))
+        h2d_rates = gathered
     del cls_h, reg_h, cls_in, reg_in
 
     if rank == 0:
-        # algorithmic bytes of the forward launches: assign_codes_kernel (anchors + GT in, codes + the
-        # zero-filled dreg out; issue-bound), positives_kernel (negligible) and the HBM-bound focal_stream_kernel (cls +
-        # codes in, dcls out; the dominant kernel).  G3D_LOSS_FUSED=1: the experimental single persistent kernel for
-        # both.  backward (dcls already written): the positive rows only.
-        fused = os.environ.get("G3D_LOSS_FUSED", "0") == "1"
-        stream_bytes = B * A * (C_CLS * 4 + 4 + C_CLS * 4)          # cls + codes in, dcls out
-        assign_bytes = B * A * (4 + R_REG * 4) + A * 16             # codes + the zero-filled dreg out, anchors in
-        fwd_bytes = stream_bytes + assign_bytes + ann_h.numel() * 4
-        bwd_bytes = int(sum(p[3] for p in per_image_vals)) * (R_REG * 4 * 2 + 4 + 21 * 4)
-        if fused:
-            knames = ("focal_fused_kernel", "positives_finalize_kernel", "-")
-            dom, dom_bytes, dom_ms = "focal_fused_kernel", stream_bytes + assign_bytes, ms_assign
-        else:
-            knames = ("assign_codes_kernel", "positives_kernel", "focal_stream_kernel")
-            # the two long launches are within a few percent of each other: the dominant one is whichever measured longer
-            # in THIS run (assign_codes_kernel is FP32-issue-bound - its HBM fraction says how much bandwidth it leaves
-            # idle, not how good it is -, focal_stream_kernel is the HBM-bound one)
-            dom, dom_bytes, dom_ms = max((("focal_stream_kernel", stream_bytes, ms_stream),
-                                          ("assign_codes_kernel", assign_bytes, ms_assign)), key=lambda t: t[2])
-        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-        per_kernel = [] if fused else [
-            {"kernel": "focal_stream_kernel", "ms": ms_stream, "share_of_forward": ms_stream / ms_fwd, "bytes": stream_bytes,
-             "GBps": stream_bytes / (ms_stream * 1e-3) / 1e9, "frac": stream_bytes / (ms_stream * 1e-3) / 1e9 / hbm_peak,
-             "limiter": "hbm", "traffic": _traffic("focal_stream_kernel")},
-            {"kernel": "assign_codes_kernel", "ms": ms_assign, "share_of_forward": ms_assign / ms_fwd, "bytes": assign_bytes,
-             "GBps": assign_bytes / (ms_assign * 1e-3) / 1e9, "frac": assign_bytes / (ms_assign * 1e-3) / 1e9 / hbm_peak,
-             "limiter": "fp32 issue (ncu: 75 % of issue slots busy, anchors + GT L2-resident)",
-             "traffic": _traffic("assign_codes_kernel")}]
+        # algorithmic bytes.  The sweep (focal_stream8_kernel) moves, per (image, anchor): 32 B of
+        # classification in, 32 B of classification gradient out, 48 B of regression-gradient zeros out = 112 B - everything
+        # SURVEY §8(d)'s fused forward+backward figure (160 B) contains except the 48 B read of `reg`, which this design
+        # touches only on the ~1 % positive rows (positives_kernel).  The other launches move little and are latency-bound.
+        stream_bytes = B * A * (C_CLS * 4 * 2 + R_REG * 4)
+        chain_bytes = B * A * 4 * 2 + A * 16 + ann_h.numel() * 4               # key zero fill + keys of touched chunks, anchors, GT
+        ms_stream = ms_k[3]
+        achieved = stream_bytes / (ms_stream * 1e-3) / 1e9
+        step_bytes = stream_bytes + chain_bytes
+        per_kernel = [{"kernel": n, "ms": m, "share_of_traced_step": m / (ms_fwd + ms_bwd)} for n, m in zip(knames, ms_k)]
+        per_kernel.append({"kernel": "backward: autograd dispatch on the host + focal_bwd_kernel (verifies the expected upstream gradients, exits)", "ms": ms_bwd,
+                           "share_of_traced_step": ms_bwd / (ms_fwd + ms_bwd)})
+        per_kernel[3].update({"bytes": stream_bytes, "GBps": achieved, "frac": achieved / hbm_peak, "limiter": "hbm",
+                              "traffic": _traffic("focal_stream8_kernel")})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -571,67 +709,79 @@ def run_ours(args):
                                    "G=200 GT/img, C=8, 12-d regression", "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": f"images sharded over {world} GPU(s), 5-scalar all-gather only",
                        "l2": "inputs (1.0 GB/step) exceed the 126 MB L2; no flush needed",
-                       "launch_mode": mode, "ms_per_step_eager": ms_step_eager},
+                       "launch_mode": mode, "ms_per_step_eager": ms_step_eager, "ms_per_step_graph": ms_graph},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
-                    "ms_per_step": t_e2e * 1e3, "steps": e2e_steps},
-            # gt_prepare, focal_fused, positives_finalize, focal_cls_grad, positives (bwd) per step
-            "gpu_launches": (5 if fused else 6) * args.steps,
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": _traffic(dom), "peak_source": peak_src,
+                    "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                    "module": "losses.FocalLoss() as shipped (default constructor: lazy empty-batch check, no host sync)",
+                    "h2d_only_ms": t_copy * 1e3, "h2d_roof_fraction": t_copy / t_e2e,
+                    "h2d_GBps_per_rank": h2d_rates if world == 1 else [x[0] for x in h2d_rates],
+                    "numa": numa if world == 1 else [x[1] for x in h2d_rates],
+                    "note": "the step is bound by the host->device copy of its 1 GB of inputs: h2d_roof_fraction = the share "
+                            "of the step that the same copies take alone; each rank's pinned buffers are allocated on the "
+                            "NUMA node of its GPU"},
+            # prologue, pairs, resolve, stream, positives + the backward's verification launch
+            "gpu_launches": 6 * args.steps,
+            "roofline": {"kernel": "focal_stream8_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": _traffic("focal_stream8_kernel"), "peak_source": peak_src,
+                         "bytes_per_launch": stream_bytes, "ms_per_launch": ms_stream,
                          "kernels": per_kernel,
-                         "ms": {"forward": ms_fwd, "backward": ms_bwd, knames[0]: ms_assign, knames[1]: ms_pos,
-                                knames[2]: ms_stream},
-                         # SURVEY.md §8(d) "fused fwd+bwd": 160 B per (image, anchor) - cls + reg in, dcls + dreg out - plus
-                         # the anchors once: the whole step against the HBM roofline (this design never reads reg except
-                         # for the positives, so its own traffic is lower: see forward / backward below)
+                         # the whole step on the bytes it has to move (cls in, dcls + dreg out, key fill + touched keys) ...
+                         "step_on_bytes_moved": {"bytes": step_bytes, "GBps": step_bytes / (ms_step * 1e-3) / 1e9,
+                                                 "frac": step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak},
+                         # ... and on SURVEY.md §8(d)'s 160 B per (image, anchor), 48 B of which (reading reg) this design never moves
                          "step_on_survey_bytes": {"bytes": B * A * 160 + A * 16,
                                                   "GBps": (B * A * 160 + A * 16) / (ms_step * 1e-3) / 1e9,
-                                                  "frac": (B * A * 160 + A * 16) / (ms_step * 1e-3) / 1e9 / hbm_peak},
-                         "forward": {"bytes": fwd_bytes, "GBps": fwd_bytes / (ms_fwd * 1e-3) / 1e9,
-                                     "frac": fwd_bytes / (ms_fwd * 1e-3) / 1e9 / hbm_peak},
-                         "backward": {"bytes": bwd_bytes, "GBps": bwd_bytes / (ms_bwd * 1e-3) / 1e9,
-                                      "frac": bwd_bytes / (ms_bwd * 1e-3) / 1e9 / hbm_peak}},
-            "losses": loss_vals, "e2e_losses": [float(x) for x in host_losses], "ms_kernels": ms_k,
+                                                  "frac": (B * A * 160 + A * 16) / (ms_step * 1e-3) / 1e9 / hbm_peak}},
+            "parity": parity,
+            "losses": loss_vals, "e2e_losses": [float(x) for x in host_losses],
+            "positives_per_image_mean": sum(p[3] for p in per_image_vals) / len(per_image_vals),
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
 
     # forward-only pass (validation loss, no gradient buffers): GT-centric assignment on the tagged pyramid table against
     # the anchor-centric kernel on an untagged copy of the same table (same codes, same losses)
-    fwd_only = None
     if rank == 0 and world == 1:
         anc_plain = anc.clone()
 
         def fwd_time(table):
             with torch.no_grad():
-                for _ in range(3):
-                    out = ops.focal_loss_forward(cls_d, reg_d, table, ann_d)
-                torch.cuda.synchronize(dev)
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(10):
-                    out = ops.focal_loss_forward(cls_d, reg_d, table, ann_d)
-                a1.record()
-                torch.cuda.synchronize(dev)
-            return a0.elapsed_time(a1) / 10, out
+                t = _timed(lambda: ops.focal_loss_forward(cls_d, reg_d, table, ann_d, want_assign=False), 10, dev)
+                return t, ops.focal_loss_forward(cls_d, reg_d, table, ann_d)
         t_gt, o_gt = fwd_time(anc)
         t_an, o_an = fwd_time(anc_plain)
         assert o_gt["gt_centric"] and not o_an["gt_centric"] and torch.equal(o_gt["assign"], o_an["assign"])
-        fwd_only = {"ms_gt_centric": t_gt, "ms_anchor_centric": t_an,
-                    "G_pairs_per_s_gt_centric": pairs_per_step / (t_gt * 1e-3) / 1e9}
-        del anc_plain, o_gt, o_an
-        line["forward_only"] = fwd_only
+        line["forward_only"] = {"ms_gt_centric": t_gt, "ms_anchor_centric": t_an,
+                                "G_pairs_per_s_gt_centric": pairs_per_step / (t_gt * 1e-3) / 1e9}
+        # the training step on an untagged table (any anchor tensor): anchor-centric assignment
+        cp, rp = cls_d.detach().clone().requires_grad_(True), reg_d.detach().clone().requires_grad_(True)
+
+        def step_plain():
+            cp.grad = None
+            rp.grad = None
+            l3 = losses_impl.focal_loss(cp, rp, anc_plain, ann_d)[0]
+            l3.backward(ones)
+            return l3
+        line["anchor_centric_step_ms"] = _timed(step_plain, 5, dev)
+        del anc_plain, o_gt, o_an, cp, rp
     del cls_d, reg_d
     torch.cuda.empty_cache()
+    extras = None
+    if not args.no_extras:
+        try:
+            extras = other_workloads(dev, hbm_peak, rank, world)
+        except Exception as e:  # the headline line must still be printed
+            extras = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise
     if rank == 0:
         if world == 1:
             cpu_value, cpu_s = cpu_loss_sample(8)
             line["cpu_baseline"] = {"value": cpu_value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"8 of the 32 images (oracle port, forward+backward, best of 2 after 1 warm-up, {cpu_s:.2f} s/run)"}
-            if not args.no_extras:
-                try:
-                    line["other_workloads"] = other_workloads(dev, hbm_peak)
-                except Exception as e:  # the headline line must still be printed
-                    line["other_workloads"] = {"error": f"{type(e).__name__}: {e}"}
+        if extras is not None:
+            line["other_workloads"] = extras
         print(json.dumps(line), flush=True)
     if world > 1:
         # A captured graph holds NCCL work; tearing the process group down with it alive can block.  Everything is

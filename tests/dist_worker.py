@@ -1,4 +1,5 @@
-"""Multi-GPU parity of dist.sharded_focal_loss: torchrun --nproc-per-node N tools/check_dist.py
+"""Worker of tests/test_gpu_dist.py (multi-GPU parity of dist.sharded_focal_loss over real NCCL):
+    python -m torch.distributed.run --nproc-per-node N tests/dist_worker.py
 Every rank holds the FULL batch (same seed), computes the loss of its shard through sharded_focal_loss and compares the
 global losses and its local gradients with the single-GPU loss of the full batch."""
 import os, sys
@@ -13,7 +14,8 @@ dev = torch.device("cuda", local); torch.cuda.set_device(dev)
 dist.init_process_group("nccl", device_id=dev)
 B = 2 * world + 3                       # uneven shards on purpose (every rank gets at least 2 images)
 g = synth.gen(5)
-anc = synth.anchors(200, 168).to(dev); A = anc.shape[1]
+from geom3d_b200.anchors_impl import Anchors
+anc = Anchors()(torch.zeros(1, 3, 200, 168, device=dev)); A = anc.shape[1]     # the tagged table: GT-centric assignment
 ann = synth.gt_annotations_3d(B, 9, 200, 168, g, n_pad=1, empty_images=(1,), **synth.TINY).to(dev)
 cls, reg = synth.head_outputs(B, A, 8, 12, g)
 cf, rf = cls.to(dev).requires_grad_(True), reg.to(dev).requires_grad_(True)
