@@ -46,6 +46,8 @@ SIGNATURES = {
                                   _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_set_tuning": (_int, [_int, _i64]),
     "g3d_combine_shard_stats": (_int, [_c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
+    "g3d_exchange_buffer_doubles": (_i64, [_i64]),
+    "g3d_exchange_shard_stats": (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_decode3d": (_int, [_c_ptr, _c_ptr, _i64, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_decode2d": (_int, [_c_ptr, _i64, _c_ptr, _i64, _i64, _c_ptr, _c_ptr, _int, _f32, _f32, _c_ptr, _int, _c_ptr]),
     "g3d_clip_boxes": (_int, [_c_ptr, _i64, _i64, _f32, _f32, _int, _c_ptr]),

@@ -1247,6 +1247,60 @@ __global__ void combine_shard_stats_kernel(const double* __restrict__ gathered, 
     scale[2] = nl > 0.0 ? (float)(nl / t[4]) : 0.0f;
 }
 
+// The same reduction WITHOUT a collective library call: every rank stores its 5 statistics straight into the exchange
+// buffer of every peer over NVLink (peer-mapped symmetric memory), publishes them with a system-scope fence + an epoch
+// flag, and waits for the epoch flags of the others in its own buffer - one launch of one warp per rank instead of an
+// NCCL all-gather plus the combine kernel, and nothing between the loss kernels and it but stream order.
+// Exchange buffer of a rank (doubles): [2 parities][world][8] = {5 statistics, epoch flag (as bits), 2 unused}, then one
+// local epoch counter.  Two parities: a peer can be at most one call ahead of this rank (its next call needs this rank's
+// statistics of that call), so the slot it overwrites then is never the one still being read.  Zero on first use.
+__global__ void exchange_shard_stats_kernel(const double* __restrict__ stats, const unsigned long long* __restrict__ peers,
+                                            int world, int rank, float* __restrict__ losses, float* __restrict__ scale) {
+    const int lane = threadIdx.x;
+    double* mine = reinterpret_cast<double*>(peers[rank]);
+    unsigned long long* epoch_ctr = reinterpret_cast<unsigned long long*>(mine + 2 * world * 8);
+    const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(epoch_ctr) + 1ull;
+    const int parity = (int)(e & 1ull);
+    double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    bool ok = true;
+    if (lane < world) {
+        volatile double* dst = reinterpret_cast<volatile double*>(peers[lane]) + ((int64_t)parity * world + rank) * 8;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) dst[k] = stats[k];
+        __threadfence_system();
+        reinterpret_cast<volatile unsigned long long*>(dst)[5] = e;
+        const volatile double* src = mine + ((int64_t)parity * world + lane) * 8;
+        const long long t0 = clock64();
+        while (reinterpret_cast<const volatile unsigned long long*>(src)[5] != e) {
+            if (clock64() - t0 > 6000000000LL) { ok = false; break; }       // ~3 s: a peer never arrived - do not hang the GPU
+            __nanosleep(100);
+        }
+        __threadfence_system();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = src[k];
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    double t[5] = {0.0, 0.0, 0.0, 0.0, 0.0}, bl = 0.0, nl = 0.0;
+    for (int r = 0; r < world; ++r) {                       // fixed (rank) summation order: the same bits on every rank
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const double x = __shfl_sync(0xffffffffu, v[k], r);
+            t[k] += x;
+            if (r == rank && k == 3) bl = x;
+            if (r == rank && k == 4) nl = x;
+        }
+    }
+    if (lane == 0) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        losses[0] = ok ? (float)(t[0] / t[3]) : (float)nan;
+        losses[1] = ok ? (float)(t[1] / t[3]) : (float)nan;
+        losses[2] = ok ? (float)(t[2] / t[4]) : (float)nan;
+        scale[0] = scale[1] = (float)(bl / t[3]);
+        scale[2] = nl > 0.0 ? (float)(nl / t[4]) : 0.0f;
+        *reinterpret_cast<volatile unsigned long long*>(epoch_ctr) = e;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1344,6 +1398,19 @@ extern "C" int g3d_combine_shard_stats(const double* gathered, int64_t world, in
     G3D_REQUIRE(world >= 1 && rank >= 0 && rank < world && world < (1 << 20), "bad world / rank");
     G3D_GUARD(device);
     combine_shard_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(gathered, (int)world, (int)rank, losses, scale);
+    G3D_LAUNCH_CHECK();
+    return G3D_OK;
+}
+
+extern "C" int64_t g3d_exchange_buffer_doubles(int64_t world) { return world < 1 ? G3D_ERR_INVALID : 2 * world * 8 + 8; }
+
+extern "C" int g3d_exchange_shard_stats(const double* shard_stats, const void* peer_ptrs_dev, int64_t world, int64_t rank,
+                                        float* losses, float* scale, int device, void* stream) {
+    G3D_REQUIRE(shard_stats && peer_ptrs_dev && losses && scale, "null pointer");
+    G3D_REQUIRE(world >= 1 && world <= 32 && rank >= 0 && rank < world, "bad world / rank (one warp exchanges: world <= 32)");
+    G3D_GUARD(device);
+    exchange_shard_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(shard_stats, (const unsigned long long*)peer_ptrs_dev,
+                                                                    (int)world, (int)rank, losses, scale);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

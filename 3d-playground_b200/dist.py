@@ -46,10 +46,51 @@ def combine_on_host(gathered, rank):
     return losses, scale.to(torch.float32)
 
 
+class _PeerExchange:
+    """Peer-mapped exchange buffers of the ranks of one NVLink / NVSwitch box (torch.distributed._symmetric_memory): the
+    shard statistics travel as plain stores into the peers' memory from one tiny kernel (ops.exchange_shard_stats) - no
+    NCCL call inside the step.  Falls back to the NCCL all-gather when symmetric memory cannot be set up."""
+    _cache = {}
+
+    def __init__(self, group, dev):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        pg = group if group is not None else dist.group.WORLD
+        n = int(_lib.lib().g3d_exchange_buffer_doubles(self.world))
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, pg)
+        self.peer_ptrs_dev = int(self.handle.buffer_ptrs_dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)                      # every buffer is zero before anybody stores into it
+
+    @classmethod
+    def get(cls, group, dev):
+        """the exchange of (group, device), or None if it is disabled (G3D_PEER_EXCHANGE=0) or not available; all ranks
+        take the same branch"""
+        import os
+        key = (id(group), dev.index)
+        if key not in cls._cache:
+            ex, ok = None, 1
+            if os.environ.get("G3D_PEER_EXCHANGE", "1") == "0" or dev.type != "cuda":
+                ok = 0
+            else:
+                try:
+                    ex = cls(group, dev)
+                except Exception:   # noqa: BLE001 - no P2P / no symmetric memory on this system: use NCCL
+                    ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            cls._cache[key] = ex if int(flag.item()) else None
+        return cls._cache[key]
+
+
 class _ShardedFocalLossFn(torch.autograd.Function):
-    """forward: local fused loss (+ gradients for the expected upstream value B_local / B_global = 1 / world) -> all-gather
-    of the 5 shard statistics the kernel wrote -> one tiny kernel forms the global means and this rank's gradient scales.
-    Two extra launches and one collective per step; the backward adds none (it only verifies the scale on the device)."""
+    """forward: local fused loss (+ gradients for the expected upstream value B_local / B_global = 1 / world) -> exchange of
+    the 5 shard statistics the kernel wrote -> global means and this rank's gradient scales.  On one NVLink box the exchange
+    is ONE tiny kernel that stores into the peers' memory (_PeerExchange); otherwise an NCCL all-gather + a combine kernel.
+    The backward adds nothing (it only verifies the scale on the device)."""
 
     @staticmethod
     def forward(ctx, classifications, regressions, anchors, annotations, group, trace_events, hyper):
@@ -61,8 +102,12 @@ class _ShardedFocalLossFn(torch.autograd.Function):
         fwd = ops.focal_loss_forward(classifications, regressions, anchors, annotations, want_assign=False,
                                      grad_expected=(1.0 / world) if needs_grad else None,
                                      trace_events=trace_events, want_shard_stats=True, hyper=hyper)
-        gathered = gather_shard_stats(fwd["shard_stats"], group)
-        losses, scale = ops.combine_shard_stats(gathered, rank)
+        exchange = _PeerExchange.get(group, classifications.device) if world > 1 else None
+        if exchange is not None:       # stores over NVLink into the peers' buffers: one launch, no collective call
+            losses, scale = ops.exchange_shard_stats(fwd["shard_stats"], exchange.peer_ptrs_dev, world, rank)
+        else:
+            gathered = gather_shard_stats(fwd["shard_stats"], group)
+            losses, scale = ops.combine_shard_stats(gathered, rank)
         ctx.fwd, ctx.scale = fwd, scale
         ctx.in_dtypes = (classifications.dtype, regressions.dtype)
         ctx.save_for_backward(classifications, regressions)

@@ -272,6 +272,19 @@ def combine_shard_stats(gathered, rank):
     return losses, scale
 
 
+def exchange_shard_stats(stats, peer_ptrs_dev, world, rank):
+    """stats f64[5] of this rank -> (losses f32[3] global means, scale f32[3]) through the peers' exchange buffers
+    (g3d_exchange_shard_stats: stores over NVLink + epoch flags, no collective call).  peer_ptrs_dev: int, device address of
+    the array of the `world` buffer pointers."""
+    dev = _need_cuda(stats)
+    stats = _prep(stats, torch.float64)
+    losses = torch.empty((3,), dtype=torch.float32, device=dev)
+    scale = torch.empty((3,), dtype=torch.float32, device=dev)
+    check(_lib.lib().g3d_exchange_shard_stats(_p(stats), ctypes.c_void_p(int(peer_ptrs_dev)), int(world), int(rank), _p(losses),
+                                              _p(scale), _idx(dev), _stream(dev)), "g3d_exchange_shard_stats")
+    return losses, scale
+
+
 def focal_loss_backward(fwd, grad_out, grad_scale=None, take=False):
     """Backward of focal_loss_forward.  grad_out f32[3] (device).  Returns (dcls[B,A,C], dreg[B,A,R]).
 

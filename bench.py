@@ -627,7 +627,7 @@ def run_ours(args):
         strong = {"global_batch": B_PER_GPU, "images_per_gpu": Bs, "ms_per_step": ms_s, "ms_per_step_eager": ms_s_eager,
                   "launch_mode": mode_s, "value": B_PER_GPU * A * G_PER_IMG / (ms_s * 1e-3) / 1e9, "unit": UNIT,
                   "note": "same global batch as N = 1: speed-up = ms_per_step(N = 1) / this; the fixed part of a step (six "
-                          "launches of latency-bound work + the 5-scalar all-gather) does not shrink with the shard"}
+                          "launches of latency-bound work + the 5-scalar exchange) does not shrink with the shard"}
         del cs, rs
 
     # ---- end to end through the public module (default constructor), from pinned host buffers
@@ -707,7 +707,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "training-loss path (BASELINE configs[1]): FocalLoss fwd+bwd, 1080p, A=389205, "
                                    "G=200 GT/img, C=8, 12-d regression", "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": f"images sharded over {world} GPU(s), 5-scalar all-gather only",
+                       "parallelism": f"images sharded over {world} GPU(s); only exchange: 5 scalars per rank, stored into the peers' memory over NVLink",
                        "l2": "inputs (1.0 GB/step) exceed the 126 MB L2; no flush needed",
                        "launch_mode": mode, "ms_per_step_eager": ms_step_eager, "ms_per_step_graph": ms_graph},
             "clocks": clocks,

@@ -159,6 +159,18 @@ int g3d_set_tuning(int key, int64_t value);
 int g3d_combine_shard_stats(const double* gathered, int64_t world, int64_t rank, float* losses, float* scale,
                             int device, void* stream);
 
+/* The same reduction without a collective library call, over peer-mapped ("symmetric") memory of the GPUs of one
+ * NVLink / NVSwitch box: every rank owns an exchange buffer of g3d_exchange_buffer_doubles(world) doubles, zero before the
+ * first call, mapped into every peer; peer_ptrs_dev = DEVICE array of `world` pointers, entry r = rank r's buffer as
+ * addressable from this device (torch.distributed._symmetric_memory: rendezvous(...).buffer_ptrs_dev).  One launch of one
+ * warp: stores this rank's shard_stats[5] into every peer's buffer, publishes them (system-scope fence + epoch flag), waits
+ * for the flags of all ranks in its own buffer (bounded: NaN losses after ~3 s instead of a hang) and forms losses[3] /
+ * scale[3] exactly as g3d_combine_shard_stats does (rank-order sums).  Every rank must make the same sequence of calls.
+ */
+int64_t g3d_exchange_buffer_doubles(int64_t world);
+int g3d_exchange_shard_stats(const double* shard_stats, const void* peer_ptrs_dev, int64_t world, int64_t rank,
+                             float* losses, float* scale, int device, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * a7  3D BBoxTransform.forward     pytorch_retinanet_detector_directional/retinanet/utils.py:102-149
  * anchors[A,4] (the reference's boxes[1,A,4]), reg[B,A,12] -> out[B,A,20].  Bit-identical to the eager reference

@@ -36,6 +36,15 @@ errs = [rel(got, full.detach()), rel(cl.grad, cf.grad[lo:hi]), rel(rl.grad, rf.g
 ok = all(e < 1e-5 for e in errs)
 flag = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 print(f"check_dist rank {rank}/{world} shard [{lo},{hi}) errs (losses, dcls, dreg) = {errs}", flush=True)
-if rank == 0: print("check_dist", "OK" if int(flag) else "FAILED", "world", world, [float(x) for x in got.detach()])
+path = "peer-memory exchange" if gdist._PeerExchange.get(None, dev) is not None else "NCCL all-gather"
+# a second and third step through the same exchange buffers (epochs / parities advance), gradients unchanged
+for _ in range(2):
+    cl.grad = None; rl.grad = None
+    again = gdist.sharded_focal_loss(cl, rl, anc, ann[lo:hi].contiguous())
+    (again * w).sum().backward()
+    ok2 = torch.equal(again, got) and rel(cl.grad, cf.grad[lo:hi]) < 1e-5
+    flag2 = torch.tensor([1 if ok2 else 0], device=dev); dist.all_reduce(flag2, op=dist.ReduceOp.MIN)
+    flag = torch.minimum(flag, flag2)
+if rank == 0: print("check_dist", "OK" if int(flag) else "FAILED", "world", world, "via", path, [float(x) for x in got.detach()])
 dist.barrier(); dist.destroy_process_group()
 sys.exit(0 if int(flag) else 1)
