@@ -64,7 +64,7 @@ SIGNATURES = {
     "g3d_exclusive_scan_i32": (_int, [_c_ptr, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_assemble_detections": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _c_ptr, _i64,
                                        _c_ptr, _int, _c_ptr, _c_ptr, _int, _f32, _f32, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
-                                       _int, _c_ptr]),
+                                       _i64, _int, _c_ptr]),
     "g3d_nms_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "g3d_nms_segmented": (_int, [_c_ptr, _i64, _i64, _c_ptr, _i64, _c_ptr, _i64, _i64, _f64, _int, _c_ptr, _c_ptr,
                                  _c_ptr, _i64, _int, _c_ptr]),

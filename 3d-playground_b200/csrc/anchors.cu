@@ -79,7 +79,7 @@ extern "C" int g3d_generate_anchors(const double* shapes_host, const double* str
     G3D_REQUIRE(anchors, "null output");
     G3D_GUARD(device);
     const int64_t blocks = ceil_div(A, 256);
-    generate_anchors_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+    generate_anchors_kernel<<<(unsigned)(blocks < sm_count(device) * 8 ? blocks : sm_count(device) * 8), 256, 0, (cudaStream_t)stream>>>(
         tab, reinterpret_cast<float4*>(anchors));
     G3D_LAUNCH_CHECK();
     return G3D_OK;

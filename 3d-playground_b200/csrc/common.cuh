@@ -9,6 +9,7 @@
 namespace g3d {
 
 void set_error(const char* fmt, ...);
+int sm_count(int device);     // SMs of `device`, queried once per device (148 on B200); grids are sized in multiples of it
 
 struct DeviceGuard {
     int prev = -1;

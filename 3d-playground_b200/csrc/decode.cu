@@ -94,7 +94,7 @@ extern "C" int g3d_decode3d(const float* anchors, const float* reg, int64_t B, i
     // one CTA per anchor tile and image group: anchors are read once per CTA and reused over its images
     const int64_t tiles = ceil_div(A, kDecTile);
     int64_t gy = B;
-    while (gy > 1 && tiles * gy > (int64_t)148 * 14 * 8) gy = (gy + 1) / 2;
+    while (gy > 1 && tiles * gy > (int64_t)sm_count(device) * 14 * 8) gy = (gy + 1) / 2;
     dim3 grid((unsigned)tiles, (unsigned)gy);
     decode3d_kernel<<<grid, kDecTile, 0, (cudaStream_t)stream>>>((const float4*)anchors, (const float4*)reg, (int)B,
                                                                  (int)A, (float4*)out);
@@ -115,7 +115,7 @@ extern "C" int g3d_decode2d(const float* anchors, int64_t Ba, const float* delta
     G3D_GUARD(device);
     const int64_t BA = B * A;
     const int64_t blocks = ceil_div(BA, 256);
-    const int grid = (int)(blocks < (int64_t)148 * 32 ? blocks : (int64_t)148 * 32);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 32 ? blocks : (int64_t)sm_count(device) * 32);
     decode2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const float4*)anchors, (Ba == B && B > 1) ? 1 : 0, (const float4*)deltas, BA, (int)A,
         make_float4(mean_host[0], mean_host[1], mean_host[2], mean_host[3]),
@@ -131,7 +131,7 @@ extern "C" int g3d_clip_boxes(float* boxes, int64_t N, int64_t K, float width, f
     G3D_REQUIRE((K & 3) != 0 || ((uintptr_t)boxes % 16) == 0, "boxes must be 16-byte aligned");
     G3D_GUARD(device);
     const int64_t blocks = ceil_div(N, 256);
-    const int grid = (int)(blocks < (int64_t)148 * 32 ? blocks : (int64_t)148 * 32);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 32 ? blocks : (int64_t)sm_count(device) * 32);
     clip_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, N, (int)K, width, height);
     G3D_LAUNCH_CHECK();
     return G3D_OK;

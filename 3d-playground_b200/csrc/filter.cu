@@ -297,7 +297,7 @@ extern "C" int g3d_rowmax(const float* cls, int64_t rows, int64_t C, float* smax
     G3D_REQUIRE(cls && smax && amax, "null pointer");
     G3D_GUARD(device);
     const int64_t blocks = ceil_div(rows, 256);
-    const int grid = (int)(blocks < (int64_t)148 * 32 ? blocks : (int64_t)148 * 32);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 32 ? blocks : (int64_t)sm_count(device) * 32);
     rowmax_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cls, rows, (int)C, smax, amax);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
@@ -308,9 +308,9 @@ extern "C" int64_t g3d_ladder_workspace_bytes(int64_t S, int64_t L) {
     return align_up(S * (L + 1) * 4, 256) + align_up(L * 4, 256);
 }
 
-static int grid_x_for(int64_t N, int64_t outer) {
+static int grid_x_for(int64_t N, int64_t outer, int device) {
     int64_t gx = ceil_div(N, 256);
-    const int64_t want = ceil_div((int64_t)148 * 8, outer > 0 ? outer : 1);
+    const int64_t want = ceil_div((int64_t)sm_count(device) * 8, outer > 0 ? outer : 1);
     if (gx > want) gx = want;
     return (int)(gx < 1 ? 1 : gx);
 }
@@ -343,7 +343,7 @@ extern "C" int g3d_threshold_ladder(const float* scores, int64_t outer, int64_t 
     float step = last > 0 ? (log2f(thresholds_host[last]) - log2_t0) / (float)last : 1.0f;
     if (!(step > 1e-6f)) step = 1.0f;
     if (N > 0) {
-        dim3 grid((unsigned)grid_x_for(N, outer), (unsigned)outer);
+        dim3 grid((unsigned)grid_x_for(N, outer, device), (unsigned)outer);
         const size_t smem = (size_t)(L + inner * (L + 1)) * 4;
         if (inner == 8) {
             G3D_CUDA(cudaFuncSetAttribute(ladder_hist_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -372,7 +372,7 @@ extern "C" int g3d_filter_compact(const float* scores, int64_t outer, int64_t in
     cudaStream_t st = (cudaStream_t)stream;
     G3D_CUDA(cudaMemsetAsync(count_out, 0, outer * inner * 4, st));
     if (N == 0) return G3D_OK;
-    dim3 grid((unsigned)grid_x_for(N, outer), (unsigned)outer);
+    dim3 grid((unsigned)grid_x_for(N, outer, device), (unsigned)outer);
     if (inner == 8)
         compact8_kernel<<<grid, 256, 0, st>>>(scores, N, outer_pitch, thr, (int)cap, idx_out, count_out);
     else
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(128) assemble_detections_kernel(const int64_t*
                                                                   const BoxDecode dec, float* __restrict__ out_scores,
                                                                   int64_t* __restrict__ out_classes,
                                                                   float* __restrict__ out_boxes,
-                                                                  int64_t* __restrict__ out_image) {
+                                                                  int64_t* __restrict__ out_image, int64_t capacity) {
     const int s = blockIdx.x;
     const int n = keep_count[s];
     const int64_t in0 = seg_offsets[s], out0 = out_offsets[s];
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(128) assemble_detections_kernel(const int64_t*
         const int64_t pos = keep[in0 + k];
         const int64_t e = cand_src[pos];
         const int64_t row = out0 + k;
+        if (row >= capacity) break;            // speculative output buffers: the caller re-runs with the exact size
         out_scores[row] = cand_scores[pos];
         out_classes[row] = c;
         out_image[row] = o;
@@ -507,8 +508,8 @@ extern "C" int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_
                                        int64_t outer, int64_t inner, int64_t N, const float* anchors, int64_t Ba,
                                        const float* reg, int variant, const float* mean_host, const float* std_host,
                                        int clip, float clip_w, float clip_h, float* out_scores, int64_t* out_classes,
-                                       float* out_boxes, int64_t* out_image, int device, void* stream) {
-    G3D_REQUIRE(outer >= 1 && inner >= 1 && N >= 0 && outer * inner < ((int64_t)1 << 24), "bad size");
+                                       float* out_boxes, int64_t* out_image, int64_t capacity, int device, void* stream) {
+    G3D_REQUIRE(outer >= 1 && inner >= 1 && N >= 0 && outer * inner < ((int64_t)1 << 24) && capacity >= 0, "bad size");
     G3D_REQUIRE(keep_count && seg_offsets && out_offsets, "null pointer");
     BoxDecode d;
     int rc = make_box_decode(d, anchors, Ba, outer, reg, variant, mean_host, std_host, clip, clip_w, clip_h);
@@ -517,7 +518,7 @@ extern "C" int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_
     G3D_GUARD(device);
     assemble_detections_kernel<<<(unsigned)(outer * inner), 128, 0, (cudaStream_t)stream>>>(
         keep, keep_count, seg_offsets, out_offsets, cand_scores, cand_src, (int)inner, N, d, out_scores, out_classes,
-        out_boxes, out_image);
+        out_boxes, out_image, capacity);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

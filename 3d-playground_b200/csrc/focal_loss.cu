@@ -1445,8 +1445,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
                 "cls/dcls must be 32-byte, reg/dreg/anchors/per_image 16-byte and the workspace 256-byte aligned");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
-    int sms = 148;
-    G3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int sms = sm_count(device);
     const bool grad = dcls != nullptr;
     int32_t* npos = ws_npos(w, B);
     auto trace = [&](int i) -> cudaError_t {
@@ -1585,8 +1584,7 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     G3D_REQUIRE(workspace_bytes >= w.bytes, "workspace too small (pass the forward's workspace, untouched)");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
-    int sms = 148;
-    G3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int sms = sm_count(device);
     Pyramid pyr;
     const bool gt_centric = use_gt_centric(pyramid_host, A, C, Gmax, h, pyr);    // the decision the forward took
     ClsGradArgs p;

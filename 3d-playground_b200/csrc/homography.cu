@@ -412,9 +412,9 @@ __global__ void __launch_bounds__(256) corners_to_box_kernel(const T* __restrict
     }
 }
 
-static inline int grid_for(int64_t n) {
+static inline int grid_for(int64_t n, int device) {
     const int64_t b = ceil_div(n, 256);
-    const int64_t cap = (int64_t)148 * 16;
+    const int64_t cap = (int64_t)sm_count(device) * 16;
     return (int)(b < 1 ? 1 : (b < cap ? b : cap));
 }
 static int check_cams(int64_t ncam, const void* cam, int cam_const) {
@@ -432,7 +432,7 @@ extern "C" int g3d_state_to_space(const float* states, int64_t d, int64_t S, flo
     if (d == 0) return G3D_OK;
     G3D_REQUIRE(states && out, "null pointer");
     G3D_GUARD(device);
-    state_to_space_kernel<<<grid_for(d * 8), 256, 0, (cudaStream_t)stream>>>(states, d, S, out);
+    state_to_space_kernel<<<grid_for(d * 8, device), 256, 0, (cudaStream_t)stream>>>(states, d, S, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }
@@ -449,11 +449,11 @@ extern "C" int g3d_space_to_im(const void* pts, int pts_is_f64, int64_t d, int64
     const size_t smem = (size_t)ncam * 24 * 8;
     if (pts_is_f64) {
         G3D_CUDA(cudaFuncSetAttribute(space_to_im_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        space_to_im_kernel<double><<<grid_for(d * m), 256, smem, (cudaStream_t)stream>>>(
+        space_to_im_kernel<double><<<grid_for(d * m, device), 256, smem, (cudaStream_t)stream>>>(
             (const double*)pts, d, (int)m, P, (int)ncam, cam, cam_const, wrapper, (double2*)out);
     } else {
         G3D_CUDA(cudaFuncSetAttribute(space_to_im_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        space_to_im_kernel<float><<<grid_for(d * m), 256, smem, (cudaStream_t)stream>>>(
+        space_to_im_kernel<float><<<grid_for(d * m, device), 256, smem, (cudaStream_t)stream>>>(
             (const float*)pts, d, (int)m, P, (int)ncam, cam, cam_const, wrapper, (double2*)out);
     }
     G3D_LAUNCH_CHECK();
@@ -478,7 +478,7 @@ extern "C" int g3d_state_to_im(const float* states, int64_t d, int64_t S, const 
         const size_t smem = mat_bytes + sizeof(OUT2) * 8 * kS2IThreads;                                                \
         G3D_CUDA(cudaFuncSetAttribute(state_to_im_kernel<OUT2, ALLC>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                       (int)smem));                                                                     \
-        state_to_im_kernel<OUT2, ALLC><<<grid_for(items), kS2IThreads, smem, st>>>(states, d, S, P, (int)ncam, cam,    \
+        state_to_im_kernel<OUT2, ALLC><<<grid_for(items, device), kS2IThreads, smem, st>>>(states, d, S, P, (int)ncam, cam,    \
                                                                                    cam_const, wrapper, (OUT2*)out);    \
     } while (0)
     if (out_f32) {
@@ -502,10 +502,10 @@ extern "C" int g3d_im_to_space(const void* pts, const void* heights, int in_is_f
     G3D_GUARD(device);
     const size_t smem = (size_t)ncam * 18 * 8;
     if (in_is_f64)
-        im_to_space_kernel<double><<<grid_for(d * 8), 256, smem, (cudaStream_t)stream>>>(
+        im_to_space_kernel<double><<<grid_for(d * 8, device), 256, smem, (cudaStream_t)stream>>>(
             (const double*)pts, (const double*)heights, d, H, (int)ncam, cam, cam_const, wrapper, out);
     else
-        im_to_space_kernel<float><<<grid_for(d * 8), 256, smem, (cudaStream_t)stream>>>(
+        im_to_space_kernel<float><<<grid_for(d * 8, device), 256, smem, (cudaStream_t)stream>>>(
             (const float*)pts, (const float*)heights, d, H, (int)ncam, cam, cam_const, wrapper, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
@@ -517,9 +517,9 @@ extern "C" int g3d_space_to_state(const void* pts, int pts_is_f64, int64_t d, fl
     G3D_REQUIRE(pts && out, "null pointer");
     G3D_GUARD(device);
     if (pts_is_f64)
-        space_to_state_kernel<double><<<grid_for(d), 256, 0, (cudaStream_t)stream>>>((const double*)pts, d, out);
+        space_to_state_kernel<double><<<grid_for(d, device), 256, 0, (cudaStream_t)stream>>>((const double*)pts, d, out);
     else
-        space_to_state_kernel<float><<<grid_for(d), 256, 0, (cudaStream_t)stream>>>((const float*)pts, d, out);
+        space_to_state_kernel<float><<<grid_for(d, device), 256, 0, (cudaStream_t)stream>>>((const float*)pts, d, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }
@@ -537,10 +537,10 @@ extern "C" int g3d_im_to_state(const void* pts, const void* heights, int in_is_f
     const size_t smem = (size_t)ncam * 18 * 8;
     G3D_REQUIRE(((uintptr_t)pts % 16) == 0, "pts must be 16-byte aligned");
     if (in_is_f64)
-        im_to_state_kernel<double><<<grid_for(d * 4), 256, smem, (cudaStream_t)stream>>>(
+        im_to_state_kernel<double><<<grid_for(d * 4, device), 256, smem, (cudaStream_t)stream>>>(
             (const double*)pts, (const double*)heights, d, H, (int)ncam, cam, cam_const, wrapper, out);
     else
-        im_to_state_kernel<float><<<grid_for(d * 4), 256, smem, (cudaStream_t)stream>>>(
+        im_to_state_kernel<float><<<grid_for(d * 4, device), 256, smem, (cudaStream_t)stream>>>(
             (const float*)pts, (const float*)heights, d, H, (int)ncam, cam, cam_const, wrapper, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
@@ -553,7 +553,7 @@ extern "C" int g3d_height_from_template(const void* tb, int tb_is_f64, const voi
     G3D_REQUIRE(tb && th && bx && out, "null pointer");
     G3D_GUARD(device);
     cudaStream_t st = (cudaStream_t)stream;
-    const int g = grid_for(d);
+    const int g = grid_for(d, device);
     const int key = (tb_is_f64 ? 4 : 0) | (th_is_f64 ? 2 : 0) | (bx_is_f64 ? 1 : 0);
 #define HFT(TB, TH, BX, OUT) \
     height_from_template_kernel<TB, TH, BX, OUT><<<g, 256, 0, st>>>((const TB*)tb, (const TH*)th, (const BX*)bx, d, (OUT*)out)
@@ -585,11 +585,11 @@ extern "C" int g3d_im_to_state_refined(const void* pts, const void* heights, int
     const size_t smem = (size_t)ncam * 42 * 8;
     if (in_is_f64) {
         G3D_CUDA(cudaFuncSetAttribute(im_to_state_refined_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        im_to_state_refined_kernel<double><<<grid_for(d), 256, smem, (cudaStream_t)stream>>>(
+        im_to_state_refined_kernel<double><<<grid_for(d, device), 256, smem, (cudaStream_t)stream>>>(
             (const double*)pts, (const double*)heights, d, H, P, (int)ncam, cam, cam_const, wrapper, out, heights_out);
     } else {
         G3D_CUDA(cudaFuncSetAttribute(im_to_state_refined_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        im_to_state_refined_kernel<float><<<grid_for(d), 256, smem, (cudaStream_t)stream>>>(
+        im_to_state_refined_kernel<float><<<grid_for(d, device), 256, smem, (cudaStream_t)stream>>>(
             (const float*)pts, (const float*)heights, d, H, P, (int)ncam, cam, cam_const, wrapper, out, heights_out);
     }
     G3D_LAUNCH_CHECK();
@@ -602,7 +602,7 @@ extern "C" int g3d_state_footprint(const float* states, int64_t d, int64_t S, fl
     G3D_REQUIRE(states && out, "null pointer");
     G3D_REQUIRE(((uintptr_t)out % 16) == 0, "out must be 16-byte aligned");
     G3D_GUARD(device);
-    state_footprint_kernel<<<grid_for(d), 256, 0, (cudaStream_t)stream>>>(states, d, S, (float4*)out);
+    state_footprint_kernel<<<grid_for(d, device), 256, 0, (cudaStream_t)stream>>>(states, d, S, (float4*)out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }
@@ -613,9 +613,9 @@ extern "C" int g3d_corners_to_box(const void* pts, int is_f64, int64_t d, void* 
     G3D_REQUIRE(pts && out, "null pointer");
     G3D_GUARD(device);
     if (is_f64)
-        corners_to_box_kernel<double><<<grid_for(d), 256, 0, (cudaStream_t)stream>>>((const double*)pts, d, (double*)out);
+        corners_to_box_kernel<double><<<grid_for(d, device), 256, 0, (cudaStream_t)stream>>>((const double*)pts, d, (double*)out);
     else
-        corners_to_box_kernel<float><<<grid_for(d), 256, 0, (cudaStream_t)stream>>>((const float*)pts, d, (float*)out);
+        corners_to_box_kernel<float><<<grid_for(d, device), 256, 0, (cudaStream_t)stream>>>((const float*)pts, d, (float*)out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;
 }

@@ -124,7 +124,7 @@ extern "C" int g3d_calc_iou(const float* a, int64_t A, const float* b, int64_t G
     G3D_GUARD(device);
     const int64_t total = A * G;
     const int64_t blocks = ceil_div(total, 256);
-    const int grid = (int)(blocks < (int64_t)148 * 64 ? blocks : (int64_t)148 * 64);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 64 ? blocks : (int64_t)sm_count(device) * 64);
     calc_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)a, A, (const float4*)b, G, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;

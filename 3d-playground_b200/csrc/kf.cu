@@ -114,6 +114,47 @@ __global__ void __launch_bounds__(128) kf_predict_kernel(float* __restrict__ X, 
     }
 }
 
+// predict for S == 6 and F = identity apart from F[0][5] (every filter of the reference: kf.py:58,315), written out: the
+// products of the general kernel with the exact 0 / 1 entries are exact and adding +0 changes nothing, so
+//   x0 += f x5;   row 0 of P += f * row 5;   then column 0 of P += f * column 5;   P += Q * dt / dt_default
+// gives the same floats for finite inputs - in place, with 36 + a few live registers instead of three 6 x 6 matrices,
+// hence twice the CTAs per SM for this latency-bound, 364-bytes-per-object kernel.
+__global__ void __launch_bounds__(128, 6) kf_predict_fid6_kernel(float* __restrict__ X, float* __restrict__ P,
+                                                                 const float* __restrict__ D, const double* __restrict__ dt_arr,
+                                                                 double dt_scalar, double dt_default, double* __restrict__ T,
+                                                                 int64_t n, const KfModel m) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double dt = dt_arr ? dt_arr[i] : dt_scalar;
+        const double dt_over_default = dt / dt_default;
+        const float f = (float)((double)D[i] * dt);                  // kf.py:315
+        float p[36];
+        float4* prow = reinterpret_cast<float4*>(P + i * 36);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const float4 v = prow[q];
+            p[4 * q] = v.x; p[4 * q + 1] = v.y; p[4 * q + 2] = v.z; p[4 * q + 3] = v.w;
+        }
+        float2* xrow = reinterpret_cast<float2*>(X + i * 6);
+        const float2 x01 = xrow[0], x45 = xrow[2];
+        xrow[0] = make_float2(__fadd_rn(x01.x, __fmul_rn(f, x45.y)), x01.y);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) p[c] = __fadd_rn(p[c], __fmul_rn(f, p[30 + c]));          // A = F P: row 0
+#pragma unroll
+        for (int r = 0; r < 6; ++r) p[6 * r] = __fadd_rn(p[6 * r], __fmul_rn(p[6 * r + 5], f)); // A F^T: column 0
+#pragma unroll
+        for (int e = 0; e < 36; ++e) {
+            if (dt_arr) {   // float * double tensor / python float: the scaling and the sum in double, then .float()
+                p[e] = (float)((double)p[e] + (double)m.Q[e] * dt_over_default);
+            } else {        // float tensor * python scalar: FP32 with the scalar rounded to FP32
+                p[e] = __fadd_rn(p[e], __fdiv_rn(__fmul_rn(m.Q[e], (float)dt), (float)dt_default));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) prow[q] = make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+        if (T) T[i] += dt;
+    }
+}
+
 // update (kf.py:339-403) of the objects rows[j]:  y = z + mu_R - H x;  S = H P H^T + R;  K = P H^T S^-1;
 // x += K y;  P = (I - K H) P
 // HSEL: H = [I_M | 0] (the measurement is the first M states - every tracker configuration of the reference): H P, P H^T and
@@ -126,8 +167,7 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
     const int SS = (S > 0) ? S : s_rt, MM = (M > 0) ? M : m_rt;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < mcount; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = rows[j];
-        float Pm[kKfMax][kKfMax], x[kKfMax], HP[kKfMax][kKfMax], Sm[kKfMax][kKfMax], Si[kKfMax][kKfMax];
-        float PHt[kKfMax][kKfMax], K[kKfMax][kKfMax], y[kKfMax];
+        float Pm[kKfMax][kKfMax], x[kKfMax], HP[kKfMax][kKfMax], Sm[kKfMax][kKfMax], Si[kKfMax][kKfMax], y[kKfMax];
         if (S == 6) {   // 144-byte rows: nine 16-byte loads per object instead of 36 scalar ones
             const float4* prow = reinterpret_cast<const float4*>(P + i * 36);
 #pragma unroll
@@ -201,13 +241,15 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
 #pragma unroll
             for (int r = 0; r < kKfMax; ++r)
                 if (r > col && r < MM && fabsf(Sm[r][col]) > best) { best = fabsf(Sm[r][col]); piv = r; }
+            if (piv != col) {      // rare for an innovation covariance (diagonally dominant): a real branch, not 5 predicated swaps
 #pragma unroll
-            for (int r = 0; r < kKfMax; ++r) {
-                if (r != piv || r == col) continue;
+                for (int r = 0; r < kKfMax; ++r) {
+                    if (r != piv || r == col) continue;
 #pragma unroll
-                for (int c = 0; c < kKfMax; ++c) {
-                    const float t = Sm[col][c]; Sm[col][c] = Sm[r][c]; Sm[r][c] = t;
-                    const float u = Si[col][c]; Si[col][c] = Si[r][c]; Si[r][c] = u;
+                    for (int c = 0; c < kKfMax; ++c) {
+                        const float t = Sm[col][c]; Sm[col][c] = Sm[r][c]; Sm[r][c] = t;
+                        const float u = Si[col][c]; Si[col][c] = Si[r][c]; Si[r][c] = u;
+                    }
                 }
             }
             const float inv = 1.0f / Sm[col][col];
@@ -224,52 +266,46 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
                 }
             }
         }
-        // PHt = P H^T [S,M];  K = PHt S^-1 [S,M]
+        // Row by row (a full K and a full copy of the new P would cost 60 + 36 more live registers - the difference between
+        // four and six CTAs per SM for this latency-bound kernel):  PHt_r = P_r H^T;  K_r = PHt_r S^-1;  x_r += K_r y;
+        // P_r <- ((I - K H) P)_r.  Every new row is formed from the ORIGINAL matrix (Pm), as the reference's bmm does.
 #pragma unroll
-        for (int r = 0; r < kKfMax; ++r)
+        for (int r = 0; r < kKfMax; ++r) {
+            if (r >= SS) continue;
+            float PHt[kKfMax], K[kKfMax], IKH[kKfMax], Pn[kKfMax];
 #pragma unroll
             for (int a = 0; a < kKfMax; ++a) {
-                if (r >= SS || a >= MM) continue;
+                if (a >= MM) continue;
                 float acc = 0.0f;
                 if (HSEL) acc = Pm[r][a];
                 else {
 #pragma unroll
                     for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(Pm[r][k], mdl.H[a * SS + k]));
                 }
-                PHt[r][a] = acc;
+                PHt[a] = acc;
             }
-#pragma unroll
-        for (int r = 0; r < kKfMax; ++r)
 #pragma unroll
             for (int a = 0; a < kKfMax; ++a) {
-                if (r >= SS || a >= MM) continue;
+                if (a >= MM) continue;
                 float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(PHt[r][k], Si[k][a]));
-                K[r][a] = acc;
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(PHt[k], Si[k][a]));
+                K[a] = acc;
             }
-        // x += K y
+            {   // x += K y
+                float acc = 0.0f;
 #pragma unroll
-        for (int r = 0; r < kKfMax; ++r) {
-            if (r >= SS) continue;
-            float acc = 0.0f;
-#pragma unroll
-            for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[r][k], y[k]));
-            X[i * SS + r] = __fadd_rn(x[r], acc);
-        }
-        // P = (I - K H) P, stored row by row (a full copy of the new matrix would cost 36 more live registers)
-#pragma unroll
-        for (int r = 0; r < kKfMax; ++r) {
-            if (r >= SS) continue;
-            float IKH[kKfMax], Pn[kKfMax];
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[k], y[k]));
+                X[i * SS + r] = __fadd_rn(x[r], acc);
+            }
 #pragma unroll
             for (int c = 0; c < kKfMax; ++c) {
                 if (c >= SS) continue;
                 float acc = 0.0f;
-                if (HSEL) acc = (c < MM) ? K[r][c < kKfMax ? c : 0] : 0.0f;
+                if (HSEL) acc = (c < MM) ? K[c < kKfMax ? c : 0] : 0.0f;
                 else {
 #pragma unroll
-                    for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[r][k], mdl.H[k * SS + c]));
+                    for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[k], mdl.H[k * SS + c]));
                 }
                 IKH[c] = __fsub_rn((r == c) ? 1.0f : 0.0f, acc);
             }
@@ -322,8 +358,15 @@ extern "C" int g3d_kf_predict(float* X, float* P, const float* D, const double* 
     G3D_GUARD(device);
     KfModel m;
     fill_model(m, F_host, Q_host, nullptr, nullptr, nullptr, (int)S, 0);
-    const int grid = (int)(ceil_div(n, 128) < 148 * 8 ? ceil_div(n, 128) : 148 * 8);
-    if (S == 6)
+    const int sms = sm_count(device);
+    const int grid = (int)(ceil_div(n, 128) < (int64_t)sms * 16 ? ceil_div(n, 128) : (int64_t)sms * 16);
+    bool fid = S == 6;                       // F == identity apart from [0][5] (which the kernel overwrites with D * dt)?
+    for (int64_t r = 0; r < S && fid; ++r)
+        for (int64_t c = 0; c < S; ++c)
+            if (!(r == 0 && c == 5) && F_host[r * S + c] != ((r == c) ? 1.0f : 0.0f)) { fid = false; break; }
+    if (fid && ((uintptr_t)X % 8) == 0)
+        kf_predict_fid6_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, D, dt_per_object, dt_scalar, dt_default, T, n, m);
+    else if (S == 6)
         kf_predict_kernel<6><<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, D, dt_per_object, dt_scalar, dt_default, T, n, 6, m);
     else
         kf_predict_kernel<0><<<grid, 128, 0, (cudaStream_t)stream>>>(X, P, D, dt_per_object, dt_scalar, dt_default, T, n,
@@ -341,7 +384,8 @@ extern "C" int g3d_kf_update(float* X, float* P, const int64_t* rows, const doub
     G3D_GUARD(device);
     KfModel m;
     fill_model(m, nullptr, nullptr, H_host, R_host, mu_R_host, (int)S, (int)M);
-    const int grid = (int)(ceil_div(m_count, 128) < 148 * 8 ? ceil_div(m_count, 128) : 148 * 8);
+    const int sms = sm_count(device);
+    const int grid = (int)(ceil_div(m_count, 128) < (int64_t)sms * 8 ? ceil_div(m_count, 128) : (int64_t)sms * 8);
     bool hsel = M <= S;                      // H == [I_M | 0] exactly?
     for (int64_t a = 0; a < M && hsel; ++a)
         for (int64_t k = 0; k < S; ++k)

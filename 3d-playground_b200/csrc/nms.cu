@@ -657,7 +657,7 @@ extern "C" int g3d_nms_segmented(const float* boxes, int64_t box_stride, int64_t
         while (P < max_seg_len) P <<= 1;
         G3D_REQUIRE(P < ((int64_t)1 << 31), "segment too long");
         const int n = (int)N;  // S == 1: the single segment is [0, N)
-        const int g256 = (int)(ceil_div(P, 256) < 148 * 16 ? ceil_div(P, 256) : 148 * 16);
+        const int g256 = (int)(ceil_div(P, 256) < sm_count(device) * 16 ? ceil_div(P, 256) : sm_count(device) * 16);
         keys_init_kernel<<<g256, 256, 0, st>>>(scores, n, (int)P, w.keys);
         G3D_LAUNCH_CHECK();
         bitonic_local_kernel<<<(unsigned)(P / kLocalSort), kNmsThreads, 0, st>>>(w.keys, 0, 1);

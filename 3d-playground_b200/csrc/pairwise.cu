@@ -94,7 +94,7 @@ extern "C" int g3d_cross_camera_pairs(const float* boxes, const int32_t* cams, i
                 "pass row_count (count pass) or row_offsets + pairs (write pass)");
     G3D_GUARD(device);
     const int64_t blocks = ceil_div(d, 8);       // 8 warps per CTA, one row per warp
-    const int grid = (int)(blocks < (int64_t)148 * 8 ? blocks : (int64_t)148 * 8);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 8 ? blocks : (int64_t)sm_count(device) * 8);
     if (row_offsets)
         cross_camera_pairs_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
             (const float4*)boxes, cams, (int)d, threshold, nullptr, row_offsets, (int2*)pairs, capacity);
@@ -113,7 +113,7 @@ extern "C" int g3d_pairwise_iou_f64(const float* first, int64_t n, const float* 
     G3D_REQUIRE(((uintptr_t)first % 16) == 0 && ((uintptr_t)second % 16) == 0, "boxes must be 16-byte aligned");
     G3D_GUARD(device);
     const int64_t blocks = ceil_div(n * m, 256);
-    const int grid = (int)(blocks < (int64_t)148 * 16 ? blocks : (int64_t)148 * 16);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 16 ? blocks : (int64_t)sm_count(device) * 16);
     pairwise_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)first, n, (const float4*)second, m, eps,
                                                                 one_minus, out);
     G3D_LAUNCH_CHECK();
@@ -126,7 +126,7 @@ extern "C" int g3d_md_iou(const double* a, const double* b, int64_t n, double* o
     G3D_REQUIRE(a && b && out, "null pointer");
     G3D_GUARD(device);
     const int64_t blocks = ceil_div(n, 256);
-    const int grid = (int)(blocks < (int64_t)148 * 16 ? blocks : (int64_t)148 * 16);
+    const int grid = (int)(blocks < (int64_t)sm_count(device) * 16 ? blocks : (int64_t)sm_count(device) * 16);
     md_iou_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
     G3D_LAUNCH_CHECK();
     return G3D_OK;

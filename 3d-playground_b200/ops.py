@@ -532,7 +532,8 @@ def assemble_detections(keep, keep_count, seg_offsets, cand_scores, cand_src, ou
                         mean=None, std=None, clip_wh=None, out_offsets=None, K=None):
     """Final (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K]) from the per-segment keep lists of
     nms_segmented(relative=False): one scan, ONE 4-byte device->host read (K), one assembly launch.  A caller that
-    pipelines several batches passes out_offsets (detection_offsets) and K once it has read it."""
+    pipelines several batches passes out_offsets (detection_offsets) and K once it has read it; K may also be an estimate
+    made BEFORE the count is known - rows beyond it are simply not written (the caller checks and repeats if short)."""
     dev = _need_cuda(keep, keep_count, seg_offsets, cand_scores, cand_src, anchors, regression)
     anc, reg, variant, mean_h, std_h, clip, cw, ch = _decode_args(anchors, regression, mean, std, clip_wh)
     S = outer * inner
@@ -549,7 +550,7 @@ def assemble_detections(keep, keep_count, seg_offsets, cand_scores, cand_src, ou
     if K:
         check(L.g3d_assemble_detections(_p(keep), _p(keep_count), _p(seg_offsets), _p(out_offsets), _p(cand_scores),
                                         _p(cand_src), outer, inner, N, _p(anc), anc.shape[0], _p(reg), variant, mean_h,
-                                        std_h, clip, cw, ch, _p(scores), _p(classes), _p(boxes), _p(image), _idx(dev),
+                                        std_h, clip, cw, ch, _p(scores), _p(classes), _p(boxes), _p(image), K, _idx(dev),
                                         _stream(dev)), "g3d_assemble_detections")
     return scores, classes, boxes, image
 

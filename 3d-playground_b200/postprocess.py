@@ -146,11 +146,15 @@ def detect_per_class(classification, boxes, box_col=0, score_threshold=None, lad
 
 
 _TAIL_HOST = {}
+_TAIL_ROWS = {}        # (device, segments) -> rows the speculative output buffers get (grows with what was seen)
 
 
-def _tail_launch(cls, regression, anchors, score_threshold, ladder_start, keep_max, iou_threshold, cap, mean, std, clip_wh):
-    """everything of the detection tail that needs no host decision, on the current stream; the two integers the host
-    needs (number of detections, largest candidate count) go to pinned memory behind an event"""
+def _tail_run(cls, regression, anchors, score_threshold, ladder_start, keep_max, iou_threshold, cap, mean, std, clip_wh):
+    """The detection tail with ONE host synchronisation, at the very end.  Everything that needs no host decision is one
+    library call (g3d_detect_tail); the assembly launch follows immediately into output buffers sized from an estimate
+    (twice the largest result seen for this shape), so the GPU does not idle while the host learns the number of
+    detections; only then the two integers the host needs (detections, largest candidate count) are read, through pinned
+    memory.  A result larger than the estimate is assembled again at its exact size."""
     dev = cls.device
     B, A, C = cls.shape
     if ladder_start is not None:
@@ -158,6 +162,13 @@ def _tail_launch(cls, regression, anchors, score_threshold, ladder_start, keep_m
     else:
         thr = torch.full((B * C,), float(np.float32(score_threshold)), dtype=torch.float32, device=dev)
     t = ops.detect_tail(cls, B, C, A, A * C, thr, cap, anchors, regression, iou_threshold, mean, std, clip_wh)
+    rows_key = (dev.index, B * C)
+    guess = _TAIL_ROWS.get(rows_key, 4096 * B)
+
+    def assemble(rows):
+        return ops.assemble_detections(t["keep"], t["keep_count"], t["seg_offsets"], t["cand_scores"], t["cand_src"], B, C, A,
+                                       anchors, regression, mean, std, clip_wh, out_offsets=t["out_offsets"], K=rows)
+    out = assemble(guess)
     stream = torch.cuda.current_stream(dev)
     key = (dev.index, stream.cuda_stream)
     if key not in _TAIL_HOST:                                # one pinned pair + event per stream, reused (each call
@@ -165,19 +176,15 @@ def _tail_launch(cls, regression, anchors, score_threshold, ladder_start, keep_m
     host, done = _TAIL_HOST[key]
     host.copy_(t["summary"], non_blocking=True)
     done.record(stream)
-    t.update(B=B, A=A, C=C, regression=regression, host=host, done=done, cap=cap)
-    return t
-
-
-def _tail_finish(st, anchors, mean, std, clip_wh):
-    st["done"].synchronize()
-    K, most = int(st["host"][0]), int(st["host"][1])
-    if most > st["cap"]:
+    done.synchronize()
+    K, most = int(host[0]), int(host[1])
+    if most > cap:
         raise Geom3dError(f"a (image, class) segment has {most} candidates above the score threshold but the candidate "
-                          f"capacity is {st['cap']}; pass a larger `cap` (<= 16384) or raise the threshold")
-    return ops.assemble_detections(st["keep"], st["keep_count"], st["seg_offsets"], st["cand_scores"], st["cand_src"],
-                                   st["B"], st["C"], st["A"], anchors, st["regression"], mean, std, clip_wh,
-                                   out_offsets=st["out_offsets"], K=K)
+                          f"capacity is {cap}; pass a larger `cap` (<= 16384) or raise the threshold")
+    _TAIL_ROWS[rows_key] = max(guess, 2 * K)
+    if K > guess:
+        out = assemble(K)
+    return tuple(x[:K] for x in out)
 
 
 def detect_per_class_fused(classification, regression, anchors, score_threshold=None, ladder_start=None, keep_max=KEEP_MAX,
@@ -185,9 +192,9 @@ def detect_per_class_fused(classification, regression, anchors, score_threshold=
     """detect_per_class without the decoded tensor: the score filter runs first, only the candidates' NMS
     boxes and the kept rows are decoded - from regression[B,A,12] (3D directional model: NMS on columns 16..19, 20-column
     rows out) or regression[B,A,4] (2D model: mean / std / optional clip as BBoxTransform + ClipBoxes).
-    Same result, bit for bit, as decode -> detect_per_class.  Everything up to the one host decision (how many rows to
-    allocate) is ONE library call (g3d_detect_tail: ~10 launches issued from C++), then one 8-byte device->host read
-    and the assembly launch.  (Pipelining half-batches on two streams was tried: the sort / NMS chain is latency-bound per
+    Same result, bit for bit, as decode -> detect_per_class.  Everything up to the assembly is ONE library call
+    (g3d_detect_tail: ~10 launches issued from C++); the assembly launch follows at once into buffers sized from an
+    estimate, and the single 8-byte device->host read comes last (_tail_run).  (Pipelining half-batches on two streams was tried: the sort / NMS chain is latency-bound per
     segment, so halves take as long as the whole and the pipeline only adds host time - 0.66 ms vs 0.46 ms at B = 64.)
     Returns (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K])."""
     if (score_threshold is None) == (ladder_start is None):
@@ -198,8 +205,7 @@ def detect_per_class_fused(classification, regression, anchors, score_threshold=
     if cap is None:
         cap = min(keep_max, 16384) if ladder_start is not None else 16384
     cap = int(min(cap, max(A, 1)))
-    st = _tail_launch(cls, reg, anchors, score_threshold, ladder_start, keep_max, iou_threshold, cap, mean, std, clip_wh)
-    return _tail_finish(st, anchors, mean, std, clip_wh)
+    return _tail_run(cls, reg, anchors, score_threshold, ladder_start, keep_max, iou_threshold, cap, mean, std, clip_wh)
 
 
 def detect_multi_frame(classification, boxes, box_col=16, ladder_start=LADDER_START_MULTI, keep_max=KEEP_MAX,

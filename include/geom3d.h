@@ -242,7 +242,8 @@ int g3d_gather_candidates(const float* scores, int64_t outer, int64_t inner, int
  * g3d_assemble_detections: rows out_offsets[s] ... of out_scores[K], out_classes[K] (int64), out_image[K] (int64) and
  *   out_boxes[K,20|4] from the keep lists of g3d_nms_segmented(relative = 0): segment s = o*inner + c contributes its
  *   keep_count[s] kept candidates in NMS order (descending score) - image-major, then class, as the reference
- *   concatenates them.
+ *   concatenates them.  `capacity` = rows the four output arrays hold: rows beyond it are not written (a caller may
+ *   launch into buffers sized from an estimate before it has read the number of detections, and repeat if it was short).
  */
 int g3d_gather_candidates_decoded(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
                                   const float* anchors, int64_t Ba, const float* reg, int variant,
@@ -268,7 +269,7 @@ int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_count, cons
                             int64_t outer, int64_t inner, int64_t N, const float* anchors, int64_t Ba,
                             const float* reg, int variant, const float* mean_host, const float* std_host,
                             int clip, float clip_w, float clip_h, float* out_scores, int64_t* out_classes,
-                            float* out_boxes, int64_t* out_image, int device, void* stream);
+                            float* out_boxes, int64_t* out_image, int64_t capacity, int device, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * a11 NMS       torchvision.ops.nms as called at retinanet/model.py:297, 3D model.py:383 (and :336 through
