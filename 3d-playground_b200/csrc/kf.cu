@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
         }
         // Row by row (a full K and a full copy of the new P would cost 60 + 36 more live registers - the difference between
         // four and six CTAs per SM for this latency-bound kernel):  PHt_r = P_r H^T;  K_r = PHt_r S^-1;  x_r += K_r y;
-        // P_r <- ((I - K H) P)_r.  Every new row is formed from the ORIGINAL matrix (Pm), as the reference's bmm does.
+        // P_r <- ((I - K H) P)_r.  Every new row is formed from the ORIGINAL matrix (Pm), as the reference's bmm does; the
+        // dot products accumulate with FMA in index order (what the reference's CPU GEMM does too: parity is 1e-5, not bits).
 #pragma unroll
         for (int r = 0; r < kKfMax; ++r) {
             if (r >= SS) continue;
@@ -289,13 +290,13 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
                 if (a >= MM) continue;
                 float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(PHt[k], Si[k][a]));
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = fmaf(PHt[k], Si[k][a], acc);
                 K[a] = acc;
             }
             {   // x += K y
                 float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = __fadd_rn(acc, __fmul_rn(K[k], y[k]));
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = fmaf(K[k], y[k], acc);
                 X[i * SS + r] = __fadd_rn(x[r], acc);
             }
 #pragma unroll
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
                 if (c >= SS) continue;
                 float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = __fadd_rn(acc, __fmul_rn(IKH[k], Pm[k][c]));
+                for (int k = 0; k < kKfMax; ++k) if (k < SS) acc = fmaf(IKH[k], Pm[k][c], acc);
                 Pn[c] = acc;
             }
             if (S == 6) {      // 24-byte rows of a 16-byte aligned matrix: three 8-byte stores

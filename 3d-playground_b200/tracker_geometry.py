@@ -130,6 +130,75 @@ def estimate_ts_bias(boxes, camera_idxs, objs, timestamps, ts_bias, mu_v, phi_nm
     return ts_bias
 
 
+def remove_overlaps(boxes, frames_alive, phi_over):
+    """MC_Crop_Tracker.remove_overlaps (MC3D_crop_tracker.py:482-518) without the filter bookkeeping: boxes[n,>=6] are the
+    tracked objects' states (the filter view advanced to the newest time stamp), frames_alive[n] the number of frames each
+    has been tracked - used as the NMS confidence, so of two overlapping tracklets the younger one goes.  Returns
+    (keepers int64[k] as torchvision.nms orders them, removed bool[n]); phi_over <= 0 keeps everything (:489)."""
+    dev = _exec_device(boxes, frames_alive)
+    n = boxes.shape[0]
+    if n == 0 or phi_over <= 0:
+        keep = torch.arange(n, dtype=torch.int64, device=dev)
+        return _ret(keep, boxes), _ret(torch.zeros(n, dtype=torch.bool, device=dev), boxes)
+    fp = ops.state_footprint(_to_dev(boxes, dev))
+    keep = ops.nms(fp, _to_dev(torch.as_tensor(frames_alive), dev).to(torch.float32), phi_over)
+    removed = torch.ones(n, dtype=torch.bool, device=dev)
+    removed[keep] = False
+    return _ret(keep, boxes), _ret(removed, boxes)
+
+
+def parse_detections(hg, scores, labels, boxes, camera_idxs, cameras, sigma_d, phi_nms_im, phi_nms_space, n_best=200,
+                     perform_nms=True, refine_height=False, heights=None):
+    """MC_Crop_Tracker.parse_detections (MC3D_crop_tracker.py:319-383) with the detections staying on the GPU from the
+    detector's output to the tracker's state space (the reference moves them to the CPU first, :1080-1083):
+
+        score cut `scores > sigma_d` (:337-344) -> drop the 2D box columns (:349-350) -> im_nms with the reference's scalar
+        group offset (:354, :592-615) -> guess_heights + im_to_state (:363-364), optionally the two-pass height refinement
+        (:366-370) in ONE fused kernel (g3d_im_to_state_refined) -> space_nms (:376-381).
+
+    hg: the drop-in Homography / Homography_Wrapper; cameras: list of camera names indexed by camera_idxs (:361).
+    scores[d], labels[d] (integer classes: like the reference, guess_heights then falls back to the "other" height unless
+    `heights[d]` is given), boxes[d,20], camera_idxs[d].  n_best is accepted and, as in the reference body, not used.
+    Returns (boxes[k,6] float32 states, labels[k], scores[k], camera_idxs[k]); four empty lists when nothing survives the
+    cut, as the reference does (:332-333, :346-347).  estimate_ts_bias (:372-374) is a separate call (estimate_ts_bias)."""
+    if len(scores) == 0:
+        return [], [], [], []
+    dev = _exec_device(scores, boxes)
+    sc, lb = _to_dev(scores, dev), _to_dev(torch.as_tensor(labels), dev)
+    bx, cam = _to_dev(boxes, dev), _to_dev(torch.as_tensor(camera_idxs), dev)
+    keepers = torch.nonzero(sc > float(sigma_d)).reshape(-1)          # the one data-dependent size of the function
+    if keepers.numel() == 0:
+        return [], [], [], []
+    sc, lb, cam = sc[keepers], lb[keepers], cam[keepers]
+    det = bx[keepers].reshape(-1, 10, 2)[:, :8, :].contiguous()
+    if perform_nms:
+        idxs = im_nms(det, sc, threshold=phi_nms_im, groups=cam)
+        sc, lb, cam, det = sc[idxs], lb[idxs], cam[idxs], det[idxs].contiguous()
+    if heights is None:
+        h = hg.guess_heights(lb.tolist())                   # integer labels: the "other" height, as in the reference
+    else:
+        h = _to_dev(torch.as_tensor(heights), dev)[keepers]
+        h = h[idxs] if perform_nms else h
+    # camera names -> the homography's own camera indices, on the device (a Python list of d names is what dominates the
+    # reference's call, SURVEY §7-8)
+    bank = hg._bank()
+    lut = torch.tensor([bank.index[c] for c in cameras], dtype=torch.uint8, device=dev)
+    cam_names = lut[cam.long()]
+    h = _to_dev(h, dev)
+    if refine_height:
+        states = hg.im_to_state_refined(det, heights=h, name=cam_names) if hasattr(hg, "im_to_state_refined") else None
+        if states is None:
+            states = hg.im_to_state(det, heights=h, name=cam_names)
+            repro = hg.state_to_im(states, name=cam_names)
+            states = hg.im_to_state(det, heights=hg.height_from_template(repro, h, det), name=cam_names)
+    else:
+        states = hg.im_to_state(det, heights=h, name=cam_names)
+    if perform_nms:
+        idxs = space_nms(states, sc, threshold=phi_nms_space)
+        states, sc, lb, cam = states[idxs], sc[idxs], lb[idxs], cam[idxs]
+    return _ret(states, boxes), _ret(lb, boxes), _ret(sc, boxes), _ret(cam, boxes)
+
+
 class FrameGeometry:
     """One tracker frame's geometry as a single CUDA graph.
 

@@ -124,3 +124,32 @@ def pairwise_iou_eps(a, b, eps=1e-6):
     ih = (torch.min(a[:, None, 3], b[None, :, 3]) - torch.max(a[:, None, 1], b[None, :, 1])).clamp(min=0)
     inter = iw * ih
     return inter / (area_a[:, None] + area_b[None, :] - inter + eps)
+
+
+def remove_overlaps(boxes, frames_alive, phi_over):
+    """MC3D_crop_tracker.py:482-518: NMS on the footprints with the number of frames alive as the confidence"""
+    return nms_oracle.nms(footprint(boxes).float(), torch.as_tensor(frames_alive).float(), phi_over)
+
+
+def parse_detections(scores, labels, boxes, camera_idxs, H1, H2, P1, P2, sigma_d, phi_im, phi_space, heights,
+                     perform_nms=True, refine_height=False):
+    """MC3D_crop_tracker.py:319-383 step by step on CPU tensors; H1/H2/P1/P2: per-camera matrices [ncam,3,3] / [ncam,3,4] of
+    the wrapper's two homographies; heights[d]: the guess_heights values.  Returns (states, labels, scores, camera_idxs)."""
+    keep = torch.where(scores > torch.ones(scores.shape) * sigma_d)
+    labels, det, scores, cams, heights = labels[keep], boxes[keep], scores[keep], camera_idxs[keep], heights[keep]
+    if len(det) == 0:
+        return [], [], [], []
+    det = det.reshape(-1, 10, 2)[:, :8, :]
+    if perform_nms:
+        idx = im_nms(det, scores, threshold=phi_im, groups=cams)
+        labels, det, scores, cams, heights = labels[idx], det[idx], scores[idx], cams[idx], heights[idx]
+    c = cams.long()
+    states = ho.wrapper_im_to_state(det, H1[c], H2[c], heights)
+    if refine_height:
+        repro = ho.wrapper_state_to_im(states, P1[c], P2[c])
+        refined = ho.height_from_template(repro, heights, det)
+        states = ho.wrapper_im_to_state(det, H1[c], H2[c], refined)
+    if perform_nms:
+        idx = space_nms(states, scores, threshold=phi_space)
+        labels, states, scores, cams = labels[idx], states[idx], scores[idx], cams[idx]
+    return states, labels, scores, cams

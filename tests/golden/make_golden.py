@@ -368,6 +368,62 @@ def golden_best_box():
     save("best_box", prior=prior, preds=preds, confs=confs, classes=classes, eval_a=a, eval_b=b, eval_iou=eps_iou, **out)
 
 
+def parse_inputs(seed=95, n_obj=60, n_cams=3):
+    """seeded parse_detections scenario shared with the tests: detector output [d,20] (8 projected corners + 2D box) for
+    objects seen by their camera, jittered duplicates (so both NMS stages bite), scores around the cut, integer labels"""
+    g = synth.gen(seed)
+    Pm, Hm = synth.camera_matrices(n_cams)
+    st, cam = synth.vehicle_states(n_obj, g, n_cams=n_cams)
+    dup = torch.randint(0, n_obj, (n_obj,), generator=g)
+    st = torch.cat((st, st[dup] + torch.randn(n_obj, 6, generator=g) * torch.tensor([0.6, 0.15, 0.3, 0.1, 0.1, 0.0])))
+    cam = torch.cat((cam, cam[dup]))
+    d = st.shape[0]
+    scores = torch.rand(d, generator=g)
+    labels = torch.randint(0, 8, (d,), generator=g)
+    return st, cam.long(), scores, labels, Pm, Hm
+
+
+def golden_parse():
+    """MC_Crop_Tracker.parse_detections (MC3D_crop_tracker.py:319-383) and remove_overlaps' NMS (:482-518) from the
+    unmodified reference, called unbound on a namespace that carries the fields they read."""
+    sys.path.insert(0, REF)
+    import homography as ref_h
+    import MC3D_crop_tracker as mc
+    sys.path.pop(0)
+    from torchvision.ops import nms as tv_nms
+    T = mc.MC_Crop_Tracker
+    st, cam, scores, labels, Pm, Hm = parse_inputs()
+    names = synth.CAMERAS[:Pm.shape[0]]
+    hg1, hg2 = ref_h.Homography(), ref_h.Homography()
+    for i, n in enumerate(names):
+        hg1.correspondence[n] = {"P": Pm[i, 0], "H": Hm[i, 0], "H_inv": np.linalg.inv(Hm[i, 0])}
+        hg2.correspondence[n] = {"P": Pm[i, 1], "H": Hm[i, 1], "H_inv": np.linalg.inv(Hm[i, 1])}
+    hg1.default_correspondence = hg2.default_correspondence = names[0]
+    wr = ref_h.Homography_Wrapper(hg1, hg2)
+    corners = wr.state_to_im(st, name=[names[i] for i in cam.tolist()]).float()             # [d,8,2]
+    box2d = torch.stack((corners[:, :, 0].min(1).values, corners[:, :, 1].min(1).values,
+                         corners[:, :, 0].max(1).values, corners[:, :, 1].max(1).values), dim=1)
+    boxes = torch.cat((corners.reshape(-1, 16), box2d), dim=1)                               # the detector's [d,20] rows
+    out = dict(boxes=boxes, cam=cam, scores=scores, labels=labels, P=Pm, H=Hm)
+    for tag, kw in (("nms", dict(perform_nms=True, refine_height=False)), ("nms_refined", dict(perform_nms=True, refine_height=True)),
+                    ("plain", dict(perform_nms=False, refine_height=False))):
+        me = types.SimpleNamespace(sigma_d=0.35, phi_nms_im=0.3, phi_nms_space=0.1, est_ts=False, cameras=names, hg=wr)
+        me.im_nms = lambda *a, **k: T.im_nms(me, *a, **k)
+        me.space_nms = lambda *a, **k: T.space_nms(me, *a, **k)
+        b, l, s, c = T.parse_detections(me, scores.clone(), labels.clone(), boxes.clone(), cam.clone(), **kw)
+        out[f"states_{tag}"], out[f"labels_{tag}"], out[f"scores_{tag}"], out[f"cams_{tag}"] = b, l, s, c
+    # remove_overlaps: the state -> footprint -> nms(frames alive) core (:495-508) on the first half of the states
+    view = st[:40]
+    sp = hg1.state_to_space(view.clone())
+    fp = torch.zeros([sp.shape[0], 4])
+    fp[:, 0] = torch.min(sp[:, 0:4, 0], dim=1)[0]; fp[:, 2] = torch.max(sp[:, 0:4, 0], dim=1)[0]
+    fp[:, 1] = torch.min(sp[:, 0:4, 1], dim=1)[0]; fp[:, 3] = torch.max(sp[:, 0:4, 1], dim=1)[0]
+    alive = torch.randint(1, 300, (40,), generator=synth.gen(96))
+    out["overlap_states"], out["overlap_alive"] = view, alive
+    out["overlap_keep"] = tv_nms(fp.float(), alive.float(), 0.2)
+    save("parse", **out)
+
+
 def ts_bias_inputs(seed=81, n_obj=45, n_cams=4):
     """seeded estimate_ts_bias scenario shared with the tests: objects seen by 1-3 cameras (jittered duplicates), a
     filter view with both directions, per-camera timestamps"""
@@ -496,6 +552,10 @@ if __name__ == "__main__":
         _shim()
         golden_anchors()
         sys.exit(0)
+    if "--only-parse" in sys.argv:
+        _shim()
+        golden_parse()
+        sys.exit(0)
     if "--only-best-box" in sys.argv:
         _shim()
         golden_best_box()
@@ -519,3 +579,4 @@ if __name__ == "__main__":
     golden_anchors()
     golden_ts_bias()
     golden_best_box()
+    golden_parse()

@@ -152,3 +152,52 @@ def test_cfg5_full_size_frame_vs_oracle():
     corners = ho.wrapper_state_to_im(j5, Pc[:, 0], Pc[:, 1])
     assert torch.equal(out["im_keep"].cpu(), to.im_nms(corners, sc5, 0.3))
     assert 0 < out["space_keep"].numel() < 2000 and 0 < out["im_keep"].numel() < 2000
+
+
+def _wrapper_from(P, H, n_cams):
+    from geom3d_b200.homography_impl import Homography, Homography_Wrapper
+    hg1, hg2 = Homography(), Homography()
+    names = synth.CAMERAS[:n_cams]
+    for i, n in enumerate(names):
+        hg1.add_correspondence_matrices(n, H[i, 0].numpy(), P[i, 0].numpy())
+        hg2.add_correspondence_matrices(n, H[i, 1].numpy(), P[i, 1].numpy())
+    return Homography_Wrapper(hg1, hg2), names
+
+
+def test_parse_detections_on_the_device_golden():
+    """MC_Crop_Tracker.parse_detections (MC3D_crop_tracker.py:319-383) with the detections staying on the GPU
+    - score cut, im_nms, im_to_state (+ fused two-pass height refinement), space_nms - against the unmodified method's
+    output (golden): the same detections survive, in the same order; states within 1e-5"""
+    from conftest import assert_close_rel
+    from geom3d_b200 import tracker_geometry as tg
+    gd = load_golden("parse")
+    wr, names = _wrapper_from(gd["P"], gd["H"], gd["P"].shape[0])
+    for tag, kw in (("nms", dict(perform_nms=True, refine_height=False)), ("nms_refined", dict(perform_nms=True, refine_height=True)),
+                    ("plain", dict(perform_nms=False, refine_height=False))):
+        for put in (lambda t: t.cuda(), lambda t: t):
+            st, lb, sc, cm = tg.parse_detections(wr, put(gd["scores"]), put(gd["labels"]), put(gd["boxes"]), put(gd["cam"]), names,
+                                                 sigma_d=0.35, phi_nms_im=0.3, phi_nms_space=0.1, **kw)
+            assert torch.equal(lb.cpu(), gd[f"labels_{tag}"]) and torch.equal(sc.cpu(), gd[f"scores_{tag}"]), tag
+            assert torch.equal(cm.cpu(), gd[f"cams_{tag}"])
+            assert st.dtype == torch.float32
+            assert_close_rel(st.cpu(), gd[f"states_{tag}"], 1e-5, f"states {tag}")
+    assert tg.parse_detections(wr, gd["scores"].cuda() * 0, gd["labels"].cuda(), gd["boxes"].cuda(), gd["cam"].cuda(), names,
+                               0.35, 0.3, 0.1) == ([], [], [], [])
+    assert tg.parse_detections(wr, gd["scores"][:0], gd["labels"][:0], gd["boxes"][:0], gd["cam"][:0], names, 0.35, 0.3, 0.1) == ([], [], [], [])
+
+
+def test_remove_overlaps_golden_and_oracle():
+    """MC_Crop_Tracker.remove_overlaps (MC3D_crop_tracker.py:482-518): footprint NMS with the frames alive as confidence"""
+    from geom3d_b200 import tracker_geometry as tg
+    from oracle import tracker_oracle as to
+    gd = load_golden("parse")
+    keep, removed = tg.remove_overlaps(gd["overlap_states"].cuda(), gd["overlap_alive"].cuda(), 0.2)
+    assert torch.equal(keep.cpu(), gd["overlap_keep"]) and int(removed.sum()) == 40 - gd["overlap_keep"].numel()
+    keep0, removed0 = tg.remove_overlaps(gd["overlap_states"].cuda(), gd["overlap_alive"].cuda(), 0.0)
+    assert keep0.numel() == 40 and not bool(removed0.any())                       # phi_over <= 0: nothing is removed (:489)
+    g = synth.gen(97)
+    st, _ = synth.vehicle_states(1500, g, n_cams=1)
+    st[:, 0] = 100 + torch.rand(1500, generator=g) * 2000
+    alive = torch.randint(1, 500, (1500,), generator=g)
+    keep, _ = tg.remove_overlaps(st.cuda(), alive.cuda(), 0.3)
+    assert torch.equal(keep.cpu(), to.remove_overlaps(st, alive, 0.3))

@@ -256,3 +256,20 @@ def test_postprocess_batch_flattening_equals_loop_over_the_reference_expressions
         S.append(scores[idx]); K.append(torch.tensor([i] * idx.shape[0])); X.append(anchorBoxes[idx])
     got = nms_oracle.detect_3d(cls, boxes)
     assert torch.equal(got[0], torch.cat(S)) and torch.equal(got[1], torch.cat(K)) and torch.equal(got[2], torch.cat(X))
+
+
+def test_parse_detections_and_remove_overlaps(golden):
+    """tracker_oracle.parse_detections / remove_overlaps against the UNMODIFIED MC_Crop_Tracker.parse_detections
+    (MC3D_crop_tracker.py:319-383; integer labels -> the "other" height 5 from guess_heights) and the nms core of
+    remove_overlaps (:495-508) - tests/golden/parse.npz"""
+    gd = golden("parse")
+    H, P = gd["H"], gd["P"]
+    heights = torch.full((gd["scores"].shape[0],), 5.0)
+    for tag, kw in (("nms", dict(perform_nms=True, refine_height=False)), ("nms_refined", dict(perform_nms=True, refine_height=True)),
+                    ("plain", dict(perform_nms=False, refine_height=False))):
+        st, lb, sc, cm = tracker_oracle.parse_detections(gd["scores"], gd["labels"], gd["boxes"], gd["cam"], H[:, 0], H[:, 1],
+                                                          P[:, 0], P[:, 1], 0.35, 0.3, 0.1, heights, **kw)
+        assert torch.equal(lb, gd[f"labels_{tag}"]) and torch.equal(sc, gd[f"scores_{tag}"]) and torch.equal(cm, gd[f"cams_{tag}"])
+        assert_close_rel(st, gd[f"states_{tag}"], 1e-6, f"states {tag}")
+    keep = tracker_oracle.remove_overlaps(gd["overlap_states"], gd["overlap_alive"], 0.2)
+    assert torch.equal(keep, gd["overlap_keep"])
