@@ -29,6 +29,23 @@ def test_anchor_kernel_equals_reference_tables():
             assert np.array_equal(table, gd[f"anchors_{h}x{w}"])
 
 
+def test_anchor_cache_is_bounded_and_never_hands_out_an_edited_table():
+    from geom3d_b200 import ops
+    from geom3d_b200.anchors_impl import Anchors
+    mod = Anchors(max_cached=2)
+    img = torch.zeros(1, 3, 64, 96, device="cuda")
+    t = mod(img)
+    pristine = t.clone()
+    t[0, :, 0].clamp_(min=0)                          # what an in-place ClipBoxes does to its argument
+    t2 = mod(img)
+    assert t2 is not t and torch.equal(t2, pristine) and ops.anchor_pyramid_of(t2) is not None
+    assert mod(img) is t2
+    for hw in ((32, 32), (48, 48), (80, 80)):
+        mod(torch.zeros(1, 3, *hw, device="cuda"))
+    assert len(mod._cache) == 2 and (64, 96, "cuda:0") not in mod._cache
+    assert torch.equal(mod(img), pristine)
+
+
 def test_anchor_kernel_custom_pyramid_vs_oracle():
     from geom3d_b200 import ops
     from geom3d_b200.anchors_impl import Anchors

@@ -194,12 +194,12 @@ def test_kf_oracle_matches_reference_golden():
 def test_anchors_oracle_and_host_generator_equal_reference_tables():
     """anchors.py:21-40: every stored table and every sha256 of the reference's Anchors.forward, bit for bit"""
     import hashlib
-    from geom3d_b200.anchors_impl import Anchors, anchors_for_image
+    from geom3d_b200.anchors_impl import anchors_for_image
     gd = np.load(os.path.join(GOLDEN, "anchors.npz"))
     shapes = [tuple(map(int, k[7:].split("x"))) for k in gd.files if k.startswith("sha256_")]
     assert len(shapes) == 6
     for h, w in shapes:
-        for table in (anchors_oracle.anchors(h, w), anchors_for_image(h, w), Anchors()(torch.zeros(1, 3, h, w))[0].numpy()):
+        for table in (anchors_oracle.anchors(h, w), anchors_for_image(h, w)):
             assert table.dtype == np.float32 and table.shape == (int(gd[f"count_{h}x{w}"]), 4)
             assert hashlib.sha256(np.ascontiguousarray(table).tobytes()).digest() == gd[f"sha256_{h}x{w}"].tobytes(), (h, w)
             if f"anchors_{h}x{w}" in gd.files:
