@@ -87,6 +87,9 @@ SIGNATURES = {
     "g3d_detect_tail": (_int, [_c_ptr, _i64, _i64, _i64, _i64, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _int, _c_ptr, _c_ptr,
                                _int, _f32, _f32, _f64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
                                _c_ptr, _i64, _int, _c_ptr]),
+    "g3d_detect_tail_short": (_int, [_c_ptr, _i64, _i64, _i64, _i64, _c_ptr, _i64, _c_ptr, _i64, _c_ptr, _int, _c_ptr, _c_ptr,
+                               _int, _f32, _f32, _f64, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr,
+                               _c_ptr, _i64, _int, _c_ptr]),
     "g3d_cross_camera_pairs": (_int, [_c_ptr, _c_ptr, _i64, _f64, _c_ptr, _c_ptr, _c_ptr, _i64, _int, _c_ptr]),
     "g3d_generate_anchors": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _c_ptr, _i64, _int, _c_ptr]),
 }

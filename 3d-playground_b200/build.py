@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("G3D_NVCC_FLAGS", "").split()      # e.g. -DG3D_TAIL_CLOCKS (tools/tail_phases.py)
 
 
 def _nvcc():

@@ -146,12 +146,12 @@ def hyper_array(hyper):
 
 
 def set_tuning(name, value):
-    """process-wide tuning knob of the loss kernels (g3d_set_tuning): fill_chain_permille, fill_ctas, force_anchor_centric"""
+    """process-wide tuning knob of the loss path (g3d_set_tuning): pdl, force_anchor_centric"""
     check(_lib.lib().g3d_set_tuning(_lib.TUNE_KEYS[name], int(value)), "g3d_set_tuning")
 
 
 def _tuning_from_env():
-    """G3D_TUNE="fill_chain_permille=300,fill_ctas=148" (benchmark sweeps); read once, at import"""
+    """G3D_TUNE="pdl=0,force_anchor_centric=1" (benchmark sweeps); read once, at import"""
     spec = os.environ.get("G3D_TUNE", "")
     for item in filter(None, (x.strip() for x in spec.split(","))):
         k, v = item.split("=")
@@ -483,39 +483,80 @@ def gather_candidates_decoded(scores, outer, inner, N, outer_pitch, idx, count, 
     return seg_offsets, cand_scores, cand_boxes, cand_src
 
 
+class TailPlan(dict):
+    """Buffers of one detection tail - count, keep_count, seg_offsets, out_offsets, summary, cand_src, cand_scores, keep
+    (dict entries) and the workspace - for S = outer*inner segments of capacity cap on one device, with their ctypes
+    pointers made once.  A caller that runs the tail every frame keeps the plan: launch() and assemble() are then one
+    ctypes call each with no allocation besides the four result tensors (postprocess._tail_run)."""
+
+    def __init__(self, outer, inner, N, cap, dev):
+        super().__init__()
+        S, T = outer * inner, outer * inner * cap
+        L = _lib.lib()
+        self.shape = (outer, inner, N, cap, dev)
+        # one int32 block for the small arrays and the candidate tables, one int64 keep list, one workspace
+        small = torch.empty((4 * S + 6 + 2 * T + 64,), dtype=torch.int32, device=dev)
+        o = 0
+        self["count"] = small[o:o + S]; o += S
+        self["keep_count"] = small[o:o + S]; o += S
+        self["seg_offsets"] = small[o:o + S + 1]; o += S + 1
+        self["out_offsets"] = small[o:o + S + 1]; o += S + 1
+        self["summary"] = small[o:o + 4]; o += 4
+        o = (o + 3) & ~3                                        # 16-byte alignment of the two tables
+        self["cand_src"] = small[o:o + T]; o += T
+        o = (o + 3) & ~3
+        self["cand_scores"] = small[o:o + T].view(torch.float32)
+        self["keep"] = torch.empty((T,), dtype=torch.int64, device=dev)
+        self.ws = _workspace(L.g3d_detect_tail_workspace_bytes(S, cap), dev)
+        self.ptr = {k: _p(v) for k, v in self.items()}
+        self.ws_ptr, self.ws_bytes, self.dev_idx = _p(self.ws), self.ws.numel(), _idx(dev)
+
+    def launch(self, short, scores, outer_pitch, thr, decode, iou_threshold, stream):
+        """the tail up to summary; `decode` = _decode_args(...) of the anchors / regression this tail decodes from"""
+        outer, inner, N, cap, _ = self.shape
+        anc, reg, variant, mean_h, std_h, clip, cw, ch = decode
+        q = self.ptr
+        L = _lib.lib()
+        fn = L.g3d_detect_tail_short if short else L.g3d_detect_tail
+        check(fn(_p(scores), outer, inner, N, outer_pitch, _p(thr), cap, _p(anc), anc.shape[0], _p(reg), variant,
+                 mean_h, std_h, clip, cw, ch, float(iou_threshold), q["count"], q["seg_offsets"], q["cand_scores"],
+                 q["cand_src"], q["keep"], q["keep_count"], q["out_offsets"], q["summary"], self.ws_ptr, self.ws_bytes,
+                 self.dev_idx, stream), "g3d_detect_tail_short" if short else "g3d_detect_tail")
+
+    def assemble(self, rows, decode, stream):
+        """(scores f32[rows], classes i64[rows], boxes f32[rows,20|4], image i64[rows]) of the kept candidates"""
+        outer, inner, N, _, dev = self.shape
+        anc, reg, variant, mean_h, std_h, clip, cw, ch = decode
+        q = self.ptr
+        scores = torch.empty((rows,), dtype=torch.float32, device=dev)
+        classes = torch.empty((rows,), dtype=torch.int64, device=dev)
+        image = torch.empty((rows,), dtype=torch.int64, device=dev)
+        boxes = torch.empty((rows, 20 if variant == VARIANT_3D else 4), dtype=torch.float32, device=dev)
+        if rows:
+            check(_lib.lib().g3d_assemble_detections(q["keep"], q["keep_count"], q["seg_offsets"], q["out_offsets"],
+                                                     q["cand_scores"], q["cand_src"], outer, inner, N, _p(anc), anc.shape[0],
+                                                     _p(reg), variant, mean_h, std_h, clip, cw, ch, _p(scores), _p(classes),
+                                                     _p(boxes), _p(image), rows, self.dev_idx, stream),
+                  "g3d_assemble_detections")
+        return scores, classes, boxes, image
+
+
 def detect_tail(scores, outer, inner, N, outer_pitch, thr, cap, anchors, regression, iou_threshold, mean=None, std=None,
-                clip_wh=None):
+                clip_wh=None, short=False, reuse=None):
     """filter_compact -> gather_candidates_decoded -> nms_segmented(relative=False) -> detection_offsets in ONE library
-    call (g3d_detect_tail: the ~10 short launches are issued from C++ back to back).  Returns a dict with count,
-    seg_offsets, cand_scores, cand_src, keep, keep_count, out_offsets and summary i32[2] = (detections, max count)."""
+    call (g3d_detect_tail: the ~10 short launches are issued from C++ back to back).  Returns a TailPlan - a dict with
+    count, seg_offsets, cand_scores, cand_src, keep, keep_count, out_offsets and summary i32[4] = (detections, max count,
+    segments not processed, 0).  short=True: g3d_detect_tail_short - one launch for the whole chain, for segments of at
+    most 1024 candidates; summary[2] > 0 tells the caller to repeat with short=False.  `reuse`: the plan of an earlier
+    call with the same sizes on the same stream whose results are no longer needed - its buffers are written again."""
     dev = _need_cuda(scores, thr, anchors, regression)
     if scores.dtype != torch.float32 or not scores.is_contiguous():
         raise Geom3dError("detect_tail needs a contiguous float32 score tensor")
-    anc, reg, variant, mean_h, std_h, clip, cw, ch = _decode_args(anchors, regression, mean, std, clip_wh)
+    decode = _decode_args(anchors, regression, mean, std, clip_wh)
     thr = _prep(thr, torch.float32)
-    S = outer * inner
-    T = S * cap
-    L = _lib.lib()
-    # one int32 block for the small arrays and the candidate tables, one int64 keep list, one workspace
-    small = torch.empty((4 * S + 4 + 2 * T + 64,), dtype=torch.int32, device=dev)
-    o = 0
-    count = small[o:o + S]; o += S
-    keep_count = small[o:o + S]; o += S
-    seg_offsets = small[o:o + S + 1]; o += S + 1
-    out_offsets = small[o:o + S + 1]; o += S + 1
-    summary = small[o:o + 2]; o += 2
-    o = (o + 3) & ~3                                        # 16-byte alignment of the two tables
-    cand_src = small[o:o + T]; o += T
-    o = (o + 3) & ~3
-    cand_scores = small[o:o + T].view(torch.float32)
-    keep = torch.empty((T,), dtype=torch.int64, device=dev)
-    ws = _workspace(L.g3d_detect_tail_workspace_bytes(S, cap), dev)
-    check(L.g3d_detect_tail(_p(scores), outer, inner, N, outer_pitch, _p(thr), cap, _p(anc), anc.shape[0], _p(reg), variant,
-                            mean_h, std_h, clip, cw, ch, float(iou_threshold), _p(count), _p(seg_offsets), _p(cand_scores),
-                            _p(cand_src), _p(keep), _p(keep_count), _p(out_offsets), _p(summary), _p(ws), ws.numel(),
-                            _idx(dev), _stream(dev)), "g3d_detect_tail")
-    return dict(count=count, seg_offsets=seg_offsets, cand_scores=cand_scores, cand_src=cand_src, keep=keep,
-                keep_count=keep_count, out_offsets=out_offsets, summary=summary)
+    plan = reuse if reuse is not None and reuse.shape == (outer, inner, N, cap, dev) else TailPlan(outer, inner, N, cap, dev)
+    plan.launch(short, scores, outer_pitch, thr, decode, iou_threshold, _stream(dev))
+    return plan
 
 
 def detection_offsets(keep_count):

@@ -254,8 +254,8 @@ int g3d_exclusive_scan_i32(const int32_t* count, int64_t S, int32_t* offsets, in
 /* g3d_detect_tail: g3d_filter_compact -> g3d_gather_candidates_decoded -> g3d_nms_segmented(relative = 0) ->
  *   g3d_exclusive_scan_i32 issued back to back from one call (the chain is launch-latency bound; see detect_tail.cu),
  *   S = outer*inner segments, thr[S] on the device.  Outputs as the individual entry points define them: count[S],
- *   seg_offsets[S+1], cand_scores[S*cap], cand_src[S*cap], keep[S*cap], keep_count[S], out_offsets[S+1]; summary[2] =
- *   {number of detections = out_offsets[S], max count[s]} for the ONE device->host read the caller needs before
+ *   seg_offsets[S+1], cand_scores[S*cap], cand_src[S*cap], keep[S*cap], keep_count[S], out_offsets[S+1]; summary[4] =
+ *   {number of detections = out_offsets[S], max count[s], 0, 0} for the ONE device->host read the caller needs before
  *   g3d_assemble_detections.  workspace: g3d_detect_tail_workspace_bytes(S, cap) bytes, 256-byte aligned. */
 int64_t g3d_detect_tail_workspace_bytes(int64_t S, int64_t cap);
 int g3d_detect_tail(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch, const float* thr,
@@ -264,6 +264,21 @@ int g3d_detect_tail(const float* scores, int64_t outer, int64_t inner, int64_t N
                     double iou_threshold, int32_t* count, int32_t* seg_offsets, float* cand_scores, int32_t* cand_src,
                     int64_t* keep, int32_t* keep_count, int32_t* out_offsets, int32_t* summary, void* workspace,
                     int64_t workspace_bytes, int device, void* stream);
+/* g3d_detect_tail_short: the same call for the usual case of SHORT segments (at most 1024 candidates per (image, class),
+ *   iou_threshold >= 0): after the score filter ONE launch does gather + decode + sort + NMS per segment in shared memory
+ *   (pair search through a grid over the box centres, exact torchvision test on the pairs found; detect_tail.cu), then
+ *   one launch writes out_offsets and summary.  Same arguments, same results, with two differences in layout:
+ *   the candidate tables of segment s start at seg_offsets[s] = s*cap and are in NMS order (score descending, anchor
+ *   ascending) - keep / g3d_assemble_detections work on them unchanged - and summary has 4 entries:
+ *   {detections, max count[s], segments NOT processed, 0}.  A segment that is too long, has more than a few thousand suppressing
+ *   pairs or holds boxes with sides < 1e-10 or coordinates > 1e15 gets keep_count[s] = -1 and is counted in summary[2]:
+ *   the caller then repeats the tail with g3d_detect_tail.  Workspace as g3d_detect_tail. */
+int g3d_detect_tail_short(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch,
+                          const float* thr, int64_t cap, const float* anchors, int64_t Ba, const float* reg, int variant,
+                          const float* mean_host, const float* std_host, int clip, float clip_w, float clip_h,
+                          double iou_threshold, int32_t* count, int32_t* seg_offsets, float* cand_scores,
+                          int32_t* cand_src, int64_t* keep, int32_t* keep_count, int32_t* out_offsets, int32_t* summary,
+                          void* workspace, int64_t workspace_bytes, int device, void* stream);
 int g3d_assemble_detections(const int64_t* keep, const int32_t* keep_count, const int32_t* seg_offsets,
                             const int32_t* out_offsets, const float* cand_scores, const int32_t* cand_src,
                             int64_t outer, int64_t inner, int64_t N, const float* anchors, int64_t Ba,

@@ -339,3 +339,102 @@ def test_cfg3_one_image_1080p_vs_oracle(three_d):
     else:
         assert_close_rel(got[2].cpu(), want[2], 1e-6, "2D boxes")
     assert int(got[3].max()) == 0
+
+
+def _tail_both_ways(cls, reg, anc, thr_score, iou, mean, std):
+    """(short-path result, general-chain result, segments the short path left over) of one detection tail"""
+    from geom3d_b200 import ops
+    B, A, C = cls.shape
+    thr = torch.full((B * C,), thr_score, dtype=torch.float32, device="cuda")
+    cap = min(16384, A)
+    res = []
+    for short in (True, False):
+        t = ops.detect_tail(cls, B, C, A, A * C, thr, cap, anc, reg, iou, mean, std, None, short=short)
+        summ = t["summary"].cpu()
+        out = ops.assemble_detections(t["keep"], t["keep_count"], t["seg_offsets"], t["cand_scores"], t["cand_src"], B, C, A,
+                                      anc, reg, mean, std, None, out_offsets=t["out_offsets"], K=int(summ[0]))
+        res.append((out, int(summ[2]), t))
+    return res[0][0], res[1][0], res[0][1], res[0][2]
+
+
+def _boxes_as_anchors(boxes):
+    """[N,4] boxes -> (anchors [1,N,4], zero 2D regression [1,N,4], mean, std): the 2D decode of a zero delta is the box"""
+    N = boxes.shape[0]
+    return (boxes.reshape(1, N, 4).contiguous().cuda(), torch.zeros(1, N, 4, device="cuda"),
+            np.zeros(4, dtype=np.float32), np.ones(4, dtype=np.float32))
+
+
+@pytest.mark.parametrize("iou", [0.0, 0.1, 0.25, 0.3, 0.5, 0.75, 0.95])
+def test_short_tail_equals_general_chain_on_adversarial_boxes(iou):
+    """g3d_detect_tail_short finds the suppressing pairs through a grid over the box centres (a superset argument, see
+    detect_tail.cu) - its detections must equal the general chain's (all-pairs greedy NMS) bit for bit on every box set:
+    clusters, nested and extreme aspect ratios, exact duplicates, score ties, empty / inverted / NaN boxes, one spot, anisotropic extents"""
+    g = synth.gen(int(iou * 100) + 3)
+    sets = []
+    b, _ = synth.clustered_boxes(3000, g)
+    sets.append(b)
+    c = torch.rand(2500, 2, generator=g) * 300                             # sizes over six decades, heavy nesting
+    wh = 10 ** (torch.rand(2500, 2, generator=g) * 6 - 3)
+    sets.append(torch.cat((c - wh / 2, c + wh / 2), dim=1))
+    d = synth.clustered_boxes(400, g, objects=40)[0]                       # exact duplicates + near duplicates
+    sets.append(torch.cat((d, d, d + 1e-4, d[:200])))
+    e = synth.clustered_boxes(2000, g)[0]                                  # malformed rows sprinkled in
+    e[::17, 2] = e[::17, 0]                                                # zero width
+    e[5::23, [0, 2]] = e[5::23, [2, 0]]                                    # inverted
+    e[7::29, 1] = float("nan")
+    e[11::31, 3] = float("inf")                                            # the 2D decode turns it into inf - inf = NaN
+    sets.append(e)
+    sets.append(torch.tensor([[10., 10., 20., 20.]]).repeat(700, 1) + torch.rand(700, 4, generator=g) * 0.5)   # one spot
+    f = synth.clustered_boxes(1500, g, extent=1e6, jitter=3e3)[0] * torch.tensor([1.0, 1e-3, 1.0, 1e-3])      # anisotropic
+    sets.append(f)
+    for k, boxes in enumerate(sets):
+        N = boxes.shape[0]
+        C = 4
+        cls = torch.rand(1, N, C, generator=g)
+        if k == 2:
+            cls = (cls * 8).floor() / 8                                     # many equal scores
+        hot = torch.randint(0, C, (N,), generator=g)
+        cls[0, torch.arange(N), hot] += 1.0                                 # ~N/4 candidates per class above the cut ...
+        cls = cls.cuda().contiguous()
+        anc, reg, mean, std = _boxes_as_anchors(boxes.float())
+        short, general, left, t = _tail_both_ways(cls, reg, anc, 1.0, iou, mean, std)
+        assert int(t["count"].max()) <= 1024
+        if left == 0:
+            assert general[0].numel() > 0
+            for a_, b_ in zip(short, general):
+                assert a_.dtype == b_.dtype and a_.shape == b_.shape, (k, iou)
+                if a_.is_floating_point():                                  # NaN box rows survive NMS: compare the bits
+                    a_, b_ = a_.view(torch.int32), b_.view(torch.int32)
+                assert torch.equal(a_, b_), (k, iou)
+        else:
+            assert k in (2, 4) or iou < 0.25, (k, iou, left)                # only the pair-heavy sets may overflow the pool
+
+
+def test_short_tail_leaves_long_odd_and_pair_heavy_segments_to_the_general_chain():
+    from geom3d_b200 import postprocess as pp
+    g = synth.gen(77)
+    # (a) a class with more than 1024 candidates, (b) boxes with sides below 1e-10, (c) 700 boxes on one spot (245 k
+    # suppressing pairs)
+    long_b = synth.clustered_boxes(3000, g)[0]
+    tiny = synth.clustered_boxes(500, g)[0]
+    tiny[::50] = torch.tensor([1e-11, 1e-11, 1.1e-11, 1.1e-11])        # sides of 1e-12
+    spot = torch.tensor([[10., 10., 20., 20.]]).repeat(700, 1) + torch.rand(700, 4, generator=g) * 0.01
+    for boxes, C in ((long_b, 2), (tiny, 1), (spot, 1)):
+        N = boxes.shape[0]
+        cls = (torch.rand(1, N, C, generator=g) + 1.0).cuda()
+        anc, reg, mean, std = _boxes_as_anchors(boxes.float())
+        short, general, left, t = _tail_both_ways(cls, reg, anc, 1.0, 0.5, mean, std)
+        assert left >= 1 and int((t["keep_count"] < 0).sum()) == left
+        # the public entry notices and repeats with the general chain - twice, to exercise the "stay general" hint
+        for _ in range(2):
+            got = pp.detect_per_class_fused(cls, reg, anc, score_threshold=1.0, mean=mean, std=std)
+            for a_, b_ in zip(got, general):
+                assert torch.equal(a_, b_)
+    # ... and a shape goes back to the short path once its counts are short again
+    key = (torch.cuda.current_device(), 1)
+    pp._TAIL_GENERAL[key] = 1
+    few = synth.clustered_boxes(300, g)[0]
+    cls = (torch.rand(1, 300, 1, generator=g) + 1.0).cuda()
+    anc, reg, mean, std = _boxes_as_anchors(few.float())
+    pp.detect_per_class_fused(cls, reg, anc, score_threshold=1.0, mean=mean, std=std)
+    assert pp._TAIL_GENERAL[key] == 0

@@ -14,7 +14,7 @@ import sys
 
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
-    top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 40
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name", f"regex:{kern}"], capture_output=True, text=True).stdout
     rows, header, fpath, seen_kernel = [], None, None, None
@@ -41,7 +41,7 @@ def main():
     ti = sum(r[3] for r in rows) or 1
     ts = sum(r[4] for r in rows) or 1
     print(f"kernel: {seen_kernel}\n total warp-instructions {ti:,}   samples {ts:,}")
-    rows.sort(key=lambda r: -r[3])
+    rows.sort(key=lambda r: -(r[4] if '--by-samples' in sys.argv else r[3]))
     print(f"{'file:line':28s} {'inst%':>6s} {'samp%':>6s}  top stalls | source")
     for f, ln, src, inst, samp, st in rows[:top]:
         s3 = " ".join(f"{k}:{v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
