@@ -41,7 +41,7 @@ SIGNATURES = {
                                   _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _c_ptr, _int, _c_ptr]),
     "g3d_focal_loss_fwd_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
                                       _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64,
-                                      _c_ptr, _c_ptr, _int, _int, _c_ptr]),
+                                      _c_ptr, _c_ptr, _int, _int, _int, _c_ptr]),
     "g3d_focal_loss_bwd": (_int, [_c_ptr, _c_ptr, _c_ptr, _c_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int,
                                   _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr, _c_ptr, _i64, _c_ptr, _c_ptr, _c_ptr, _int, _c_ptr]),
     "g3d_set_tuning": (_int, [_int, _i64]),

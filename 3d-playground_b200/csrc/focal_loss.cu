@@ -3,41 +3,39 @@
 //   3D: pytorch_retinanet_detector_directional/retinanet/losses.py:27-362
 //   2D: retinanet/losses.py:27-177
 //
-// One training step (forward + every gradient for the expected upstream gradients) is four launches; the backward
+// One training step (forward + every gradient for the expected upstream gradients) is five launches; the backward
 // call adds one that only verifies the expectation on the device.
 //
 //   K0 loss_prologue_kernel   one CTA per image: drop class == -1 rows, the 2D box each GT row is matched with, a
 //                             128-byte table row per GT (regression targets, direction vectors), the class; zero the
-//                             counters; `nfill` extra CTAs zero the keys / chunk mask of the GT-centric assignment with
-//                             bulk async copies.
+//                             counters; extra CTAs zero the keys / chunk mask of the GT-centric assignment.
 //   K1 assignment, one of
 //      assign_pairs_kernel    (anchors = the regular pyramid of Anchors.forward, <= 256 GT rows) GT-centric: one warp per
 //                             (image, GT row) evaluates only the window of cells whose anchors can reach the negative
 //                             threshold and atomicMax-es a 32-bit (IoU, GT index) key per (image, anchor); a chunk mask
 //                             records which 32-anchor chunks hold a key at all (a few percent);
-//      assign_codes_kernel    (any anchor table) anchor-centric tiles with GT culling -> byte codes + positives lists.
+//      assign_codes_kernel    (any anchor table) anchor-centric tiles with GT culling -> byte codes + positives lists
+//                             (and the zero fill of dreg: this kernel is issue-bound and leaves HBM idle).
 //   K2 assign_resolve_kernel  (GT-centric only) touched chunks -> per-image lists of positive anchors (anchor, GT index),
 //                             their count (the normaliser of everything that follows).
-//   K3 focal_stream_kernel    the HBM-bound sweep AND, as a second CTA role in the same launch, the positive anchors:
-//        stream CTAs          read cls (one 8-class row per lane, 256-bit loads) and the keys of touched chunks, evaluate
-//                             focal terms AND their gradient from one -log(1-p) (packed FP32x2 arithmetic), write dcls
-//                             (256-bit stores), per-CTA partial sums, and zero-fill dreg (below);
-//        positives CTAs       one thread per positive anchor from the lists: 20 smooth-L1 terms + 3 direction cosines,
-//                             their gradient row written into dreg; exact fixed-point sums.  Latency-bound work that hides
-//                             completely behind the sweep.
-//        the last CTA of an image (ticket) reduces the image, the last image forms the batch means: no host
-//        synchronisation, no further launch.
+//   K3 focal_stream8_kernel   the HBM-bound sweep: lane <-> row, one 8-class row per lane with 256-bit loads, the keys of
+//                             touched chunks only; focal terms AND their gradient from one -log(1-p) (packed FP32x2
+//                             arithmetic); dcls with 256-bit stores; per-CTA partial sums; and the zero fill of dreg.
+//   K4 positives_kernel       launched as a programmatic dependent of K3 (griddepcontrol): one thread per positive anchor
+//                             from the lists - 20 smooth-L1 terms + 3 direction cosines, exact fixed-point sums, the
+//                             gradient row written into dreg - then waits for K3 and the last CTA of an image (ticket)
+//                             reduces the image, the last image forms the batch means.  No host synchronisation.
 //
 // The regression gradient dreg is zero except on the ~1 % positive rows, but autograd needs it dense: 48 B/row of
-// zeros, 41 % of all bytes the step writes.  The stream CTAs write them with bulk async copies (cp.async.bulk shared ->
-// global, TMA) of a zeroed shared-memory tile, issued by ONE lane per warp for the warp's 256 rows: no LSU issue slots,
-// no registers.  Only chunks that hold a key are written with ordinary stores, lane by lane, and the lanes of positive
-// rows write nothing - those rows belong to the positives CTAs, so the two roles never touch the same bytes and need
-// no ordering.  The anchor-centric kernel (issue-bound, HBM idle) writes the zeros itself, before K3.
+// zeros, 41 % of all bytes the step writes.  The stream warps write them with bulk async copies (cp.async.bulk shared ->
+// global) of a zeroed shared-memory tile, issued by ONE lane per warp for the warp's rows: no LSU issue slots, no
+// registers.  Only chunks that hold a key are written with ordinary stores, lane by lane, and the lanes of positive
+// rows write nothing - those rows belong to K4, so the two kernels never touch the same bytes and need no ordering
+// (which is what lets K4 start before K3 has drained).
 //
 // Gradients written during the forward assume the upstream gradients the host announces (1 for `(cls + reg +
-// vp).backward()`, 1/world under dist.py).  g3d_focal_loss_bwd checks the assumption ON THE DEVICE and recomputes
-// what does not hold; in the usual step it exits after one wave.
+// vp).backward()`, 1/world under dist.py).  g3d_focal_loss_bwd (focal_bwd_kernel) checks the assumption ON THE DEVICE
+// and recomputes what does not hold; in the usual step it exits after one wave.
 #include <atomic>
 #include <string.h>
 #include "assign_tile.cuh"
@@ -102,6 +100,12 @@ struct PrologueArgs {
     int B, Gmax, W, variant;
     FillSlice fill;        // keys + chunk mask of the GT-centric assignment: zeroed by the first nfill CTAs
     int nfill;
+    // persistent regression gradient (dreg_state == G3D_DREG_CLEAN): dreg is zero except on the rows the previous step
+    // wrote - its positive anchors, still listed in pos_anchor (prev_npos[b] of them) - which the image's CTA zeroes here
+    float* dreg;           // null: nothing to re-zero
+    const int32_t* prev_npos;
+    const int32_t* pos_anchor;
+    int A, R;
 };
 
 __global__ void __launch_bounds__(kTile) loss_prologue_kernel(const PrologueArgs p) {
@@ -117,6 +121,16 @@ __global__ void __launch_bounds__(kTile) loss_prologue_kernel(const PrologueArgs
     }
     const int b = blockIdx.x - p.nfill, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = b * kTile + threadIdx.x; i < p.zero_n; i += p.B * kTile) p.zero_ptr[i] = 0;
+    if (p.dreg) {
+        const int nprev = min(max(__ldg(p.prev_npos + b), 0), p.A);
+        const int q = p.R >> 2;                                         // float4 pieces per row (3 or 1)
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < nprev * q; i += kTile) {
+            const int r = i / q;
+            const int a = __ldg(p.pos_anchor + (int64_t)b * p.A + r);
+            if (a >= 0 && a < p.A) reinterpret_cast<float4*>(p.dreg + ((int64_t)b * p.A + a) * p.R)[i - r * q] = z;
+        }
+    }
     const float* img = p.ann + (int64_t)b * p.Gmax * p.W;
     const bool three_d = p.variant == G3D_VARIANT_3D;
     const int cls_col = three_d ? 20 : 4;
@@ -713,6 +727,8 @@ struct PosArgs {
     long long* acc;            // [B][4]: reg_hi, reg_lo, vp_hi, vp_lo (forward)
     int32_t* nonfinite;        // [B]: bit 0 / 1 set if a regression / direction term was NaN / Inf / out of range (forward)
     float* dreg;               // gradient rows of the positives (null: losses only)
+    int32_t* prev_npos;        // (forward, nullable) [B]: receives the image's number of positives - the rows of dreg this
+                               // step wrote, for the next step's re-zeroing (persistent dreg)
     float g1, g2;              // (forward) upstream gradients of the regression / direction losses the rows are formed for
     const float* grad_out;     // [3] device (backward)
     const float* grad_scale;   // [3] device or null (backward): multiplies grad_out (dist.py: local -> global means)
@@ -916,6 +932,7 @@ __global__ void __launch_bounds__(128) positives_kernel(const __grid_constant__ 
     const int n = min(__ldg(p.npos + b), p.A);
     const float npos = (float)n;
     float s_reg = 0.0f, s_vp = 0.0f;
+    if (p.prev_npos && blockIdx.x == 0 && threadIdx.x == 0) p.prev_npos[b] = p.dreg ? n : 0;
     if (p.dreg) {
         const float per_pos = (VARIANT == G3D_VARIANT_3D) ? 20.0f : 4.0f;
         s_reg = p.g1 / ((float)p.B * per_pos * npos);
@@ -1186,6 +1203,7 @@ struct FocalWorkspace {
     int32_t* counters;   // zeroed per call: [B] image tickets, [1] batch ticket, [B] npos, [B] nonfinite flags, then
                          // (8-byte aligned) [B][4] int64 fixed-point sums
     int64_t n_counters;  // number of int32 words to zero
+    int32_t* prev_npos;  // [B] NOT zeroed per call: rows of dreg written by the last gradient step (persistent dreg)
     int64_t Ap;          // per-image pitch of keys / code8 (multiple of 32)
     int64_t MW;          // chunk-mask words per image
     int64_t key_fill_bytes;   // keys + mask: zeroed together
@@ -1215,6 +1233,7 @@ static FocalWorkspace carve(void* base, int64_t B, int64_t A, int64_t Gmax) {
     const int64_t head = align_up(3 * B + 1, 2);          // int32 words before the int64 sums
     w.n_counters = head + 8 * B;
     off += align_up(w.n_counters * 4, 256);
+    w.prev_npos = (int32_t*)(p + off); off += align_up(B * 4, 256);
     w.bytes = off;
     return w;
 }
@@ -1426,10 +1445,11 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
                                       float* per_image, int32_t* assign, int32_t* gt_count_out, double* shard_stats,
                                       float* dcls, float* dreg, void* workspace, int64_t workspace_bytes,
                                       const double* pyramid_host, void* const* trace_events, int n_trace_events,
-                                      int device, void* stream) {
+                                      int dreg_state, int device, void* stream) {
     int rc = check_focal_shapes(B, A, C, R, Gmax, W, variant);
     if (rc != G3D_OK) return rc;
     G3D_REQUIRE(cls && reg && anchors && losses && per_image && workspace, "null pointer");
+    G3D_REQUIRE(dreg_state == G3D_DREG_UNDEFINED || dreg_state == G3D_DREG_CLEAN, "unknown dreg_state");
     G3D_REQUIRE(Gmax == 0 || ann, "null annotations");
     G3D_REQUIRE((dcls == nullptr) == (dreg == nullptr), "dcls and dreg must both be given or both be null");
     G3D_REQUIRE((dcls == nullptr) || grad_expected_host, "gradient buffers need grad_expected_host[3]");
@@ -1463,6 +1483,11 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     pr.B = (int)B; pr.Gmax = (int)Gmax; pr.W = (int)W; pr.variant = variant;
     pr.fill = FillSlice{nullptr, 0};
     pr.nfill = 0;
+    // persistent dreg: zero the previous step's positive rows instead of filling all of it (GT-centric path; the
+    // anchor-centric kernel writes every row anyway)
+    const bool dreg_clean = grad && gt_centric && dreg_state == G3D_DREG_CLEAN;
+    pr.dreg = dreg_clean ? dreg : nullptr; pr.prev_npos = w.prev_npos; pr.pos_anchor = w.pos_anchor;
+    pr.A = (int)A; pr.R = (int)R;
     if (gt_centric) {
         pr.nfill = sms * 8;      // fill CTAs zero the keys and the chunk mask
         pr.fill = FillSlice{(char*)w.keys, (long long)w.key_fill_bytes};
@@ -1507,7 +1532,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     // ---- K3: stream CTAs + positives CTAs + reductions
     StreamArgs p;
     p.cls = cls; p.npos = npos; p.partials = w.partials; p.dcls = dcls;
-    p.dreg = (gt_centric && grad) ? dreg : nullptr;       // the anchor-centric kernel wrote the zeros already
+    p.dreg = (gt_centric && grad && !dreg_clean) ? dreg : nullptr;   // (the anchor-centric kernel wrote the zeros already)
     p.src = make_src(w, gt_centric, Gmax, C, h);
     p.g0 = grad ? grad_expected_host[0] : 0.0f;
     p.B = (int)B; p.A = (int)A; p.C = (int)C; p.R = (int)R; p.T = (int)ceil_div(A, kRowsPerCta);
@@ -1516,6 +1541,7 @@ extern "C" int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const 
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.gt_tab = w.gt_tab; pp.pos_anchor = w.pos_anchor;
     pp.pos_gt = w.pos_gt; pp.npos = npos; pp.gt_count = w.gt_count; pp.acc = ws_acc(w, B); pp.nonfinite = ws_nonfinite(w, B);
     pp.dreg = dreg; pp.g1 = grad ? grad_expected_host[1] : 0.0f; pp.g2 = grad ? grad_expected_host[2] : 0.0f;
+    pp.prev_npos = grad ? w.prev_npos : nullptr;
     pp.grad_out = nullptr; pp.grad_scale = nullptr; pp.e1 = pp.e2 = 0.0f; pp.have_rows = 0;
     pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.h = h;
     pp.partials = w.partials; pp.counters = w.counters; pp.losses = losses; pp.per_image = per_image;
@@ -1560,7 +1586,7 @@ extern "C" int g3d_focal_loss_fwd(const float* cls, const float* reg, const floa
                                   const double* pyramid_host, int device, void* stream) {
     return g3d_focal_loss_fwd_bwd(cls, reg, anchors, ann, B, A, C, R, Gmax, W, variant, hyper_host, nullptr, losses,
                                   per_image, assign, gt_count_out, nullptr, nullptr, nullptr, workspace, workspace_bytes,
-                                  pyramid_host, nullptr, 0, device, stream);
+                                  pyramid_host, nullptr, 0, G3D_DREG_UNDEFINED, device, stream);
 }
 
 extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const float* anchors, const float* ann,
@@ -1599,7 +1625,7 @@ extern "C" int g3d_focal_loss_bwd(const float* cls, const float* reg, const floa
     PosArgs pp;
     pp.reg = reg; pp.anchors = (const float4*)anchors; pp.gt_tab = w.gt_tab; pp.pos_anchor = w.pos_anchor;
     pp.pos_gt = w.pos_gt; pp.npos = ws_npos(w, B); pp.gt_count = w.gt_count; pp.acc = nullptr; pp.nonfinite = nullptr;
-    pp.dreg = dreg; pp.g1 = pp.g2 = 0.0f; pp.grad_out = grad_out; pp.grad_scale = grad_scale;
+    pp.dreg = dreg; pp.prev_npos = nullptr; pp.g1 = pp.g2 = 0.0f; pp.grad_out = grad_out; pp.grad_scale = grad_scale;
     pp.e1 = have_grads ? grad_expected_host[1] : 0.0f; pp.e2 = have_grads ? grad_expected_host[2] : 0.0f;
     pp.have_rows = have_grads ? 1 : 0;
     pp.B = (int)B; pp.A = (int)A; pp.R = (int)R; pp.Gmax = (int)Gmax; pp.h = h;

@@ -228,9 +228,12 @@ def detect_per_class_fused(classification, regression, anchors, score_threshold=
     boxes and the kept rows are decoded - from regression[B,A,12] (3D directional model: NMS on columns 16..19, 20-column
     rows out) or regression[B,A,4] (2D model: mean / std / optional clip as BBoxTransform + ClipBoxes).
     Same result, bit for bit, as decode -> detect_per_class.  Everything up to the assembly is ONE library call
-    (g3d_detect_tail: ~10 launches issued from C++); the assembly launch follows at once into buffers sized from an
-    estimate, and the single 8-byte device->host read comes last (_tail_run).  (Pipelining half-batches on two streams was tried: the sort / NMS chain is latency-bound per
-    segment, so halves take as long as the whole and the pipeline only adds host time - 0.66 ms vs 0.46 ms at B = 64.)
+    (g3d_detect_tail_short: score filter, one launch for gather + decode + sort + NMS of every segment, offsets - or the
+    general chain g3d_detect_tail when a segment is longer than 1024 candidates); the assembly launch follows at once into
+    buffers sized from an estimate, and the single 16-byte device->host read comes last (_tail_run).  (Pipelining image
+    groups over two streams - filter of group k+1 beside the segment kernel of group k - was tried twice, from Python and
+    from inside the library: the segment kernel is latency-bound per CTA and the filter's CTAs hold the SMs, so nothing
+    overlaps and every extra group costs its launches.)
     Returns (scores f32[K], classes i64[K], boxes f32[K,20|4], image_index i64[K])."""
     if (score_threshold is None) == (ladder_start is None):
         raise ValueError("give exactly one of score_threshold / ladder_start")

@@ -265,16 +265,29 @@ def other_workloads(dev, hbm_peak, rank, world):
     thr3 = torch.full((B3 * C_CLS,), 0.05, dtype=torch.float32, device=dev)
     t_filter = timed(lambda: ops.filter_compact(cls, B3, C_CLS, A, A * C_CLS, thr3, 16384), 10)
     filt_bytes = B3 * A * C_CLS * 4
+    # the device side of the tail alone (score filter + per-segment kernel + offsets; no assembly, no host read), on
+    # reused buffers as the PostProcess path runs it; and the general chain (gather -> sort -> greedy NMS launches)
+    plan = ops.detect_tail(cls, B3, C_CLS, A, A * C_CLS, thr3, 16384, anc, reg3, 0.5, short=True)
+    assert int(plan["summary"][2]) == 0, "config 3 must run on the short-segment path"
+    t_lib = timed(lambda: ops.detect_tail(cls, B3, C_CLS, A, A * C_CLS, thr3, 16384, anc, reg3, 0.5, short=True, reuse=plan), 10)
+    t_lib_general = timed(lambda: ops.detect_tail(cls, B3, C_CLS, A, A * C_CLS, thr3, 16384, anc, reg3, 0.5, short=False, reuse=plan), 10)
+    max_count = int(plan["count"].max())
+    del plan
     entry = {"workload": f"config 3: 3D decode + scores>0.05 + per-class NMS 0.5, batch {B3_total} at 1080p, ~5k pre-NMS boxes/img, "
                          f"{B3} images per GPU",
              "metric": "decode+NMS img/s", "value": B3_total / (t_fused * 1e-3), "unit": "img/s", "n_gpus": world,
-             "ms": {"filter->decode-on-the-fly->nms->assemble (PostProcess path)": t_fused, "compact8_kernel (score filter) alone": t_filter},
-             "detections_rank0": n_fused,
-             "note": "the fused tail reads the class scores once - that launch is the HBM-bound one; the sort / NMS chain "
-                     "behind it is latency-bound (SURVEY.md §8d)",
+             "ms": {"filter->decode-on-the-fly->nms->assemble (PostProcess path)": t_fused, "compact8_kernel (score filter) alone": t_filter,
+                    "g3d_detect_tail_short alone (filter + per-segment kernel + offsets, device side)": t_lib,
+                    "g3d_detect_tail alone (general chain: filter, gather, sort, greedy NMS, scan)": t_lib_general},
+             "detections_rank0": n_fused, "largest_segment_rank0": max_count,
+             "note": "the tail reads the class scores once - that launch (compact8_kernel) is the HBM-bound one; behind it ONE "
+                     "launch does gather + decode + sort + NMS per (image, class) segment in shared memory (tail_short_kernel, "
+                     "latency-bound: ~30 us per CTA, 1.7 waves of 1024-thread CTAs), then offsets and the assembly; the rest of "
+                     "the per-call time is the host: one 16-byte read-back and the Python between two calls",
              "roofline": {"kernel": "compact8_kernel", "bound": "hbm", "achieved": filt_bytes / (t_filter * 1e-3) / 1e9,
                           "peak": hbm_peak, "unit": "GB/s", "frac": filt_bytes / (t_filter * 1e-3) / 1e9 / hbm_peak,
-                          "share_of_tail": t_filter / t_fused, "latency_bound_rest_ms": t_fused - t_filter}}
+                          "share_of_tail": t_filter / t_fused, "segment_kernel_and_offsets_ms": t_lib - t_filter,
+                          "assembly_and_host_ms": t_fused - t_lib}}
     if rank == 0 and world == 1:
         t_dec = timed(lambda: ops.decode3d(anc, reg3), 5)
         dec_bytes = B3 * A * (48 + 80) + 16 * A
@@ -765,6 +778,30 @@ def run_ours(args):
             return l3
         line["anchor_centric_step_ms"] = _timed(step_plain, 5, dev)
         del anc_plain, o_gt, o_an, cp, rp
+        # opt-in FocalLoss(persistent_grad=True): gradient buffers and workspace kept from step to step, so the 48 B/anchor
+        # of zeros of the regression gradient are not written again (only the previous step's positive rows are cleared).
+        # Not the headline: it changes who owns the gradient tensors (see losses_impl.FocalLoss).  Same kernels as the
+        # module (forward-with-gradients + the backward's verification launch), bit-identical gradients (checked here).
+        pg = ops.PersistentGrads()
+        cdet, rdet = cls_d.detach(), reg_d.detach()
+
+        def step_keep():
+            f = ops.focal_loss_forward(cdet, rdet, anc, ann_d, want_assign=False, grad_expected=1.0, persistent=pg)
+            ops.focal_loss_backward(f, ones)
+            return f["losses"]
+        ms_keep, mode_keep, ms_keep_eager, _, _ = _time_loss_steps(step_keep, args.steps, args.warmup, 1, dev,
+                                                                   allow_graph=not args.no_graph)
+        fresh = ops.focal_loss_forward(cdet, rdet, anc, ann_d, want_assign=False, grad_expected=1.0)
+        ops.focal_loss_backward(fresh, ones)
+        same = bool(torch.equal(pg.bufs[0], fresh["dcls"]) and torch.equal(pg.bufs[1], fresh["dreg"]))
+        assert same, "persistent gradient buffers differ from freshly written ones"
+        keep_bytes = B * A * 64 + A * 16
+        line["persistent_grad"] = {"ms_per_step": ms_keep, "ms_per_step_eager": ms_keep_eager, "launch_mode": mode_keep,
+                                   "G_pairs_per_s": pairs_per_step / (ms_keep * 1e-3) / 1e9,
+                                   "gradients_equal_default_path": same,
+                                   "step_bytes": keep_bytes, "step_frac_of_hbm_peak": keep_bytes / (ms_keep * 1e-3) / 1e9 / hbm_peak,
+                                   "note": "FocalLoss(persistent_grad=True), opt-in: cls in + dcls out = 64 B per (image, anchor)"}
+        del pg, fresh, cdet, rdet
     del cls_d, reg_d
     torch.cuda.empty_cache()
     extras = None

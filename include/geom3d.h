@@ -106,6 +106,13 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *                           the first launch and after the prologue, the assignment, the resolve pass, the streaming
  *                           pass and the positives / reduction launch (per-kernel timing without a profiler;
  *                           bench.py's roofline figures come from these).
+ *                           dreg_state: G3D_DREG_UNDEFINED - dreg holds anything; all of it is written (the 48 B of
+ *                           zeros per non-positive row are 43 % of the bytes the step moves).  G3D_DREG_CLEAN - the
+ *                           caller keeps dreg AND the workspace from step to step and promises that dreg is what the
+ *                           previous g3d_focal_loss_fwd_bwd call on this workspace left in it (or all zeros, with a zeroed
+ *                           workspace, before the first step), and that no other call used the workspace in between:
+ *                           only that step's positive rows (~1 % of the rows) are zeroed again, nothing is filled.
+ *                           Same result.  (Honoured on the GT-centric path; the anchor-centric kernel writes every row.)
  * pyramid_host (nullable, host doubles): tells the call that `anchors` is the regular pyramid table of Anchors.forward
  *   (retinanet/anchors.py:21-40; g3d_generate_anchors): {L, S, L x (rows, cols, stride), L x S x (anchor width, height)},
  *   L <= 8 levels, S <= 16 shapes per cell, sum rows*cols*S == A.  With it (and Gmax <= 256) the assignment runs
@@ -115,6 +122,8 @@ int g3d_assign(const float* anchors, int64_t A, const float* gt_box, const int32
  *   itself, behind its instruction stream).
  */
 #define G3D_HYPER_COUNT 8
+#define G3D_DREG_UNDEFINED 0
+#define G3D_DREG_CLEAN 1
 int64_t g3d_focal_workspace_bytes(int64_t B, int64_t A, int64_t Gmax);
 int g3d_focal_loss_fwd(const float* cls, const float* reg, const float* anchors, const float* ann,
                        int64_t B, int64_t A, int64_t C, int64_t R, int64_t Gmax, int64_t W, int variant,
@@ -125,7 +134,7 @@ int g3d_focal_loss_fwd_bwd(const float* cls, const float* reg, const float* anch
                            const float* hyper_host, const float* grad_expected_host, float* losses, float* per_image,
                            int32_t* assign, int32_t* gt_count_out, double* shard_stats, float* dcls, float* dreg,
                            void* workspace, int64_t workspace_bytes, const double* pyramid_host,
-                           void* const* trace_events, int n_trace_events, int device, void* stream);
+                           void* const* trace_events, int n_trace_events, int dreg_state, int device, void* stream);
 
 /* backward of the above (autograd of the reference graph, same file:lines) for arbitrary upstream gradients.
  * grad_out[3] = upstream gradients of the three returned [1]-tensors (device memory); grad_scale[3] (nullable, device)

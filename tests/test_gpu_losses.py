@@ -673,3 +673,40 @@ def test_lazy_empty_check_retain_graph_and_inplace_detection():
     c2b.add_(1.0)
     with pytest.raises(RuntimeError, match="modified by an inplace operation"):
         sum(o.sum() for o in out).backward()
+
+
+@pytest.mark.parametrize("three_d", [True, False])
+def test_persistent_gradient_buffers_equal_fresh_ones_step_after_step(three_d):
+    """FocalLoss(persistent_grad=True): dreg is never filled, each step zeroes only the rows the previous step wrote
+    (g3d_focal_loss_fwd_bwd, dreg_state = G3D_DREG_CLEAN).  Over steps whose annotations - and so the positive rows -
+    change, with an image losing all its boxes, a forward-only call in between, a different upstream gradient and a change
+    of batch size, losses and both gradients must equal the default module's bit for bit"""
+    ops, li = _mods()
+    H, W, B = 96, 160, 3
+    anc = _tagged_anchors(H, W)
+    A = anc.shape[1]
+    keep, fresh = li.FocalLoss(persistent_grad=True), li.FocalLoss()
+    g = synth.gen(91)
+    for step in range(6):
+        Bs = B if step < 4 else B + 1                                   # a new shape: buffers are re-made
+        cls, reg = (t.cuda() for t in synth.head_outputs(Bs, A, 8, 12 if three_d else 4, g))
+        ann = (synth.gt_annotations_3d if three_d else synth.gt_annotations_2d)(Bs, 9, H, W, g, **synth.TINY).cuda()
+        if step == 2:
+            ann[1, :, 20 if three_d else 4] = -1                        # image 1 has no box this time
+        up = 1.0 if step != 3 else 0.37                                 # not the announced upstream gradient
+        outs = []
+        for mod in (keep, fresh):
+            c1, r1 = cls.clone().requires_grad_(True), reg.clone().requires_grad_(True)
+            losses = mod(c1, r1, anc, ann)
+            (sum(l.sum() for l in losses) * up).backward()
+            outs.append((torch.cat([l.detach() for l in losses]), c1.grad.clone(), r1.grad.clone()))
+        for a_, b_ in zip(*outs):
+            assert torch.equal(a_, b_), step
+        assert int((outs[0][2].abs().sum(-1) > 0).sum()) > 0
+        if step == 1:                                                   # validation in between: no gradient, own workspace
+            with torch.no_grad():
+                keep(cls, reg, anc, ann)
+    # the functional form with an explicit PersistentGrads; the returned gradients ARE its buffers
+    pg = ops.PersistentGrads()
+    fwd = ops.focal_loss_forward(cls, reg, anc, ann, want_assign=False, grad_expected=1.0, persistent=pg)
+    assert fwd["dreg"].data_ptr() == pg.bufs[1].data_ptr() and torch.equal(fwd["dreg"], outs[1][2])
