@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# stdout carries ONE JSON line: whatever NCCL prints (its version banner under NCCL_DEBUG) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
