@@ -160,23 +160,56 @@ __global__ void __launch_bounds__(128, 6) kf_predict_fid6_kernel(float* __restri
 // HSEL: H = [I_M | 0] (the measurement is the first M states - every tracker configuration of the reference): H P, P H^T and
 // K H are then sub-blocks of P and K; multiplying by the exact 0 / 1 entries gives the same floats, so the generic path and
 // this one agree bit for bit on finite inputs, with 60 fewer live registers.
+// m x m inverse by Gauss-Jordan on [A | I] with partial pivoting; arrays in local memory (the rare path of kf_update_kernel)
+__device__ __noinline__ void invert_with_exchanges(float (*A)[kKfMax], float (*Ai)[kKfMax], int m) {
+    for (int a = 0; a < m; ++a)
+        for (int b = 0; b < m; ++b) Ai[a][b] = (a == b) ? 1.0f : 0.0f;
+    for (int col = 0; col < m; ++col) {
+        int piv = col;
+        float best = fabsf(A[col][col]);
+        for (int r = col + 1; r < m; ++r)
+            if (fabsf(A[r][col]) > best) { best = fabsf(A[r][col]); piv = r; }
+        if (piv != col)
+            for (int c = 0; c < m; ++c) {
+                const float t = A[col][c]; A[col][c] = A[piv][c]; A[piv][c] = t;
+                const float u = Ai[col][c]; Ai[col][c] = Ai[piv][c]; Ai[piv][c] = u;
+            }
+        const float inv = 1.0f / A[col][col];
+        for (int c = 0; c < m; ++c) { A[col][c] *= inv; Ai[col][c] *= inv; }
+        for (int r = 0; r < m; ++r) {
+            if (r == col) continue;
+            const float f = A[r][col];
+            for (int c = 0; c < m; ++c) {
+                A[r][c] = fmaf(-f, A[col][c], A[r][c]);
+                Ai[r][c] = fmaf(-f, Ai[col][c], Ai[r][c]);
+            }
+        }
+    }
+}
+
 template <int S, int M, bool HSEL>
-__global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X, float* __restrict__ P,
+__global__ void __launch_bounds__(128, 5) kf_update_kernel(float* __restrict__ X, float* __restrict__ P,
                                                         const int64_t* __restrict__ rows, const double* __restrict__ z,
                                                         int64_t mcount, int s_rt, int m_rt, const KfModel mdl) {
     const int SS = (S > 0) ? S : s_rt, MM = (M > 0) ? M : m_rt;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < mcount; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = rows[j];
-        float Pm[kKfMax][kKfMax], x[kKfMax], HP[kKfMax][kKfMax], Sm[kKfMax][kKfMax], Si[kKfMax][kKfMax], y[kKfMax];
-        if (S == 6) {   // 144-byte rows: nine 16-byte loads per object instead of 36 scalar ones
+        float Pm[kKfMax][kKfMax], x[kKfMax], HP[kKfMax][kKfMax], Sm[kKfMax][kKfMax], y[kKfMax];
+        // 144-byte rows: nine 16-byte loads per object instead of 36 scalar ones.  `volatile` + memory clobber: the matrix is
+        // read TWICE (see below) and the second read must be a real load (L1 hit), not the first one's registers kept alive
+        auto load_P6 = [&]() {
             const float4* prow = reinterpret_cast<const float4*>(P + i * 36);
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
-                const float4 v = __ldg(prow + q);
+                float4 v;
+                asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(prow + q) : "memory");
                 const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) Pm[(4 * q + k) / 6][(4 * q + k) % 6] = e[k];
             }
+        };
+        if (S == 6) {
+            load_P6();
             const float2* xrow = reinterpret_cast<const float2*>(X + i * 6);
 #pragma unroll
             for (int q = 0; q < 3; ++q) { const float2 v = xrow[q]; x[2 * q] = v.x; x[2 * q + 1] = v.y; }
@@ -228,43 +261,58 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
                 }
                 Sm[a][b] = __fadd_rn(acc, mdl.R[a * MM + b]);
             }
-        // S^-1: Gauss-Jordan with partial pivoting (torch: LU with partial pivoting; both backward stable)
-#pragma unroll
-        for (int a = 0; a < kKfMax; ++a)
-#pragma unroll
-            for (int b = 0; b < kKfMax; ++b) Si[a][b] = (a == b) ? 1.0f : 0.0f;
+        // S^-1 by Gauss-Jordan (torch: LU with partial pivoting; both backward stable).  In place: once column `col` is
+        // eliminated it is a unit vector, and its storage takes column `col` of the inverse - 25 live values instead of the
+        // 50 of an augmented [S | I] (the same operations on the same numbers: a structural 1 times inv, a structural 0 in
+        // an FMA).  An innovation covariance is diagonally dominant and never asks for a row exchange; if one of its columns
+        // does (a larger entry below the pivot), the flag sends this object to the out-of-line pivoting version below.
+        bool exchange = false;
 #pragma unroll
         for (int col = 0; col < kKfMax; ++col) {
             if (col >= MM) continue;
-            int piv = col;
-            float best = fabsf(Sm[col][col]);
+            const float best = fabsf(Sm[col][col]);
 #pragma unroll
             for (int r = 0; r < kKfMax; ++r)
-                if (r > col && r < MM && fabsf(Sm[r][col]) > best) { best = fabsf(Sm[r][col]); piv = r; }
-            if (piv != col) {      // rare for an innovation covariance (diagonally dominant): a real branch, not 5 predicated swaps
-#pragma unroll
-                for (int r = 0; r < kKfMax; ++r) {
-                    if (r != piv || r == col) continue;
-#pragma unroll
-                    for (int c = 0; c < kKfMax; ++c) {
-                        const float t = Sm[col][c]; Sm[col][c] = Sm[r][c]; Sm[r][c] = t;
-                        const float u = Si[col][c]; Si[col][c] = Si[r][c]; Si[r][c] = u;
-                    }
-                }
-            }
+                if (r > col && r < MM && fabsf(Sm[r][col]) > best) exchange = true;
             const float inv = 1.0f / Sm[col][col];
+            Sm[col][col] = 1.0f;
 #pragma unroll
-            for (int c = 0; c < kKfMax; ++c) { Sm[col][c] *= inv; Si[col][c] *= inv; }
+            for (int c = 0; c < kKfMax; ++c) Sm[col][c] *= inv;
 #pragma unroll
             for (int r = 0; r < kKfMax; ++r) {
                 if (r == col || r >= MM) continue;
                 const float f = Sm[r][col];
+                Sm[r][col] = 0.0f;
 #pragma unroll
-                for (int c = 0; c < kKfMax; ++c) {
-                    Sm[r][c] = fmaf(-f, Sm[col][c], Sm[r][c]);
-                    Si[r][c] = fmaf(-f, Si[col][c], Si[r][c]);
-                }
+                for (int c = 0; c < kKfMax; ++c) Sm[r][c] = fmaf(-f, Sm[col][c], Sm[r][c]);
             }
+        }
+        // The covariance was only needed for S so far; holding its 36 floats through the elimination (50 more live values)
+        // is what pins the kernel at 128 registers.  It is read again here instead - the 144 bytes are still in L1.
+        if (S == 6) load_P6();
+        if (exchange) {                 // rare: S again from P, inverted with row exchanges, in local memory
+            float Sp[kKfMax][kKfMax], Sq[kKfMax][kKfMax];
+#pragma unroll
+            for (int a = 0; a < kKfMax; ++a)
+#pragma unroll
+                for (int b = 0; b < kKfMax; ++b) {
+                    if (a >= MM || b >= MM) { Sp[a][b] = 0.0f; continue; }
+                    float acc = 0.0f;
+                    if (HSEL) acc = Pm[a][b];
+                    else {
+                        for (int k2 = 0; k2 < SS; ++k2) {
+                            float hp = 0.0f;
+                            for (int k = 0; k < SS; ++k) hp = __fadd_rn(hp, __fmul_rn(mdl.H[a * SS + k], Pm[k][k2]));
+                            acc = __fadd_rn(acc, __fmul_rn(hp, mdl.H[b * SS + k2]));
+                        }
+                    }
+                    Sp[a][b] = __fadd_rn(acc, mdl.R[a * MM + b]);
+                }
+            invert_with_exchanges(Sp, Sq, MM);
+#pragma unroll
+            for (int a = 0; a < kKfMax; ++a)
+#pragma unroll
+                for (int b = 0; b < kKfMax; ++b) Sm[a][b] = Sq[a][b];
         }
         // Row by row (a full K and a full copy of the new P would cost 60 + 36 more live registers - the difference between
         // four and six CTAs per SM for this latency-bound kernel):  PHt_r = P_r H^T;  K_r = PHt_r S^-1;  x_r += K_r y;
@@ -290,7 +338,7 @@ __global__ void __launch_bounds__(128, 4) kf_update_kernel(float* __restrict__ X
                 if (a >= MM) continue;
                 float acc = 0.0f;
 #pragma unroll
-                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = fmaf(PHt[k], Si[k][a], acc);
+                for (int k = 0; k < kKfMax; ++k) if (k < MM) acc = fmaf(PHt[k], Sm[k][a], acc);
                 K[a] = acc;
             }
             {   // x += K y
@@ -386,7 +434,8 @@ extern "C" int g3d_kf_update(float* X, float* P, const int64_t* rows, const doub
     KfModel m;
     fill_model(m, nullptr, nullptr, H_host, R_host, mu_R_host, (int)S, (int)M);
     const int sms = sm_count(device);
-    const int grid = (int)(ceil_div(m_count, 128) < (int64_t)sms * 8 ? ceil_div(m_count, 128) : (int64_t)sms * 8);
+    // 5 CTAs of 128 threads are resident per SM (launch bounds): exactly one wave, every thread the same number of objects
+    const int grid = (int)(ceil_div(m_count, 128) < (int64_t)sms * 5 ? ceil_div(m_count, 128) : (int64_t)sms * 5);
     bool hsel = M <= S;                      // H == [I_M | 0] exactly?
     for (int64_t a = 0; a < M && hsel; ++a)
         for (int64_t k = 0; k < S; ++k)

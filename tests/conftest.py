@@ -49,6 +49,9 @@ def rel_err(a, b):
     return float(((a - b).abs() / b.abs().clamp(min=1e-30)).max()) if a.numel() else 0.0
 
 
+WORST_RELATIVE = []     # (worst un-floored relative error, tolerance, what, row_scale, elements above tol un-floored, elements)
+
+
 def assert_close_rel(a, b, tol, what="", row_scale=False):
     """|a-b| <= tol * max(|b|, scale), scale = mean |b| over the non-zero entries: element-wise relative error, except
     that entries far below the tensor's typical magnitude (sums with cancellation) are judged against that magnitude.
@@ -65,8 +68,32 @@ def assert_close_rel(a, b, tol, what="", row_scale=False):
     if row_scale and b.dim() > 1:
         mag = torch.nan_to_num(mag, nan=0.0).amax(dim=-1, keepdim=True).expand_as(b)
     bound = tol * torch.maximum(mag, torch.full_like(b, scale))
+    # un-floored figure for the report at the end of the run: the worst plain element-wise relative error |a-b| / |b|
+    # (no magnitude floor, no row scale) - what north_star's "1e-5 relative" means literally
+    finite = (b != 0) & ~torch.isnan(b) & ~torch.isnan(a)
+    if bool(finite.any()):
+        rel = ((a - b).abs()[finite] / b.abs()[finite])
+        WORST_RELATIVE.append((float(rel.max()), tol, what or "?", bool(row_scale), int((rel > tol).sum()), int(finite.sum())))
     bad = (a - b).abs() > bound
     nan_mismatch = torch.isnan(a) != torch.isnan(b)
     bad = (bad & ~torch.isnan(b)) | nan_mismatch
     assert not bool(bad.any()), (f"{what}: {int(bad.sum())} of {a.numel()} elements differ by more than {tol:g} relative; "
                                  f"worst |d|={float((a - b).abs()[~torch.isnan(a - b)].max()):.3e}")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """tolerance report: for every assert_close_rel comparison of the run, the worst plain relative error (no magnitude
+    floor, no row scaling) next to the tolerance the test applied with its floor - so the floors hide nothing"""
+    if not WORST_RELATIVE:
+        return
+    tr = terminalreporter
+    tr.write_sep("-", "assert_close_rel: worst un-floored element-wise relative errors")
+    agg = {}
+    for worst, tol, what, row_scale, above, n in WORST_RELATIVE:
+        k = (what, tol, row_scale)
+        w, a_, n_, c = agg.get(k, (0.0, 0, 0, 0))
+        agg[k] = (max(w, worst), a_ + above, n_ + n, c + 1)
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][0] / kv[0][1])[:12]
+    for (what, tol, row_scale), (worst, above, n, calls) in rows:
+        tr.write_line(f"  {what[:60]:60s} tol {tol:g}{' (row-scaled)' if row_scale else ''}: worst {worst:.3e}; "
+                      f"{above} of {n} elements above tol without the floor ({calls} comparisons)")

@@ -438,3 +438,31 @@ def test_short_tail_leaves_long_odd_and_pair_heavy_segments_to_the_general_chain
     anc, reg, mean, std = _boxes_as_anchors(few.float())
     pp.detect_per_class_fused(cls, reg, anc, score_threshold=1.0, mean=mean, std=std)
     assert pp._TAIL_GENERAL[key] == 0
+
+
+def test_decode2d_is_bit_identical_to_the_reference_arithmetic_on_cuda():
+    """retinanet/utils.py:102-126 evaluated by torch ON THE GPU (where the reference's model runs it): torch's CUDA `exp`
+    is the same libdevice expf the kernel calls, every other step is one IEEE operation in the same order - so the kernel's
+    boxes are bit-identical there.  (Against torch's CPU exp - the golden vectors - they differ by <= 1 ulp, which is why
+    those tests use 1e-6 and why an NMS keep list could only differ if an IoU sat within that distance of the threshold.)"""
+    _, pp = _mods()
+    g = synth.gen(5)
+    anc = synth.anchors(200, 328).cuda()
+    A = anc.shape[1]
+    reg = (torch.randn(3, A, 4, generator=g) * 0.7).cuda()
+    t = pp.BBoxTransform2D()
+    got = t(anc, reg)
+    mean, std = t.mean.cuda(), t.std.cuda()
+    boxes = anc
+    widths = boxes[:, :, 2] - boxes[:, :, 0]
+    heights = boxes[:, :, 3] - boxes[:, :, 1]
+    ctr_x = boxes[:, :, 0] + 0.5 * widths
+    ctr_y = boxes[:, :, 1] + 0.5 * heights
+    dx = reg[:, :, 0] * std[0] + mean[0]
+    dy = reg[:, :, 1] * std[1] + mean[1]
+    dw = reg[:, :, 2] * std[2] + mean[2]
+    dh = reg[:, :, 3] * std[3] + mean[3]
+    pcx, pcy = ctr_x + dx * widths, ctr_y + dy * heights
+    pw, ph = torch.exp(dw) * widths, torch.exp(dh) * heights
+    want = torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph], dim=2)
+    assert torch.equal(got, want)

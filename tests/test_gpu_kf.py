@@ -114,3 +114,35 @@ def test_kf_update_dense_measurement_matrix_vs_oracle(S, M):
     Xr, Pr = ko.update(X, P, rows, z, H, R, mu_R)
     assert_close_rel(Xd.cpu(), Xr, TOL, "X update (dense H)")
     assert_close_rel(Pd.cpu(), Pr, 5 * TOL, "P update (dense H)")
+
+
+@pytest.mark.parametrize("dense_h", [False, True])
+def test_kf_update_with_row_exchanges_vs_oracle(dense_h):
+    """the update kernel inverts the innovation covariance in place without row exchanges and sends an object whose
+    elimination would need one (a larger entry below a pivot) to an out-of-line pivoting inverse: covariances that are not
+    diagonally dominant - and not even symmetric - must still agree with the oracle's torch.inverse"""
+    from geom3d_b200 import ops
+    from oracle import kf_oracle as ko
+    g = synth.gen(808)
+    S, M, n = 6, 5, 2000
+    H = torch.zeros(M, S); H[:M, :M] = torch.eye(M)
+    if dense_h:
+        H = H + torch.randn(M, S, generator=g) * 0.2
+    R = torch.eye(M) * 0.05
+    mu_R = torch.zeros(M)
+    P = torch.randn(n, S, S, generator=g).float() * 2.0            # tiny diagonal against the off-diagonal entries
+    P[: n // 2] = P[: n // 2] + torch.eye(S) * 8.0                  # half of the objects stay on the in-place path
+    S_mat = H @ P @ H.t() + R
+    cond = torch.linalg.cond(S_mat.double())
+    keep = cond < 50                                                # well-conditioned systems only: parity is 1e-5
+    P, n = P[keep].contiguous(), int(keep.sum())
+    needs = (S_mat[keep].abs()[:, 1:, 0].max(dim=1).values > S_mat[keep].abs()[:, 0, 0])
+    assert int(needs.sum()) > 50 and int((~needs).sum()) > 50
+    X = torch.randn(n, S, generator=g) * 5
+    rows = torch.arange(n)
+    z = torch.randn(n, M, generator=g) * 5
+    Xd, Pd = X.cuda(), P.cuda()
+    ops.kf_update_(Xd, Pd, rows.cuda(), z.cuda(), H, R, mu_R)
+    Xr, Pr = ko.update(X, P, rows, z, H, R, mu_R)
+    assert_close_rel(Xd.cpu(), Xr, 20 * TOL, "X update (row exchanges)")
+    assert_close_rel(Pd.cpu(), Pr, 20 * TOL, "P update (row exchanges)")
