@@ -1,11 +1,15 @@
 // detect_tail.cu — the whole detection tail up to the one host decision, as ONE library call.
 //
 // ResNet.forward's post-processing (3D model.py:346-397, 2D retinanet/model.py:270-311) is, on this side: score filter ->
-// candidate gather with on-the-fly decode -> segmented sort + NMS -> offsets of the kept rows.  Each step is an entry
-// point of its own (filter.cu, nms.cu); issued from Python they cost ~10 us of host time apiece, which is what the
-// ~10 short launches of this latency-bound chain wait for.  g3d_detect_tail issues them back to back from C++ on the
-// caller's stream, carving its temporaries out of one caller-owned workspace, and leaves the two integers the host needs
-// (number of detections, largest candidate count) in `summary`.
+// candidates with their NMS boxes decoded on the fly -> per-(image, class) sort + NMS -> offsets of the kept rows.
+//   g3d_detect_tail_short  the usual case, segments of at most 1024 candidates: after the score filter (filter.cu) ONE
+//                          launch does everything else per segment in shared memory (tail_short_kernel, below), one more
+//                          the offsets and the summary - 4 launches per batch with the assembly;
+//   g3d_detect_tail        any segment length (up to 16 384 candidates, the 3D model's threshold ladder keeps 10 000
+//                          per class): the entry points of filter.cu / nms.cu issued back to back from C++ on the
+//                          caller's stream (~10 launches; from Python each would cost ~10 us of host time).
+// Both carve their temporaries out of one caller-owned workspace and leave the integers the host needs (number of
+// detections, largest candidate count, segments the short path left over) in `summary`.
 #include "box_decode.cuh"
 #include "nms_common.cuh"
 
