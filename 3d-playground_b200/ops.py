@@ -417,7 +417,8 @@ def ladder_rungs(start, factor=10 ** .2):
     if key not in _RUNG_CACHE:
         t, out = float(start), []
         while True:
-            f = np.float32(t)
+            with np.errstate(over="ignore"):          # the last rung overflows to +inf on purpose
+                f = np.float32(t)
             out.append(f)
             if np.isinf(f) or len(out) >= 512:
                 break
