@@ -53,36 +53,60 @@ class _PeerExchange:
     _cache = {}
 
     def __init__(self, group, dev):
+        self.group, self.dev = group, dev
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.buf = self.handle = None
+        self.peer_ptrs_dev = 0
+
+    def _allocate(self):
+        """local step (no communication): the symmetric buffer"""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        pg = group if group is not None else dist.group.WORLD
         n = int(_lib.lib().g3d_exchange_buffer_doubles(self.world))
-        self.buf = symm_mem.empty(n, dtype=torch.float64, device=dev)
+        self.buf = symm_mem.empty(n, dtype=torch.float64, device=self.dev)
         self.buf.zero_()
+
+    def _rendezvous(self):
+        """collective step: every rank of the group must call it"""
+        import torch.distributed._symmetric_memory as symm_mem
+        pg = self.group if self.group is not None else dist.group.WORLD
         self.handle = symm_mem.rendezvous(self.buf, pg)
         self.peer_ptrs_dev = int(self.handle.buffer_ptrs_dev)
-        torch.cuda.synchronize(dev)
-        dist.barrier(group=group)                      # every buffer is zero before anybody stores into it
 
     @classmethod
     def get(cls, group, dev):
-        """the exchange of (group, device), or None if it is disabled (G3D_PEER_EXCHANGE=0) or not available; all ranks
-        take the same branch"""
+        """the exchange of (group, device), or None if it is disabled (G3D_PEER_EXCHANGE=0) or not available.  All ranks
+        take the same branch: each step that can fail locally is followed by an all-reduce of the outcome, and the
+        collective rendezvous is only entered once every rank has its buffer."""
         import os
         key = (id(group), dev.index)
-        if key not in cls._cache:
-            ex, ok = None, 1
-            if os.environ.get("G3D_PEER_EXCHANGE", "1") == "0" or dev.type != "cuda":
-                ok = 0
-            else:
-                try:
-                    ex = cls(group, dev)
-                except Exception:   # noqa: BLE001 - no P2P / no symmetric memory on this system: use NCCL
-                    ok = 0
-            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        if key in cls._cache:
+            return cls._cache[key]
+
+        def everyone(ok):
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-            cls._cache[key] = ex if int(flag.item()) else None
+            return bool(int(flag.item()))
+
+        ex, ok = None, os.environ.get("G3D_PEER_EXCHANGE", "1") != "0" and dev.type == "cuda"
+        if ok:
+            try:
+                ex = cls(group, dev)
+                ex._allocate()
+            except Exception:   # noqa: BLE001 - no symmetric memory on this system: use NCCL
+                ok = False
+        if everyone(ok):
+            try:
+                ex._rendezvous()
+            except Exception:   # noqa: BLE001 - no peer access between these devices
+                ok = False
+            ok = everyone(ok)
+        else:
+            ok = False
+        if ok:
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)                  # every buffer is zero before anybody stores into it
+        cls._cache[key] = ex if ok else None
         return cls._cache[key]
 
 

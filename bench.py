@@ -25,8 +25,11 @@ import sys
 import threading
 import time
 
-# stdout carries ONE JSON line: whatever NCCL prints (its version banner under NCCL_DEBUG) goes to stderr
+# stdout carries ONE JSON line: whatever NCCL prints goes to stderr.  (NCCL honours NCCL_DEBUG_FILE only above the
+# VERSION level - at VERSION its banner goes to stdout - so VERSION is raised to WARN, which prints the same banner.)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
