@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) tail_summary_kernel(const int32_t* __rest
         summary[0] = out_offsets[S];
         summary[1] = m;
         summary[2] = 0;             // the general chain takes every segment
+        __threadfence_system();     // `summary` may be mapped host memory that the host polls: entry 3 is written last
         summary[3] = 0;
     }
 }
@@ -480,7 +481,9 @@ __global__ void __launch_bounds__(1024) tail_offsets_kernel(const int32_t* __res
         const int k = __reduce_add_sync(0xffffffffu, wskip[lane]);
         if (lane == 31) {
             out_offsets[S] = inc2;
-            summary[0] = inc2; summary[1] = m; summary[2] = k; summary[3] = 0;
+            summary[0] = inc2; summary[1] = m; summary[2] = k;
+            __threadfence_system();     // `summary` may be mapped host memory that the host polls: entry 3 is written last
+            summary[3] = 0;
         }
     }
     __syncthreads();

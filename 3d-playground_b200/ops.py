@@ -546,8 +546,9 @@ class TailPlan(dict):
         self.ptr = {k: _p(v) for k, v in self.items()}
         self.ws_ptr, self.ws_bytes, self.dev_idx = _p(self.ws), self.ws.numel(), _idx(dev)
 
-    def launch(self, short, scores, outer_pitch, thr, decode, iou_threshold, stream):
-        """the tail up to summary; `decode` = _decode_args(...) of the anchors / regression this tail decodes from"""
+    def launch(self, short, scores, outer_pitch, thr, decode, iou_threshold, stream, summary_ptr=None):
+        """the tail up to summary; `decode` = _decode_args(...) of the anchors / regression this tail decodes from;
+        summary_ptr: where the 4 summary integers go instead of self["summary"] (mapped pinned host memory, see the header)"""
         outer, inner, N, cap, _ = self.shape
         anc, reg, variant, mean_h, std_h, clip, cw, ch = decode
         q = self.ptr
@@ -555,8 +556,8 @@ class TailPlan(dict):
         fn = L.g3d_detect_tail_short if short else L.g3d_detect_tail
         check(fn(_p(scores), outer, inner, N, outer_pitch, _p(thr), cap, _p(anc), anc.shape[0], _p(reg), variant,
                  mean_h, std_h, clip, cw, ch, float(iou_threshold), q["count"], q["seg_offsets"], q["cand_scores"],
-                 q["cand_src"], q["keep"], q["keep_count"], q["out_offsets"], q["summary"], self.ws_ptr, self.ws_bytes,
-                 self.dev_idx, stream), "g3d_detect_tail_short" if short else "g3d_detect_tail")
+                 q["cand_src"], q["keep"], q["keep_count"], q["out_offsets"], q["summary"] if summary_ptr is None else summary_ptr,
+                 self.ws_ptr, self.ws_bytes, self.dev_idx, stream), "g3d_detect_tail_short" if short else "g3d_detect_tail")
 
     def assemble(self, rows, decode, stream):
         """(scores f32[rows], classes i64[rows], boxes f32[rows,20|4], image i64[rows]) of the kept candidates"""

@@ -6,7 +6,10 @@ Reference call sites:
   2D copy  retinanet/utils.py:82-144, retinanet/model.py:270-311
   NMS      torchvision.ops.nms at all the sites listed in include/geom3d.h (a11)
 """
+import ctypes
+import os
 import threading
+import time
 
 import numpy as np
 import torch
@@ -160,7 +163,8 @@ def _tail_run(cls, regression, anchors, score_threshold, ladder_start, keep_max,
     library call; the assembly launch follows immediately into output buffers sized from an estimate (twice the largest
     result seen for this shape), so the GPU does not idle while the host learns the number of detections; only then the
     integers the host needs (detections, largest candidate count, segments left over) are read, through pinned memory.
-    A result larger than the estimate is assembled again at its exact size.
+    A result larger than the estimate is assembled again at its exact size.  (The call returns as soon as the counts are
+    known; the assembly launch may still be running - on the caller's stream, like any other asynchronous torch op.)
 
     The library call is g3d_detect_tail_short - one launch for gather + decode + sort + NMS - as long as the segments are
     short (<= 1024 candidates; what scores > 0.05 leaves per class of an image); if it reports segments it did not take,
@@ -180,12 +184,18 @@ def _tail_run(cls, regression, anchors, score_threshold, ladder_start, keep_max,
     rows_key = (dev.index, B * C)
     guess = _TAIL_ROWS.get(rows_key, 4096 * B)
     stream = torch.cuda.current_stream(dev)
-    key = (dev.index, stream.cuda_stream)
-    if key not in _TAIL_HOST:                                # one pinned block + event per stream, reused (each call
-        _TAIL_HOST[key] = (torch.empty(4, dtype=torch.int32).pin_memory(), torch.cuda.Event())   # ends with its own wait)
-    host, done = _TAIL_HOST[key]
+    bkey = (dev.index, stream.cuda_stream, threading.get_ident())
+    if bkey not in _TAIL_HOST:       # one pinned block (+ event) per stream and host thread, reused: each call ends with its own wait
+        if len(_TAIL_HOST) >= 64:
+            _TAIL_HOST.clear()
+        pinned = torch.empty(4, dtype=torch.int32).pin_memory()
+        _TAIL_HOST[bkey] = (pinned, pinned.numpy(), ctypes.c_void_p(pinned.data_ptr()), torch.cuda.Event())
+    host, host_np, host_ptr, done = _TAIL_HOST[bkey]
+    # The kernels write the summary straight into the pinned block (mapped host memory, entry 3 last behind a system
+    # fence) and the host polls it: no copy, no event, and the host moves on while the assembly launch is still running.
+    # G3D_TAIL_MAPPED=0: device buffer + asynchronous copy + event instead.
+    mapped = os.environ.get("G3D_TAIL_MAPPED", "1") != "0"
 
-    bkey = key + (threading.get_ident(),)
     decode = ops._decode_args(anchors, regression, mean, std, clip_wh)     # validated once, shared by both launches
     plan = _TAIL_BUFS.get(bkey)
     if plan is None or plan.shape != (B, C, A, cap, dev):
@@ -197,12 +207,28 @@ def _tail_run(cls, regression, anchors, score_threshold, ladder_start, keep_max,
     sptr = ops._stream(dev)
 
     def run(short):
-        plan.launch(short, cls, A * C, thr, decode, iou_threshold, sptr)
-        out = plan.assemble(guess, decode, sptr)
-        host.copy_(plan["summary"], non_blocking=True)
-        done.record(stream)
-        done.synchronize()
-        K, most, left, _ = host.tolist()
+        if mapped:
+            host_np[3] = -1
+            plan.launch(short, cls, A * C, thr, decode, iou_threshold, sptr, summary_ptr=host_ptr)
+            out = plan.assemble(guess, decode, sptr)
+            spins, t_first = 0, None
+            while host_np[3] < 0:
+                spins += 1
+                if not spins & 255:
+                    time.sleep(0)                      # let other host threads run
+                    t_first = t_first or time.monotonic()
+                    if time.monotonic() - t_first > 20.0:        # a failed launch never writes the flag
+                        torch.cuda.synchronize(dev)              # (raises the CUDA error, if there is one)
+                        if host_np[3] < 0:
+                            raise Geom3dError("detection tail: the summary was never written")
+            K, most, left = int(host_np[0]), int(host_np[1]), int(host_np[2])
+        else:
+            plan.launch(short, cls, A * C, thr, decode, iou_threshold, sptr)
+            out = plan.assemble(guess, decode, sptr)
+            host.copy_(plan["summary"], non_blocking=True)
+            done.record(stream)
+            done.synchronize()
+            K, most, left, _ = host.tolist()
         if most > cap:
             raise Geom3dError(f"a (image, class) segment has {most} candidates above the score threshold but the candidate "
                               f"capacity is {cap}; pass a larger `cap` (<= 16384) or raise the threshold")

@@ -265,7 +265,8 @@ int g3d_exclusive_scan_i32(const int32_t* count, int64_t S, int32_t* offsets, in
  *   S = outer*inner segments, thr[S] on the device.  Outputs as the individual entry points define them: count[S],
  *   seg_offsets[S+1], cand_scores[S*cap], cand_src[S*cap], keep[S*cap], keep_count[S], out_offsets[S+1]; summary[4] =
  *   {number of detections = out_offsets[S], max count[s], 0, 0} for the ONE device->host read the caller needs before
- *   g3d_assemble_detections.  workspace: g3d_detect_tail_workspace_bytes(S, cap) bytes, 256-byte aligned. */
+ *   g3d_assemble_detections.  `summary` may also be mapped pinned host memory: entry 3 is written last, after a system-wide
+ *   fence, so a host that set it to a negative value beforehand can poll it and then read entries 0..2 (no copy, no event).  workspace: g3d_detect_tail_workspace_bytes(S, cap) bytes, 256-byte aligned. */
 int64_t g3d_detect_tail_workspace_bytes(int64_t S, int64_t cap);
 int g3d_detect_tail(const float* scores, int64_t outer, int64_t inner, int64_t N, int64_t outer_pitch, const float* thr,
                     int64_t cap, const float* anchors, int64_t Ba, const float* reg, int variant,
