@@ -116,10 +116,10 @@ __device__ __forceinline__ int cell_coord(float v, float lo, float scale) {
 // wider ones through shared memory (two buffers alternate, one barrier per step).
 __device__ __forceinline__ uint64_t sort1024(uint64_t key, uint64_t (*buf)[kShortCap], int tid) {
     int flip = 0;
-#pragma unroll 1
+#pragma unroll
     for (int k = 2; k <= kShortCap; k <<= 1) {
         const bool up = (tid & k) == 0;
-#pragma unroll 1
+#pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             uint64_t other;
             if (j >= 32) {
