@@ -466,3 +466,41 @@ def test_decode2d_is_bit_identical_to_the_reference_arithmetic_on_cuda():
     pw, ph = torch.exp(dw) * widths, torch.exp(dh) * heights
     want = torch.stack([pcx - 0.5 * pw, pcy - 0.5 * ph, pcx + 0.5 * pw, pcy + 0.5 * ph], dim=2)
     assert torch.equal(got, want)
+
+
+def test_detection_tail_from_four_host_threads():
+    """the tail keeps its intermediates, its pinned summary block and its hints per (device, stream, host thread): four
+    threads running different batches at the same time (DataParallel-style) each get their own, correct, detections"""
+    import threading
+    _, pp = _mods()
+    H, W = 128, 160
+    anc = synth.anchors(H, W).cuda()
+    A = anc.shape[1]
+    jobs = []
+    for k in range(4):
+        g = synth.gen(900 + k)
+        cls = synth.detection_scores(2 + k % 2, A, 8, g, objects=10 + 3 * k, per_object=9).cuda()
+        reg = (torch.randn(cls.shape[0], A, 12, generator=g) * 0.1).cuda()
+        reg[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5]).cuda() + torch.randn(cls.shape[0], A, 4, generator=g).cuda() * 0.05
+        jobs.append((cls, reg, pp.detect_per_class_fused(cls, reg, anc, score_threshold=0.05)))
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(k):
+        try:
+            cls, reg, want = jobs[k]
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(25):
+                    got = pp.detect_per_class_fused(cls, reg, anc, score_threshold=0.05)
+                    stream.synchronize()
+                    for a_, b_ in zip(got, want):
+                        assert torch.equal(a_, b_)
+        except Exception as e:   # noqa: BLE001
+            errors.append((k, repr(e)))
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
