@@ -1004,7 +1004,7 @@ __global__ void __launch_bounds__(kTile, 4) focal_stream8_kernel(const __grid_co
 #pragma unroll
         for (int e = 0; e < 8; ++e) { cur[e] = 0.0f; nxt[e] = 0.0f; }
         if (a < p.A) {
-            ld_row8(cp, cur);
+            ld_row8<!GRAD>(cp, cur);
             if (KEYS) { if (m8 & 1u) raw = __ldg(p.src.keys + kbase + a); }
             else raw = __ldg(p.src.code8 + kbase + a);
         }
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(kTile, 4) focal_stream8_kernel(const __grid_co
             const bool valid = a < p.A;
             nraw = 0u;
             if (c + 1 < nchunks && a + 32 < p.A) {
-                ld_row8(cp + 32 * 8, nxt);
+                ld_row8<!GRAD>(cp + 32 * 8, nxt);
                 if (KEYS) { if ((m8 >> (c + 1)) & 1u) nraw = __ldg(p.src.keys + kbase + a + 32); }
                 else nraw = __ldg(p.src.code8 + kbase + a + 32);
             }

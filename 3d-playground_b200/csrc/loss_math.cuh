@@ -305,10 +305,22 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
 // ---------------------------------------------------------------------------------------------------------------
 // 256-bit global accesses (one 8-class row per lane) and the bulk-copy (TMA) zero fill
 // ---------------------------------------------------------------------------------------------------------------
+// EVICT_FIRST: the row is marked evict-first in L2.  Measured at cfg2 (A/B in one session): it helps the read-only
+// forward pass (170 -> 164 us) and hurts the pass that also writes gradients (240 -> 250 us; so do evict-first hints
+// on the gradient stores and on the bulk zero fill: +4 us each), hence a template switch.
+template <bool EVICT_FIRST>
 __device__ __forceinline__ void ld_row8(const float* p, float (&v)[8]) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
+    if (EVICT_FIRST) {
+        unsigned long long policy;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p), "l"(policy));
+    } else {
+        asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                     : "l"(p));
+    }
 }
 __device__ __forceinline__ void st_row8(float* p, const float (&v)[8]) {
     asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]),
