@@ -265,7 +265,7 @@ def other_workloads(dev, hbm_peak, rank, world):
     reg3 = torch.randn(B3, A, 12, device=dev) * 0.1
     reg3[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5], device=dev) + torch.randn(B3, A, 4, device=dev) * 0.05
     # the path PostProcess3D takes: filter first, decode only the candidates / kept rows (no [B,A,20] tensor)
-    t_fused = _max_over_ranks(timed(lambda: postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05), 5, warm=2), world, dev)
+    t_fused = _max_over_ranks(timed(lambda: postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05), 20, warm=3), world, dev)
     n_fused = postprocess.detect_per_class_fused(cls, reg3, anc, score_threshold=0.05)[0].numel()
     # its HBM-bound launch on its own (compact8_kernel: every class score read once), and the stand-alone decode
     thr3 = torch.full((B3 * C_CLS,), 0.05, dtype=torch.float32, device=dev)
