@@ -504,3 +504,21 @@ def test_detection_tail_from_four_host_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_tail_summary_by_copy_and_event_equals_mapped_polling(monkeypatch):
+    """G3D_TAIL_MAPPED=0: the summary travels by asynchronous copy + event instead of mapped pinned memory - same detections"""
+    _, pp = _mods()
+    g = synth.gen(31)
+    H, W = 128, 160
+    anc = synth.anchors(H, W).cuda()
+    A = anc.shape[1]
+    cls = synth.detection_scores(3, A, 8, g, objects=12, per_object=9).cuda()
+    reg = (torch.randn(3, A, 12, generator=g) * 0.1).cuda()
+    reg[..., 8:12] = torch.tensor([-0.5, -0.5, 0.5, 0.5]).cuda() + torch.randn(3, A, 4, generator=g).cuda() * 0.05
+    want = pp.detect_per_class_fused(cls, reg, anc, score_threshold=0.05)
+    monkeypatch.setenv("G3D_TAIL_MAPPED", "0")
+    got = pp.detect_per_class_fused(cls, reg, anc, score_threshold=0.05)
+    assert want[0].numel() > 0
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_, b_)
